@@ -1,0 +1,265 @@
+/* include/ptb.h -- C ABI of the B200-native path-tracing core ("ptb").
+ *
+ * Drop-in boundary for the render path of safardani/szakdolgozat-pathtracer.
+ * The reference has no plugin/FFI interface: its integrator sits behind the
+ * OptiX host API as called from main() (optixSphere.cpp:754-1538).  Each entry
+ * point below replaces one group of those calls and cites it.  Plain pointers
+ * and sizes only; no CUDA, OptiX or torch types appear in the signatures
+ * (streams are passed as void* = cudaStream_t).
+ *
+ * Conventions
+ *  - every function returns PTB_OK (0) or a PTB_ERR_* code; the message is
+ *    available from ptb_last_error() (thread-local).  The reference throws
+ *    from CUDA_CHECK/OPTIX_CHECK and exits 1 (optixSphere.cpp:1532-1537).
+ *  - one context is used from one host thread at a time, like the reference's
+ *    single-threaded render loop (optixSphere.cpp:1390-1437).
+ *  - ptb_launch() is asynchronous on the given stream, like optixLaunch.
+ *  - there is NO CPU fallback: every compute entry point fails with
+ *    PTB_ERR_NO_DEVICE when no CUDA device is usable.
+ */
+#ifndef PTB_H
+#define PTB_H
+#include <stddef.h>
+#include <stdint.h>
+#ifndef __cplusplus
+#include <stdbool.h>
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PTB_OK 0
+#define PTB_ERR_INVALID 1
+#define PTB_ERR_IO 2
+#define PTB_ERR_CUDA 3
+#define PTB_ERR_UNSUPPORTED 4
+#define PTB_ERR_NO_DEVICE 5
+
+/* ---- data layouts shared with the reference (optixSphere.h) ---------------
+ * Layout-identical to the CUDA vector types the reference uses; the sizes and
+ * offsets are pinned by tests against oracle/_ref/ref_probe. */
+typedef struct ptb_float2 { float x, y; } ptb_float2;
+typedef struct ptb_float3 { float x, y, z; } ptb_float3;
+#if defined(__cplusplus)
+typedef struct alignas(16) ptb_float4 { float x, y, z, w; } ptb_float4;
+typedef struct alignas(4) ptb_uchar4 { unsigned char x, y, z, w; } ptb_uchar4;
+#else
+typedef struct ptb_float4 { _Alignas(16) float x; float y, z, w; } ptb_float4;
+typedef struct ptb_uchar4 { _Alignas(4) unsigned char x; unsigned char y, z, w; } ptb_uchar4;
+#endif
+
+/* optixSphere.h:2-7 (128 bytes) */
+typedef struct ptb_TriangleData {
+    ptb_float4 v0, v1, v2, n0, n1, n2;
+    ptb_float2 uv0, uv1, uv2;
+} ptb_TriangleData;
+
+/* optixSphere.h:10-31 (120 bytes).  frame_buffer / accum_buffer are DEVICE
+ * pointers owned by the caller (or by a ptb_output); handle comes from
+ * ptb_accel_build(). */
+typedef struct ptb_Params {
+    unsigned int image_width;
+    unsigned int image_height;
+    int origin_x;
+    int origin_y;
+    int subframe_index;
+    ptb_uchar4* frame_buffer;
+    ptb_float4* accum_buffer;
+    bool dof;
+    ptb_float3 eye, U, V, W;
+    ptb_TriangleData* triangles; /* unused by the reference's device code */
+    unsigned int num_triangles;  /* unused by the reference's device code */
+    unsigned long long handle;   /* OptixTraversableHandle in the reference */
+} ptb_Params;
+
+/* optixSphere.h:58-63 */
+typedef struct ptb_MissData {
+    ptb_float4* hdr_image_data;
+    int width, height;
+} ptb_MissData;
+
+/* optixSphere.h:67-102 (168 bytes).  In ptb_scene_set_materials() the texture
+ * pointers are HOST pointers to float4 texels (the reference's upload format,
+ * optixSphere.cpp:364-380); texcoords/vertices/normals are ignored (the scene
+ * owns the geometry). */
+typedef struct ptb_HitGroupData {
+    ptb_float4* albedo_texture_data; int tex_width, tex_height; bool has_texture;
+    ptb_float4* roughness_texture_data; int roughness_width, roughness_height; bool has_roughness_map;
+    ptb_float4* normal_texture_data; int normal_width, normal_height; bool has_normal_map;
+    ptb_float4* metallic_texture_data; int metallic_width, metallic_height; bool has_metallic_map;
+    ptb_float2* texcoords;
+    ptb_float4* vertices;
+    ptb_float4* normals;
+    ptb_float3 emission_color, diffuse_color, specular;
+    float roughness;
+    bool metallic;
+    bool transparent;
+} ptb_HitGroupData;
+
+/* ---- opaque objects ---------------------------------------------------------- */
+typedef struct ptb_context ptb_context;
+typedef struct ptb_scene ptb_scene;
+typedef struct ptb_output ptb_output;
+
+/* ---- render configuration: the reference's compile-time literals ------------ */
+typedef struct ptb_render_cfg {
+    int32_t spp_per_launch;   /* optixSphere.cu:323   sample_batch_count = 10 */
+    int32_t max_depth;        /* optixSphere.cu:360   payload.depth = 20 */
+    float tmin, tmax;         /* optixSphere.cu:368-369   0.01, 1e16 */
+    float dof_blur;           /* optixSphere.cu:285   0.01 */
+    float focus_dist;         /* optixSphere.cu:329   1.0 */
+    float nmap_strength;      /* optixSphere.cu:697   0.4 */
+    float exposure;           /* optixSphere.cu:412   -0.5 */
+    float gamma;              /* optixSphere.cu:425   2.2 */
+    float contrast;           /* optixSphere.cu:432   1.25 */
+    int32_t accumulate_mode;  /* 0: running average by subframe_index (optixSphere.cu:403-409);
+                                 1: accum += launch mean (sample-split multi-GPU; resolve with ptb_resolve) */
+    int32_t write_frame;      /* 1: tonemap into Params.frame_buffer (optixSphere.cu:411-435); 0: skip */
+    int32_t env_importance_sampling; /* 0 = reference estimator (BSDF sampling only).  Reserved. */
+    int32_t count_traversal;  /* 1: also count BVH nodes visited / triangles tested (slower) */
+    int32_t* aux_primary_hit; /* optional DEVICE int32[W*H]: primitive hit by the first segment of sample 0, -1 = miss */
+} ptb_render_cfg;
+
+typedef struct ptb_launch_stats {
+    uint64_t segments;     /* closest-hit ray casts = traceRadiance calls (optixSphere.cu:364) */
+    uint64_t paths;        /* camera samples started */
+    uint64_t hits, misses;
+    uint64_t nodes_visited, tris_tested; /* only when count_traversal */
+    uint32_t iterations;   /* wavefront iterations executed */
+    uint32_t kernel_launches;
+} ptb_launch_stats;
+
+typedef struct ptb_build_cfg {
+    int32_t max_leaf_size; /* triangles per leaf after refinement (1..8), default 4 */
+    int32_t sah_refine;    /* 1: binned-SAH refinement of the LBVH (default); 0: plain LBVH */
+    int32_t sah_bins;      /* default 16 */
+    int32_t treelet_size;  /* primitives per refinement treelet, default 512 */
+} ptb_build_cfg;
+
+typedef struct ptb_build_stats {
+    uint32_t num_triangles, num_nodes, num_leaves, max_depth;
+    float sah_cost;        /* sum(area*cost)/root area, Ct=1 Ci=1 */
+    float build_ms;        /* device time of the build (CUDA events) */
+    uint64_t bvh_bytes;
+} ptb_build_stats;
+
+typedef struct ptb_material_info {
+    float emission_color[3], diffuse_color[3], specular[3];
+    float roughness;
+    int32_t metallic, transparent;
+    int32_t has_albedo, albedo_w, albedo_h;
+    int32_t has_roughness, roughness_w, roughness_h;
+    int32_t has_normal, normal_w, normal_h;
+    int32_t has_metallic, metallic_w, metallic_h;
+} ptb_material_info;
+
+/* ---- errors -------------------------------------------------------------------- */
+const char* ptb_last_error(void);
+const char* ptb_version(void);
+
+/* ---- context: optixInit / optixDeviceContextCreate (optixSphere.cpp:798-812),
+ *      optixDeviceContextDestroy (optixSphere.cpp:1529) ------------------------- */
+int ptb_context_create(int device, ptb_context** out);
+void ptb_context_destroy(ptb_context* ctx);
+int ptb_context_synchronize(ptb_context* ctx, void* stream);
+
+/* ---- scene load: createSceneGeometry(files, scale) + flatten
+ *      (optixSphere.cpp:400-649, 845-858).  Host-only; needs no device.
+ *      Materials follow the <stem>_{albedo,roughness,normal,metallic}.png
+ *      convention (optixSphere.cpp:522-546); untextured files get a random
+ *      material drawn from std::mt19937(material_seed) (the reference seeds it
+ *      from std::random_device, optixSphere.cpp:141-148).  A 2-triangle floor is
+ *      appended at the lowest vertex (optixSphere.cpp:598-646). */
+int ptb_scene_load_obj(const char* const* files, int n_files, float scale, uint32_t material_seed, ptb_scene** out);
+/* raw variant: triangles as the reference holds them before flattening */
+int ptb_scene_create(const ptb_TriangleData* tris, uint32_t n_tris, const uint32_t* mat_ids, ptb_scene** out);
+/* hit-group table: optixSphere.cpp:1196-1261 */
+int ptb_scene_set_materials(ptb_scene* scene, const ptb_HitGroupData* mats, int n);
+/* environment: sutil::loadImage(exr) + MissData (optixSphere.cpp:835-836, 1161-1188) */
+int ptb_scene_set_env_file(ptb_scene* scene, const char* path);
+int ptb_scene_set_env_pixels(ptb_scene* scene, const float* rgba, int w, int h);
+void ptb_scene_destroy(ptb_scene* scene);
+
+/* host-side read-back (parity tests, tools) */
+uint32_t ptb_scene_num_triangles(const ptb_scene* scene);
+int ptb_scene_num_materials(const ptb_scene* scene);
+int ptb_scene_copy_triangles(const ptb_scene* scene, ptb_TriangleData* out, uint32_t cap);
+int ptb_scene_copy_material_ids(const ptb_scene* scene, uint32_t* out, uint32_t cap);
+int ptb_scene_get_material(const ptb_scene* scene, int index, ptb_material_info* out);
+/* kind: 0 albedo, 1 roughness, 2 normal, 3 metallic; out = w*h*4 floats (texel = byte/255.0f) */
+int ptb_scene_copy_texture(const ptb_scene* scene, int material, int kind, float* out_rgba, size_t cap_floats);
+int ptb_scene_env_size(const ptb_scene* scene, int* w, int* h);
+int ptb_scene_copy_env(const ptb_scene* scene, float* out_rgba, size_t cap_floats);
+
+/* ---- acceleration structure: optixAccelComputeMemoryUsage / optixAccelBuild /
+ *      optixAccelCompact (optixSphere.cpp:860-968).  Uploads the scene to the
+ *      context's device and builds the BVH there (LBVH from Morton codes, then
+ *      binned-SAH refinement).  The handle goes into Params.handle. */
+void ptb_default_build_cfg(ptb_build_cfg* cfg);
+int ptb_accel_build(ptb_context* ctx, ptb_scene* scene, const ptb_build_cfg* cfg, void* stream,
+                    unsigned long long* handle, ptb_build_stats* stats);
+/* copies the flattened BVH back: nodes = 16 floats per node (64 B), tris = 12 floats per leaf-ordered triangle */
+int ptb_accel_read(ptb_context* ctx, unsigned long long handle, float* nodes, uint32_t cap_nodes,
+                   float* tris, uint32_t cap_tris, uint32_t* n_nodes, uint32_t* n_tris);
+
+/* ---- camera: sutil::Camera::UVWFrame as used by handleCameraUpdate /
+ *      configureCamera (optixSphere.cpp:102-120, 238-247) ---------------------- */
+void ptb_camera_uvw(const float eye[3], const float lookat[3], const float up[3], float fovy_deg, float aspect,
+                    float U[3], float V[3], float W[3]);
+/* fills eye/U/V/W with the reference camera: eye (0,2,6) -> (0,0,0), up +Y, fovY 50 */
+void ptb_params_default_camera(ptb_Params* params);
+
+/* ---- launch: Params upload + optixLaunch(pipeline, stream, d_param, sizeof(Params),
+ *      &sbt, width, height, 1) (optixSphere.cpp:1403-1418, 1470-1479) ---------- */
+void ptb_default_render_cfg(ptb_render_cfg* cfg);
+int ptb_launch(ptb_context* ctx, const ptb_Params* params, const ptb_render_cfg* cfg, void* stream);
+/* synchronises the stream of the last launch and returns its counters */
+int ptb_launch_get_stats(ptb_context* ctx, ptb_launch_stats* out);
+/* accumulate/tonemap stage on its own (optixSphere.cu:401-435): frame = tonemap(accum * scale).
+ * Used after a multi-GPU reduce of sum-mode accumulators. */
+int ptb_resolve(ptb_context* ctx, const ptb_float4* accum, ptb_float4* accum_out, ptb_uchar4* frame, uint32_t n_pixels,
+                float scale, const ptb_render_cfg* cfg, void* stream);
+/* batch closest-hit query on the built BVH (device arrays of float3 / outputs) */
+int ptb_trace_rays(ptb_context* ctx, unsigned long long handle, const float* d_origins, const float* d_dirs, uint32_t n,
+                   float tmin, float tmax, int32_t* d_prim, float* d_t, float* d_b1, float* d_b2, void* stream);
+
+/* ---- output buffer: sutil::CUDAOutputBuffer<uchar4> (optixSphere.cpp:1284,
+ *      1376-1382, 1401, 1419, 1484-1486, 256) ----------------------------------- */
+int ptb_output_create(ptb_context* ctx, uint32_t width, uint32_t height, ptb_output** out);
+int ptb_output_resize(ptb_output* ob, uint32_t width, uint32_t height);
+ptb_uchar4* ptb_output_map(ptb_output* ob);       /* device pointer */
+void ptb_output_unmap(ptb_output* ob, void* stream);
+const ptb_uchar4* ptb_output_host_ptr(ptb_output* ob); /* device->host copy, then host pointer */
+uint32_t ptb_output_width(const ptb_output* ob);
+uint32_t ptb_output_height(const ptb_output* ob);
+void ptb_output_destroy(ptb_output* ob);
+
+/* ---- device memory helpers (the reference calls cudaMalloc/cudaMemcpy directly,
+ *      e.g. accum buffer optixSphere.cpp:1298-1301) ------------------------------ */
+int ptb_device_alloc(ptb_context* ctx, size_t bytes, void** out);
+int ptb_device_free(ptb_context* ctx, void* p);
+int ptb_device_memset(ptb_context* ctx, void* p, int value, size_t bytes, void* stream);
+int ptb_copy_to_device(ptb_context* ctx, void* dst, const void* src, size_t bytes, void* stream);
+int ptb_copy_to_host(ptb_context* ctx, void* dst, const void* src, size_t bytes, void* stream);
+
+/* ---- image files: sutil::loadImage / sutil::saveImage (optixSphere.cpp:359, 836,
+ *      1483-1489).  PNG (8/16-bit gray, gray+alpha, RGB, RGBA, palette) -> RGBA8 with
+ *      stb_image STBI_rgb_alpha semantics; EXR scanline NONE/ZIPS/ZIP, HALF/FLOAT
+ *      -> float4 (missing A = 1).  Buffers are released with ptb_free(). */
+int ptb_image_load_rgba8(const char* path, uint8_t** pixels, int* w, int* h);
+int ptb_image_load_float4(const char* path, float** pixels, int* w, int* h);
+/* .png or .ppm by extension; rows are written bottom-up (row 0 of the frame buffer is
+ * the bottom image row, optixSphere.cu:332,400) when flip_y != 0 */
+int ptb_save_image(const char* path, const ptb_uchar4* pixels, int w, int h, int flip_y);
+void ptb_free(void* p);
+
+/* ---- device self-test hooks used by the parity tests --------------------------- */
+/* op: 0 rng (in: seed as uint bits -> out: next seed bits, u), 1 sincos (x -> s, c),
+ *     2 atan2 (y, x -> r), 3 asin (x -> r).  in/out are HOST arrays. */
+int ptb_test_device_math(ptb_context* ctx, int op, const float* in, int in_stride, float* out, int out_stride, uint32_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTB_H */

@@ -1,0 +1,518 @@
+// oracle/oracle_pt.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// CPU oracle: a scalar host C++ restatement of the reference integrator
+// /root/reference/optixSphere.cu (raygen cu:297-436, closest hit cu:616-872
+// live part, miss cu:531-567, helpers cu:24-61,244-294,439-500,503-613).
+// Each function cites the reference lines it follows.
+//
+// Pinning status:
+//  * The shading/RNG/estimator logic IS pinned against the reference's own
+//    source compiled on the host (oracle/_ref/libref_pt.so, built by
+//    oracle/Makefile from /root/reference/optixSphere.cu through ref_shim/):
+//    tests/test_oracle_vs_ref.py requires bit-identical accum buffers.
+//  * PARITY UNPINNED at the OptiX/sutil boundary (closed source or absent):
+//    ray/triangle intersection + traversal (oracle_isect.h), vec_math.h
+//    helpers and make_color (oracle_math.h, restated from the SDK as
+//    remembered), and CUDA libm (replaced by detmath on both sides).
+//
+// Oracle rules where the reference is undefined:
+//  R1 float->uint in myrnd saturates like CUDA.
+//  R2 myrnd() calls that the reference passes as function arguments are
+//     sequenced left to right (cu:328, cu:260).
+//  R3 texel fetches use the reference's linear index y*w+x; where that is
+//     negative (x0 or y0 == -1, cu:509-510, cu:579-580: an out-of-bounds read
+//     in the reference) it wraps by +w*h.  A NaN coordinate maps to index 0
+//     (CUDA cvt of NaN).
+//  R4 the path loop also ends when done && !(p > 0), contributing 0 (cu:384).
+//  R5 one texture set per material (the reference shares one global device
+//     pointer per texture kind, optixSphere.cpp:395-398).
+//
+// Build: g++ -O2 -ffp-contract=off -fopenmp (see oracle/Makefile).
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <mutex>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+#include "oracle.h"
+#include "oracle_isect.h"
+
+using namespace orc;
+
+namespace {
+
+const float PI_F = 3.14159265358979323846f;  // sutil M_PIf
+
+// CUDA cvt.rzi.s32.f32 semantics: NaN -> 0, saturating.
+inline int f2i_cuda(float f) {
+    if (f != f) return 0;
+    if (f >= 2147483648.0f) return 2147483647;
+    if (f <= -2147483648.0f) return (-2147483647 - 1);
+    return (int)f;
+}
+
+struct Ctx {
+    const OrcScene* sc;
+    const OrcConfig* cfg;
+    TriSoup soup;
+    const CpuBvh* bvh;
+    bool sat;
+};
+
+struct Payload {  // optixSphere.h:33-45
+    v3 atten; uint32_t seed; v3 emitted, radiance, origin, direction; int done; int depth; int specular_bounce;
+};
+
+inline float rnd(uint32_t& seed, const Ctx& c) { return myrnd(seed, c.sat); }
+
+// cu:38-61
+struct Onb {
+    v3 t, b, n;
+    explicit Onb(v3 normal) {
+        n = normalize(normal);
+        v3 up = fabsf(n.y) < 0.9999f ? mk3(0.0f, 1.0f, 0.0f) : mk3(1.0f, 0.0f, 0.0f);
+        t = normalize(cross(up, n));
+        b = normalize(cross(n, t));
+    }
+    v3 inverse_transform(v3 p) const { return p.x * t + p.y * n + p.z * b; }
+};
+
+// cu:244-254
+inline v3 cosine_sample_hemisphere(float u1, float u2) {
+    float r = sqrtf(u1);
+    float phi = 2.0f * PI_F * u2;
+    float s, c; det_sincosf(phi, &s, &c);
+    v3 p; p.x = r * c; p.z = r * s;
+    p.y = sqrtf(fmaxf(0.0f, 1.0f - p.x * p.x - p.z * p.z));
+    return p;
+}
+
+// cu:257-263 (R2: x, y, z drawn in that order)
+inline v3 random_in_unit_sphere(uint32_t& seed, const Ctx& c) {
+    v3 p;
+    do {
+        float a = rnd(seed, c), b = rnd(seed, c), d = rnd(seed, c);
+        p = 2.0f * mk3(a, b, d) - mk3(1.0f, 1.0f, 1.0f);
+    } while (p.x * p.x + p.y * p.y + p.z * p.z >= 1.0f);
+    return p;
+}
+
+// cu:266-277
+inline v3 tonemap(v3 x) {
+    const float A = 0.15f, B = 0.50f, C = 0.10f, D = 0.20f, E = 0.02f, F = 0.30f;
+    return ((x * (A * x + C * B) + D * E) / (x * (A * x + B) + D * F)) - E / F;
+}
+
+// cu:279-294; seed is passed BY VALUE in the reference, so the caller's
+// stream does not advance.
+inline v3 defocus_disk_sample(v3 u, v3 v, uint32_t seed, const Ctx& c) {
+    const float r = sqrtf(rnd(seed, c));
+    const float theta = (float)(2.0f * 3.14159265358979323846 * (double)rnd(seed, c));
+    const float blurriness = c.cfg->dof_blur;
+    float sn, cs; det_sincosf(theta, &sn, &cs);
+    const float x = blurriness * sqrtf(r) * cs;
+    const float y = blurriness * sqrtf(r) * sn;
+    return x * u + y * v;
+}
+
+// cu:439-449
+inline float D_GGX(v3 n, v3 h, float a) {
+    float a2 = a * a;
+    float NdotH = fmaxf(dot(n, h), 1e-10f);
+    float NdotH2 = NdotH * NdotH;
+    float denom = (NdotH2 * (a2 - 1.0f) + 1.0f);
+    denom = PI_F * denom * denom;
+    return a2 / denom;
+}
+// cu:463-472
+inline float G_SchlickGGX(float alpha, v3 n, v3 x) {
+    float numerator = fabsf(dot(n, x));
+    float k = alpha / 2.0f;
+    float denominator = fabsf(dot(n, x)) * (1.0f - k) + k;
+    denominator = fmaxf(denominator, 1e-10f);
+    return numerator / denominator;
+}
+// cu:480-484
+inline v3 Fresnel_Schlick(float cosTheta, v3 F0) {
+    cosTheta = clampf(cosTheta, 0.0f, 1.0f);
+    return F0 + (mk3(1.0f) - F0) * det_pow5(1.0f - cosTheta);
+}
+// cu:487-492
+inline float Fresnel_Schlick_float(float cosine, float refraction_index) {
+    float r0 = (1.0f - refraction_index) / (1.0f + refraction_index);
+    r0 = r0 * r0;
+    return r0 + (1.0f - r0) * det_pow5(1.0f - cosine);
+}
+// cu:494-500
+inline v3 GGX_importance_sample(float r1, float r2, float alpha) {
+    float phi = 2.0f * PI_F * r1;
+    float cosTheta = sqrtf((1.0f - r2) / (1.0f + (alpha * alpha - 1.0f) * r2));
+    float sinTheta = sqrtf(1.0f - cosTheta * cosTheta);
+    float s, c; det_sincosf(phi, &s, &c);
+    return normalize(mk3(sinTheta * c, cosTheta, sinTheta * s));
+}
+
+// Texel fetch by the reference's linear index y*w + x (cu:518-521, 587-590).
+// x0/y0 can be -1 (cu:509-510 keeps C's negative remainder, cu:579-580 has no
+// wrap at all); the reference then reads out of bounds when the linear index
+// is negative.  R3: a negative linear index wraps by +w*h; everything that is
+// in bounds in the reference is read exactly as the reference reads it.
+inline v4 texel(const float* img, int w, int h, int x, int y) {
+    long long idx = (long long)y * (long long)w + (long long)x;
+    if (idx < 0) idx += (long long)w * (long long)h;
+    const float* p = img + (size_t)idx * 4;
+    return mk4(p[0], p[1], p[2], p[3]);
+}
+
+// cu:503-529
+inline v4 sampleHDRI(const float* img, int width, int height, float u, float v) {
+    float x = u * width - 0.5f;
+    float y = v * height - 0.5f;
+    int x0 = f2i_cuda(floorf(x)) % width;
+    int y0 = f2i_cuda(floorf(y)) % height;
+    int x1 = (x0 + 1) % width;
+    int y1 = (y0 + 1) % height;
+    float s = x - floorf(x);
+    float t = y - floorf(y);
+    v4 c00 = texel(img, width, height, x0, y0), c10 = texel(img, width, height, x1, y0);
+    v4 c01 = texel(img, width, height, x0, y1), c11 = texel(img, width, height, x1, y1);
+    v4 c0 = lerp(c00, c10, s), c1 = lerp(c01, c11, s);
+    return lerp(c0, c1, t);
+}
+
+// cu:569-596
+inline v4 sampleTexture(const float* img, int width, int height, float u, float v) {
+    u = u - floorf(u);
+    v = v - floorf(v);
+    float x = u * width - 0.5f;
+    float y = v * height - 0.5f;
+    int x0 = f2i_cuda(floorf(x));
+    int y0 = f2i_cuda(floorf(y));
+    int x1 = (x0 + 1) % width;
+    int y1 = (y0 + 1) % height;
+    float s = x - floorf(x);
+    float t = y - floorf(y);
+    v4 c00 = texel(img, width, height, x0, y0), c10 = texel(img, width, height, x1, y0);
+    v4 c01 = texel(img, width, height, x0, y1), c11 = texel(img, width, height, x1, y1);
+    v4 c0 = lerp(c00, c10, s), c1 = lerp(c01, c11, s);
+    return lerp(c0, c1, t);
+}
+
+// cu:598-613
+inline v3 setMaterialProperty(const OrcTexture& tx, v3 fallback, float u, float v) {
+    if (tx.has && tx.rgba != nullptr) {
+        v4 c = sampleTexture(tx.rgba, tx.w, tx.h, u, v);
+        return mk3(c.x, c.y, c.z);
+    }
+    return fallback;
+}
+
+inline v3 attr3(const float* a, uint32_t idx) { const float* p = a + (size_t)idx * 4; return mk3(p[0], p[1], p[2]); }
+
+// cu:616-801, 858-871 (the transparent branch cu:803-856 is unreachable).
+void closest_hit(const Ctx& c, uint32_t prim_idx, float b1, float b2, float t_hit, v3 ray_orig, v3 ray_dir, Payload& io) {
+    const OrcScene& sc = *c.sc;
+    const OrcMaterial& m = sc.mats[sc.mat_ids[prim_idx]];
+    const uint32_t vo = prim_idx * 3;
+    const v3 v0 = attr3(sc.vertices, vo + 0), v1 = attr3(sc.vertices, vo + 1), v2 = attr3(sc.vertices, vo + 2);
+    v3 flat_normal = normalize(cross(v1 - v0, v2 - v0));
+    flat_normal = faceforward(flat_normal, -ray_dir, flat_normal);
+
+    // getPayloadCH (cu:160-172): only atten, seed, depth, specular_bounce come in.
+    Payload p = {};
+    p.atten = io.atten; p.seed = io.seed; p.depth = io.depth; p.specular_bounce = io.specular_bounce;
+
+    v3 n0 = attr3(sc.normals, vo + 0), n1 = attr3(sc.normals, vo + 1), n2 = attr3(sc.normals, vo + 2);
+    const float bary_beta = b1, bary_gamma = b2;
+    const float bary_alpha = 1.0f - bary_beta - bary_gamma;
+    const float* tc = sc.texcoords + (size_t)vo * 2;
+    orc::v2 uv;
+    uv.x = tc[0] * bary_alpha + tc[2] * bary_beta + tc[4] * bary_gamma;
+    uv.y = tc[1] * bary_alpha + tc[3] * bary_beta + tc[5] * bary_gamma;
+    uv.y = 1.0f - uv.y;
+
+    v3 normal = bary_alpha * n0 + bary_beta * n1 + bary_gamma * n2;
+    if (length(normal) > 0.01f) normal = normalize(normal);
+    else { p.done = 1; io = p; return; }
+    if (dot(normal, ray_dir) > 0.0f) normal = flat_normal;
+
+    const v3 hit_pos = ray_orig + t_hit * ray_dir;
+    uint32_t seed = p.seed;
+
+    v3 diffuse_albedo = setMaterialProperty(m.albedo, mk3(m.diffuse_color[0], m.diffuse_color[1], m.diffuse_color[2]), uv.x, uv.y);
+    v3 normal_map = setMaterialProperty(m.normal, mk3(0.0f, 1.0f, 0.0f), uv.x, uv.y);
+    if (m.normal.has) {
+        normal_map = normalize(2.0f * normal_map - mk3(1.0f));
+        normal_map = mk3(normal_map.x, normal_map.z, normal_map.y);
+    }
+    const float normal_map_strength = c.cfg->nmap_strength;
+    Onb onb_nmap(normal);
+    normal_map = onb_nmap.inverse_transform(normal_map);
+    normal = normalize(normal_map_strength * normal_map + (1.0f - normal_map_strength) * normal);
+    v3 specular_albedo = diffuse_albedo;
+    v3 emission_color = mk3(m.emission_color[0], m.emission_color[1], m.emission_color[2]);
+
+    float roughness = setMaterialProperty(m.roughness, mk3(m.roughness_value), uv.x, uv.y).x;
+    float metallicity = setMaterialProperty(m.metallic, m.metallic_flag ? mk3(1.0f) : mk3(0.0f), uv.x, uv.y).x;
+    const float ior = 1.5f;
+
+    if (p.depth == 0) p.emitted = emission_color; else p.emitted = mk3(0.0f);
+
+    if (length(emission_color) > 0.0001f) {
+        p.radiance = p.radiance + p.atten * emission_color;
+        p.done = 1;
+        io = p;  // seed not advanced
+        return;
+    }
+
+    random_in_unit_sphere(seed, c);  // cu:733: result discarded, draws consumed
+
+    if (roughness < 0.015f) roughness = 0.015f;
+    if (roughness > 0.999f) roughness = 0.999f;
+    if (p.depth <= 0) p.done = 1;
+
+    float r1 = rnd(seed, c);
+    float r2 = rnd(seed, c);
+    float alpha = roughness * roughness;
+    v3 half_vec = GGX_importance_sample(r1, r2, alpha);
+    Onb onb(normal);
+    half_vec = onb.inverse_transform(half_vec);  // cu:750 normalize() result is discarded
+
+    v3 light_dir = reflect(ray_dir, half_vec);
+    r1 = rnd(seed, c);
+    r2 = rnd(seed, c);
+    v3 light_dir_diffuse = cosine_sample_hemisphere(r1, r2);
+    light_dir_diffuse = onb.inverse_transform(light_dir_diffuse);
+
+    float f0s = (float)fabs((1.0 - (double)ior) / (1.0 + (double)ior));
+    v3 F0 = mk3(f0s);
+    F0 = F0 * F0;
+    F0 = lerp(F0, specular_albedo, metallicity);
+
+    v3 F = Fresnel_Schlick(fmaxf(dot(normal, -ray_dir), 0.0f), F0);
+    float D = D_GGX(normal, half_vec, alpha);
+    float G = G_SchlickGGX(alpha, normal, -ray_dir) * G_SchlickGGX(alpha, normal, light_dir);
+    v3 brdf_specular = F * D * G / (4.0f * fabsf(dot(normal, -ray_dir)) * fabsf(dot(normal, light_dir)));
+
+    float NdotH = fmaxf(dot(normal, half_vec), 1e-10f);
+    float VdotH = fmaxf(dot(-ray_dir, half_vec), 1e-10f);
+    float NdotV = fmaxf(dot(normal, -ray_dir), 0.0f);
+    float IdotN = fabsf(dot(normal, normalize(light_dir)));
+    float F_blend_factor = Fresnel_Schlick_float(NdotV, ior);
+
+    float specular_probability = metallicity + (1.0f - metallicity) * F_blend_factor;
+    float spdf = D * NdotH / (4.0f * VdotH);
+    float dpdf = 1.0f / PI_F;
+    if (rnd(seed, c) < specular_probability) {
+        p.direction = normalize(light_dir);
+        p.specular_bounce = 1;
+    } else {
+        p.direction = normalize(light_dir_diffuse);
+        p.specular_bounce = 0;
+    }
+    v3 brdf = specular_probability * (brdf_specular / spdf) + (1.0f - specular_probability) * (diffuse_albedo / dpdf);
+
+    if (length(brdf) >= 1e-10f) p.atten = p.atten * (brdf * IdotN);
+    p.origin = hit_pos;
+    p.seed = seed;
+    io = p;
+}
+
+// cu:531-567; getPayloadMiss/setPayloadMiss (cu:175-190, 225-241): seed,
+// origin, direction, specular_bounce are left untouched.
+void miss(const Ctx& c, v3 dir, Payload& io) {
+    v3 ray_dir = normalize(dir);
+    float u = 0.5f + det_atan2f(ray_dir.z, ray_dir.x) / (2.0f * PI_F);
+    float v = 0.5f - det_asinf(ray_dir.y) / PI_F;
+    v4 hdr = sampleHDRI(c.sc->env_rgba, c.sc->env_w, c.sc->env_h, u, v);
+    io.radiance = io.radiance + io.atten * mk3(hdr.x, hdr.y, hdr.z);
+    io.emitted = mk3(0.0f);
+    io.done = 1;
+}
+
+// SDK cuda/helpers.h make_color (restated): clamp -> sRGB -> quantize.
+inline float to_srgb1(float c) {
+    float invGamma = 1.0f / 2.4f;
+    float powed = powf(c, invGamma);
+    return c < 0.0031308f ? 12.92f * c : 1.055f * powed - 0.055f;
+}
+inline uint8_t quantize8(float x) {
+    x = clampf(x, 0.0f, 1.0f);
+    uint32_t q = (uint32_t)(x * 256.0f);
+    return (uint8_t)(q < 255u ? q : 255u);
+}
+// cu:411-435
+void tonemap_pixel(v3 accum_color, const OrcConfig& cfg, uint8_t out[4]) {
+    v3 rgb = accum_color * exp2f(cfg.exposure);
+    rgb = tonemap(rgb);
+    rgb = clamp(rgb, 0.0f, 1.0f);
+    float ig = 1.0f / cfg.gamma;
+    rgb = mk3(powf(rgb.x, ig), powf(rgb.y, ig), powf(rgb.z, ig));
+    rgb = (rgb - 0.5f) * cfg.contrast + 0.5f;  // cu:433: 0.5f + contrast * (rgb - 0.5f)
+    v3 s = clamp(rgb, 0.0f, 1.0f);
+    out[0] = quantize8(to_srgb1(s.x)); out[1] = quantize8(to_srgb1(s.y)); out[2] = quantize8(to_srgb1(s.z)); out[3] = 255;
+}
+
+Hit trace(const Ctx& c, v3 o, v3 d) {
+    if (c.bvh) return c.bvh->closest(c.soup, o, d, c.cfg->tmin, c.cfg->tmax);
+    return closest_brute(c.soup, o, d, c.cfg->tmin, c.cfg->tmax);
+}
+
+// cu:297-436 for one pixel.
+void raygen_pixel(const Ctx& c, const OrcParams& P, uint32_t ix, uint32_t iy, float* accum, uint8_t* frame,
+                  int32_t* primary_hit, OrcStats& st) {
+    const v3 eye = mk3(P.eye[0], P.eye[1], P.eye[2]);
+    const v3 U = mk3(P.U[0], P.U[1], P.U[2]), V = mk3(P.V[0], P.V[1], P.V[2]), W = mk3(P.W[0], P.W[1], P.W[2]);
+    const int subframe_index = P.subframe_index;
+    uint32_t seed = iy * P.width + ix + (uint32_t)subframe_index * P.width * P.height;
+    v3 payload_rgb = mk3(0.0f);
+    const int spp = c.cfg->spp_per_launch;
+    for (int i = 0; i < spp; ++i) {
+        float jx = rnd(seed, c);  // R2
+        float jy = rnd(seed, c);
+        float dx = 2.0f * (((float)ix + jx) / (float)P.width) - 1.0f;
+        float dy = 2.0f * (((float)iy + jy) / (float)P.height) - 1.0f;
+        v3 origin, direction;
+        if (P.dof) {
+            origin = defocus_disk_sample(U, V, seed, c);
+            v3 target = c.cfg->focus_dist * (dx * U + dy * V + W);
+            direction = normalize(target - origin);
+            origin = origin + eye;
+        } else {
+            origin = eye;
+            direction = normalize(dx * U + dy * V + W);
+        }
+        v3 path_rgb = mk3(0.0f);
+        Payload pl;
+        pl.atten = mk3(1.0f); pl.radiance = mk3(0.0f); pl.emitted = mk3(0.0f); pl.specular_bounce = 0;
+        pl.origin = mk3(0.0f); pl.direction = mk3(0.0f);
+        pl.seed = seed; pl.done = 0; pl.depth = c.cfg->max_depth;
+        st.paths++;
+        bool first = true;
+        for (;;) {
+            Hit h = trace(c, origin, direction);
+            st.segments++;
+            if (first && i == 0 && primary_hit) primary_hit[(size_t)iy * P.width + ix] = h.prim;
+            first = false;
+            if (h.prim >= 0) { st.hits++; closest_hit(c, (uint32_t)h.prim, h.b1, h.b2, h.t, origin, direction, pl); }
+            else { st.misses++; miss(c, direction, pl); }
+            path_rgb = pl.radiance;
+            const float p = fmaxf(pl.atten.x, fmaxf(pl.atten.y, pl.atten.z));
+            const bool done = pl.done || rnd(seed, c) > p;  // short-circuit: no draw when payload.done
+            if (done && p > 0.0f) { path_rgb = path_rgb / p; break; }
+            if (done) { path_rgb = mk3(0.0f); break; }  // R4
+            origin = pl.origin; direction = pl.direction;
+            pl.depth--;
+        }
+        payload_rgb = payload_rgb + path_rgb;
+    }
+    const size_t image_index = (size_t)iy * P.width + ix;
+    v3 accum_color = payload_rgb / (float)spp;
+    float* a = accum + image_index * 4;
+    if (c.cfg->accumulate_sum) {
+        accum_color = mk3(a[0], a[1], a[2]) + accum_color;
+    } else if (subframe_index > 0) {
+        const float w = 1.0f / (float)(subframe_index + 1);
+        accum_color = lerp(mk3(a[0], a[1], a[2]), accum_color, w);
+    }
+    a[0] = accum_color.x; a[1] = accum_color.y; a[2] = accum_color.z; a[3] = 1.0f;
+    if (frame) tonemap_pixel(accum_color, *c.cfg, frame + image_index * 4);
+}
+
+// The BVH is cached per vertex pointer/count so repeated orc_render calls on
+// the same scene (bench loops) do not rebuild it.
+std::mutex g_bvh_mu;
+const float* g_bvh_key = nullptr; uint32_t g_bvh_n = 0; CpuBvh g_bvh;
+const CpuBvh* get_bvh(const TriSoup& s) {
+    std::lock_guard<std::mutex> lk(g_bvh_mu);
+    if (g_bvh_key != s.verts || g_bvh_n != s.n) { g_bvh.build(s); g_bvh_key = s.verts; g_bvh_n = s.n; }
+    return &g_bvh;
+}
+
+}  // namespace
+
+extern "C" {
+
+void orc_default_config(OrcConfig* cfg) {
+    cfg->spp_per_launch = 10; cfg->max_depth = 20; cfg->tmin = 0.01f; cfg->tmax = 1e16f;
+    cfg->dof_blur = 0.01f; cfg->focus_dist = 1.0f; cfg->nmap_strength = 0.4f;
+    cfg->exposure = -0.5f; cfg->gamma = 2.2f; cfg->contrast = 1.25f;
+    cfg->sat_cuda = 1; cfg->use_bvh = 1; cfg->threads = 0; cfg->accumulate_sum = 0;
+}
+
+int orc_render(const OrcScene* scene, const OrcParams* params, const OrcConfig* cfg, float* accum, uint8_t* frame,
+               int32_t* primary_hit, OrcStats* stats, int32_t x0, int32_t y0, int32_t x1, int32_t y1) {
+    if (!scene || !params || !cfg || !accum) return 1;
+    Ctx c; c.sc = scene; c.cfg = cfg; c.soup.verts = scene->vertices; c.soup.n = scene->num_tris;
+    c.sat = cfg->sat_cuda != 0;
+    c.bvh = cfg->use_bvh ? get_bvh(c.soup) : nullptr;
+    int nthreads = cfg->threads;
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+#else
+    nthreads = 1;
+#endif
+    uint64_t seg = 0, paths = 0, hits = 0, misses = 0;
+    auto t0 = std::chrono::steady_clock::now();
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads) reduction(+ : seg, paths, hits, misses)
+    for (int32_t y = y0; y < y1; ++y) {
+        OrcStats st = {};
+        for (int32_t x = x0; x < x1; ++x) raygen_pixel(c, *params, (uint32_t)x, (uint32_t)y, accum, frame, primary_hit, st);
+        seg += st.segments; paths += st.paths; hits += st.hits; misses += st.misses;
+    }
+    auto t1 = std::chrono::steady_clock::now();
+    if (stats) {
+        stats->segments = seg; stats->paths = paths; stats->hits = hits; stats->misses = misses;
+        stats->seconds = std::chrono::duration<double>(t1 - t0).count(); stats->threads = nthreads;
+    }
+    return 0;
+}
+
+int32_t orc_closest_hit(const OrcScene* scene, const float org[3], const float dir[3], float tmin, float tmax,
+                        int32_t use_bvh, float* t, float* b1, float* b2) {
+    TriSoup s; s.verts = scene->vertices; s.n = scene->num_tris;
+    v3 o = mk3(org[0], org[1], org[2]), d = mk3(dir[0], dir[1], dir[2]);
+    Hit h = use_bvh ? get_bvh(s)->closest(s, o, d, tmin, tmax) : closest_brute(s, o, d, tmin, tmax);
+    if (t) *t = h.t;
+    if (b1) *b1 = h.b1;
+    if (b2) *b2 = h.b2;
+    return h.prim;
+}
+
+uint32_t orc_rng_next(uint32_t seed, int32_t sat_cuda, float* u) {
+    float r = myrnd(seed, sat_cuda != 0);
+    if (u) *u = r;
+    return seed;
+}
+void orc_sincos(float x, float* s, float* c) { det_sincosf(x, s, c); }
+float orc_atan2(float y, float x) { return det_atan2f(y, x); }
+float orc_asin(float x) { return det_asinf(x); }
+void orc_tonemap_pixel(const float rgb[3], const OrcConfig* cfg, uint8_t out[4]) { tonemap_pixel(mk3(rgb[0], rgb[1], rgb[2]), *cfg, out); }
+void orc_sample_texture(const OrcTexture* tex, float u, float v, float out[4]) {
+    v4 c = sampleTexture(tex->rgba, tex->w, tex->h, u, v);
+    out[0] = c.x; out[1] = c.y; out[2] = c.z; out[3] = c.w;
+}
+void orc_sample_env(const float* env, int32_t w, int32_t h, const float dir[3], float out[4]) {
+    v3 d = normalize(mk3(dir[0], dir[1], dir[2]));
+    float u = 0.5f + det_atan2f(d.z, d.x) / (2.0f * PI_F);
+    float v = 0.5f - det_asinf(d.y) / PI_F;
+    v4 c = sampleHDRI(env, w, h, u, v);
+    out[0] = c.x; out[1] = c.y; out[2] = c.z; out[3] = c.w;
+}
+// sutil::Camera::UVWFrame (SDK, restated; optixSphere.cpp:102-120, 238-247).
+void orc_camera_uvw(const float eye[3], const float lookat[3], const float up[3], float fovy_deg, float aspect,
+                    float U[3], float V[3], float W[3]) {
+    v3 w = mk3(lookat[0], lookat[1], lookat[2]) - mk3(eye[0], eye[1], eye[2]);
+    float wlen = length(w);
+    v3 u = normalize(cross(w, mk3(up[0], up[1], up[2])));
+    v3 v = normalize(cross(u, w));
+    float vlen = wlen * tanf(0.5f * fovy_deg * PI_F / 180.0f);
+    v = v * vlen;
+    float ulen = vlen * aspect;
+    u = u * ulen;
+    U[0] = u.x; U[1] = u.y; U[2] = u.z; V[0] = v.x; V[1] = v.y; V[2] = v.z; W[0] = w.x; W[1] = w.y; W[2] = w.z;
+}
+const char* orc_impl_name(void) { return "oracle-restatement"; }
+
+}  // extern "C"

@@ -1,0 +1,439 @@
+// bvh_build.cu -- device BVH build for sm_100a.
+//
+// Replaces optixAccelComputeMemoryUsage / optixAccelBuild / optixAccelCompact
+// (optixSphere.cpp:917-967).  Only the input contract is the reference's
+// (optixSphere.cpp:862-913: float3 positions at 16-byte stride, 3 per triangle,
+// no index buffer); the algorithm is ours:
+//   1. k_tri_bounds      per-triangle AABB + centroid, scene bounds by warp
+//                        shuffle reduction + one atomic per warp
+//   2. k_morton          30-bit Morton code of the centroid
+//   3. radix sort        own 4 x 8-bit LSD passes (histogram / scan / stable
+//                        scatter with __match_any_sync ranking)
+//   4. k_hierarchy       Karras 2012 radix tree, one thread per internal node
+//   5. k_refit           bottom-up AABBs with one atomic arrival flag per node
+//   6. treelet SAH       (bvh_refine.cuh) binned-SAH rebuild of every subtree
+//                        of <= treelet_size triangles, in place
+//   7. k_emit            64-byte two-child nodes + 48-byte leaf-ordered
+//                        triangles (layout in bvh.cuh); subtrees of
+//                        <= max_leaf_size triangles collapse into one leaf
+// All kernels are HBM-streaming integer/float work; grids are sized from N.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "bvh_build.h"
+#include "device_math.cuh"
+
+namespace ptb {
+
+namespace {
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { err = std::string(#call) + ": " + cudaGetErrorString(e_); return false; } } while (0)
+
+// float atomic min/max through the ordered-int trick
+__device__ __forceinline__ void atomic_min_f(float* addr, float v) {
+    if (v >= 0.0f) atomicMin((int*)addr, __float_as_int(v)); else atomicMax((unsigned int*)addr, __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_f(float* addr, float v) {
+    if (v >= 0.0f) atomicMax((int*)addr, __float_as_int(v)); else atomicMin((unsigned int*)addr, __float_as_uint(v));
+}
+
+// scene_bounds: [0..2] = lo, [3..5] = hi of the triangle AABBs, [6..8]/[9..11] of the centroids
+__global__ void k_tri_bounds(const float4* __restrict__ verts, uint32_t n, float4* __restrict__ tri_lo,
+                             float4* __restrict__ tri_hi, float* __restrict__ scene_bounds) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    float clo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, chi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    if (i < n) {
+        const float4 a = verts[(size_t)i * 3 + 0], b = verts[(size_t)i * 3 + 1], c = verts[(size_t)i * 3 + 2];
+        lo[0] = fminf(a.x, fminf(b.x, c.x)); lo[1] = fminf(a.y, fminf(b.y, c.y)); lo[2] = fminf(a.z, fminf(b.z, c.z));
+        hi[0] = fmaxf(a.x, fmaxf(b.x, c.x)); hi[1] = fmaxf(a.y, fmaxf(b.y, c.y)); hi[2] = fmaxf(a.z, fmaxf(b.z, c.z));
+        tri_lo[i] = make_float4(lo[0], lo[1], lo[2], 0.0f);
+        tri_hi[i] = make_float4(hi[0], hi[1], hi[2], 0.0f);
+        for (int k = 0; k < 3; ++k) clo[k] = chi[k] = 0.5f * (lo[k] + hi[k]);
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        for (int k = 0; k < 3; ++k) {
+            lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], off));
+            hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], off));
+            clo[k] = fminf(clo[k], __shfl_xor_sync(0xffffffffu, clo[k], off));
+            chi[k] = fmaxf(chi[k], __shfl_xor_sync(0xffffffffu, chi[k], off));
+        }
+    }
+    if ((threadIdx.x & 31u) == 0u) {
+        for (int k = 0; k < 3; ++k) {
+            atomic_min_f(scene_bounds + k, lo[k]); atomic_max_f(scene_bounds + 3 + k, hi[k]);
+            atomic_min_f(scene_bounds + 6 + k, clo[k]); atomic_max_f(scene_bounds + 9 + k, chi[k]);
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t expand_bits10(uint32_t v) {
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+
+__global__ void k_morton(const float4* __restrict__ tri_lo, const float4* __restrict__ tri_hi, uint32_t n,
+                         const float* __restrict__ scene_bounds, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 lo = tri_lo[i], hi = tri_hi[i];
+    const float c[3] = {0.5f * (lo.x + hi.x), 0.5f * (lo.y + hi.y), 0.5f * (lo.z + hi.z)};
+    uint32_t q[3];
+    for (int k = 0; k < 3; ++k) {
+        const float clo = scene_bounds[6 + k], ext = scene_bounds[9 + k] - clo;
+        float u = ext > 0.0f ? (c[k] - clo) / ext : 0.0f;
+        u = fminf(fmaxf(u * 1024.0f, 0.0f), 1023.0f);
+        q[k] = (uint32_t)u;
+    }
+    keys[i] = (expand_bits10(q[0]) << 2) | (expand_bits10(q[1]) << 1) | expand_bits10(q[2]);
+    vals[i] = i;
+}
+
+// ---- LSD radix sort, 8 bits per pass ------------------------------------------------
+// One warp owns a tile of SORT_TILE consecutive keys.  Ranking inside a 32-key
+// chunk uses __match_any_sync, so the scatter is stable.
+#define SORT_TILE 2048u
+
+__global__ void k_sort_hist(const uint32_t* __restrict__ keys, uint32_t n, int shift, uint32_t* __restrict__ hist,
+                            uint32_t n_tiles) {
+    __shared__ uint32_t h[256];
+    const uint32_t tile = blockIdx.x, lane = threadIdx.x;
+    for (uint32_t b = lane; b < 256; b += 32) h[b] = 0;
+    __syncwarp();
+    const uint32_t begin = tile * SORT_TILE, end = min(begin + SORT_TILE, n);
+    for (uint32_t i = begin + lane; i < end; i += 32) atomicAdd(&h[(keys[i] >> shift) & 255u], 1u);
+    __syncwarp();
+    for (uint32_t b = lane; b < 256; b += 32) hist[(size_t)b * n_tiles + tile] = h[b];  // bin-major
+}
+
+// exclusive scan of hist[256 * n_tiles] in place, one block
+__global__ void k_sort_scan(uint32_t* __restrict__ hist, uint32_t total) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < total; base += blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < total ? hist[i] : 0u;
+        uint32_t x = v;
+        for (int off = 1; off < 32; off <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, off); if ((int)lane >= off) x += y; }
+        if (lane == 31u) warp_sums[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t s = lane < (blockDim.x >> 5) ? warp_sums[lane] : 0u;
+            for (int off = 1; off < 32; off <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, s, off); if ((int)lane >= off) s += y; }
+            warp_sums[lane] = s;  // inclusive
+        }
+        __syncthreads();
+        const uint32_t warp_off = warp ? warp_sums[warp - 1] : 0u;
+        const uint32_t c = carry;
+        if (i < total) hist[i] = c + warp_off + x - v;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = c + warp_off + x;
+        __syncthreads();
+    }
+}
+
+__global__ void k_sort_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t n,
+                               int shift, const uint32_t* __restrict__ hist, uint32_t n_tiles,
+                               uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
+    __shared__ uint32_t offs[256];
+    const uint32_t tile = blockIdx.x, lane = threadIdx.x;
+    for (uint32_t b = lane; b < 256; b += 32) offs[b] = hist[(size_t)b * n_tiles + tile];
+    __syncwarp();
+    const uint32_t begin = tile * SORT_TILE, end = min(begin + SORT_TILE, n);
+    for (uint32_t base = begin; base < end; base += 32) {
+        const uint32_t i = base + lane;
+        const bool active = i < end;
+        const uint32_t key = active ? keys_in[i] : 0u, val = active ? vals_in[i] : 0u;
+        const uint32_t digit = active ? ((key >> shift) & 255u) : 256u;  // 256 = inactive group
+        const unsigned peers = __match_any_sync(0xffffffffu, digit);
+        const uint32_t rank = (uint32_t)__popc(peers & ((1u << lane) - 1u));
+        uint32_t dst = 0;
+        if (active) dst = offs[digit] + rank;
+        __syncwarp();
+        if (active && rank == 0u) offs[digit] += (uint32_t)__popc(peers);
+        __syncwarp();
+        if (active) { keys_out[dst] = key; vals_out[dst] = val; }
+    }
+}
+
+// ---- Karras 2012 ----------------------------------------------------------------------
+__device__ __forceinline__ int delta(const uint32_t* __restrict__ keys, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    const uint32_t a = keys[i], b = keys[j];
+    if (a == b) return 32 + __clz((uint32_t)i ^ (uint32_t)j);
+    return __clz(a ^ b);
+}
+
+// child encoding in the build tree: >= 0 internal node index, < 0 leaf ~index
+__global__ void k_hierarchy(const uint32_t* __restrict__ keys, int n, int2* __restrict__ children,
+                            int2* __restrict__ ranges, int* __restrict__ node_parent, int* __restrict__ leaf_parent) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    const int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    const int dmin = delta(keys, n, i, i - d);
+    int lmax = 2;
+    while (delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1) if (delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    const int j = i + l * d;
+    const int dnode = delta(keys, n, i, j);
+    int s = 0, t = l;
+    do {
+        t = (t + 1) >> 1;
+        if (delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    const int gamma = i + s * d + min(d, 0);
+    const int first = min(i, j), last = max(i, j);
+    int left, right;
+    if (first == gamma) { left = ~gamma; leaf_parent[gamma] = i; } else { left = gamma; node_parent[gamma] = i; }
+    if (last == gamma + 1) { right = ~(gamma + 1); leaf_parent[gamma + 1] = i; } else { right = gamma + 1; node_parent[gamma + 1] = i; }
+    children[i] = make_int2(left, right);
+    ranges[i] = make_int2(first, last);
+    if (i == 0) node_parent[0] = -1;
+}
+
+// Leaf boxes are padded so that the conservative slab test of the traversal can
+// never reject a box whose triangle passes the watertight test: the edge
+// functions of that test are evaluated relative to the ray origin, so their
+// rounding error scales with the scene extent, not with the triangle.
+__global__ void k_leaf_boxes(const float4* __restrict__ tri_lo, const float4* __restrict__ tri_hi,
+                             const uint32_t* __restrict__ sorted_vals, uint32_t n, const float* __restrict__ scene_bounds,
+                             float4* __restrict__ leaf_lo, float4* __restrict__ leaf_hi) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t p = sorted_vals[i];
+    float4 lo = tri_lo[p], hi = tri_hi[p];
+    const float ex = scene_bounds[3] - scene_bounds[0], ey = scene_bounds[4] - scene_bounds[1], ez = scene_bounds[5] - scene_bounds[2];
+    const float diag = sqrtf(ex * ex + ey * ey + ez * ez);
+    float mag = fmaxf(fmaxf(fabsf(lo.x), fabsf(hi.x)), fmaxf(fmaxf(fabsf(lo.y), fabsf(hi.y)), fmaxf(fabsf(lo.z), fabsf(hi.z))));
+    const float pad = diag * 2.384185791015625e-7f + mag * 9.5367431640625e-7f + 1e-30f;  // 2^-22, 2^-20
+    leaf_lo[i] = make_float4(lo.x - pad, lo.y - pad, lo.z - pad, 0.0f);
+    leaf_hi[i] = make_float4(hi.x + pad, hi.y + pad, hi.z + pad, 0.0f);
+}
+
+__global__ void k_refit(const int2* __restrict__ children, const int* __restrict__ node_parent,
+                        const int* __restrict__ leaf_parent, const float4* __restrict__ leaf_lo,
+                        const float4* __restrict__ leaf_hi, int n, float4* __restrict__ node_lo, float4* __restrict__ node_hi,
+                        unsigned int* __restrict__ flags, unsigned int* __restrict__ max_depth) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int node = leaf_parent[i];
+    while (node >= 0) {
+        if (atomicAdd(&flags[node], 1u) == 0u) break;  // first arrival: the sibling subtree is not finished yet
+        __threadfence();
+        const int2 ch = children[node];
+        // volatile-style reads through L2: the sibling's box was written by another SM
+        const float4 alo = ch.x < 0 ? leaf_lo[~ch.x] : __ldcg(&node_lo[ch.x]);
+        const float4 ahi = ch.x < 0 ? leaf_hi[~ch.x] : __ldcg(&node_hi[ch.x]);
+        const float4 blo = ch.y < 0 ? leaf_lo[~ch.y] : __ldcg(&node_lo[ch.y]);
+        const float4 bhi = ch.y < 0 ? leaf_hi[~ch.y] : __ldcg(&node_hi[ch.y]);
+        node_lo[node] = make_float4(fminf(alo.x, blo.x), fminf(alo.y, blo.y), fminf(alo.z, blo.z), 0.0f);
+        node_hi[node] = make_float4(fmaxf(ahi.x, bhi.x), fmaxf(ahi.y, bhi.y), fmaxf(ahi.z, bhi.z), 0.0f);
+        __threadfence();
+        node = node_parent[node];
+    }
+    // depth of this leaf (number of internal nodes above it)
+    unsigned int depth = 0;
+    for (int p = leaf_parent[i]; p >= 0; p = node_parent[p]) depth++;
+    atomicMax(max_depth, depth);
+}
+
+__device__ __forceinline__ float half_area(float4 lo, float4 hi) {
+    const float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
+    return dx * dy + dy * dz + dz * dx;
+}
+
+// Final layout.  A child subtree with <= max_leaf triangles becomes one leaf
+// (its triangles are contiguous in sorted order); nodes below it stay unused.
+// stats: [0] live nodes, [1] leaves, sah: sum of area-weighted costs (Ct = Ci = 1).
+__global__ void k_emit_nodes(const int2* __restrict__ children, const int2* __restrict__ ranges,
+                             const int* __restrict__ node_parent, const float4* __restrict__ leaf_lo,
+                             const float4* __restrict__ leaf_hi, const float4* __restrict__ node_lo,
+                             const float4* __restrict__ node_hi, int n, int max_leaf, float4* __restrict__ out_nodes,
+                             unsigned int* __restrict__ stats, float* __restrict__ sah) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    const int2 r = ranges[i];
+    const bool live = (i == 0) || (r.y - r.x + 1 > max_leaf);
+    if (!live) {
+        // keep the slot well defined (never referenced)
+        const float qnan = __int_as_float(0x7fc00000);
+        out_nodes[(size_t)i * 4 + 0] = out_nodes[(size_t)i * 4 + 1] = out_nodes[(size_t)i * 4 + 2] = make_float4(qnan, qnan, qnan, qnan);
+        out_nodes[(size_t)i * 4 + 3] = make_float4(__int_as_float(-1), __int_as_float(-1), 0.0f, 0.0f);
+        return;
+    }
+    const int2 ch = children[i];
+    float4 lo[2], hi[2];
+    int code[2];
+    int leaves_here = 0; float cost = 0.0f;
+    for (int c = 0; c < 2; ++c) {
+        const int child = c ? ch.y : ch.x;
+        if (child < 0) {
+            lo[c] = leaf_lo[~child]; hi[c] = leaf_hi[~child];
+            code[c] = ~(((~child) << 3) | 0);
+            leaves_here++; cost += half_area(lo[c], hi[c]) * 1.0f;
+        } else {
+            lo[c] = node_lo[child]; hi[c] = node_hi[child];
+            const int2 cr = ranges[child];
+            const int cnt = cr.y - cr.x + 1;
+            if (cnt <= max_leaf) { code[c] = ~((cr.x << 3) | (cnt - 1)); leaves_here++; cost += half_area(lo[c], hi[c]) * (float)cnt; }
+            else code[c] = child;
+        }
+    }
+    out_nodes[(size_t)i * 4 + 0] = make_float4(lo[0].x, hi[0].x, lo[0].y, hi[0].y);
+    out_nodes[(size_t)i * 4 + 1] = make_float4(lo[1].x, hi[1].x, lo[1].y, hi[1].y);
+    out_nodes[(size_t)i * 4 + 2] = make_float4(lo[0].z, hi[0].z, lo[1].z, hi[1].z);
+    out_nodes[(size_t)i * 4 + 3] = make_float4(__int_as_float(code[0]), __int_as_float(code[1]), 0.0f, 0.0f);
+    cost += half_area(node_lo[i], node_hi[i]);  // one traversal step for this node
+    atomicAdd(&stats[0], 1u);
+    atomicAdd(&stats[1], (unsigned int)leaves_here);
+    atomicAdd(sah, cost);
+}
+
+__global__ void k_emit_tris(const float4* __restrict__ verts, const uint32_t* __restrict__ sorted_vals, uint32_t n,
+                            float4* __restrict__ out_tris) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t p = sorted_vals[i];
+    float4 a = verts[(size_t)p * 3 + 0], b = verts[(size_t)p * 3 + 1], c = verts[(size_t)p * 3 + 2];
+    a.w = __int_as_float((int)p); b.w = 0.0f; c.w = 0.0f;
+    out_tris[(size_t)i * 3 + 0] = a; out_tris[(size_t)i * 3 + 1] = b; out_tris[(size_t)i * 3 + 2] = c;
+}
+
+struct Scratch {
+    std::vector<void*> ptrs;
+    ~Scratch() { for (void* p : ptrs) cudaFree(p); }
+    template <typename T> bool alloc(T** out, size_t count, std::string& err) {
+        void* p = nullptr;
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+        if (e != cudaSuccess) { err = std::string("cudaMalloc (BVH scratch): ") + cudaGetErrorString(e); return false; }
+        ptrs.push_back(p); *out = (T*)p; return true;
+    }
+};
+
+}  // namespace
+
+bool build_bvh(const float4* d_verts, uint32_t n, const ptb_build_cfg& cfg, cudaStream_t stream, DeviceBvh& out,
+               ptb_build_stats& stats, std::string& err) {
+    memset(&stats, 0, sizeof(stats));
+    stats.num_triangles = n;
+    const int max_leaf = cfg.max_leaf_size < 1 ? 1 : (cfg.max_leaf_size > 8 ? 8 : cfg.max_leaf_size);
+    if (n >= (1u << 28)) { err = "BVH build: more than 2^28 triangles"; return false; }
+
+    const uint32_t n_nodes = n >= 2 ? n - 1 : 1;
+    float4* d_nodes = nullptr; float4* d_tris = nullptr;
+    CK(cudaMalloc((void**)&d_nodes, (size_t)n_nodes * 64));
+    if (cudaMalloc((void**)&d_tris, (size_t)std::max(n, 1u) * 48) != cudaSuccess) { cudaFree(d_nodes); err = "cudaMalloc (BVH triangles) failed"; return false; }
+    out.nodes = d_nodes; out.tris = d_tris; out.n_nodes = n_nodes; out.n_tris = n;
+
+    cudaEvent_t ev0, ev1;
+    CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
+    CK(cudaEventRecord(ev0, stream));
+
+    if (n < 2) {
+        // Degenerate scenes: a root whose missing children have NaN boxes (never entered).
+        const float qnan = __builtin_nanf("");
+        float h[16];
+        for (int i = 0; i < 12; ++i) h[i] = qnan;
+        int codes[4] = {-1, -1, 0, 0};
+        memcpy(h + 12, codes, 16);
+        if (n == 1) {
+            float v[12];
+            CK(cudaMemcpyAsync(v, d_verts, 48, cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
+            float lo[3], hi[3];
+            for (int k = 0; k < 3; ++k) { lo[k] = std::min(v[k], std::min(v[4 + k], v[8 + k])); hi[k] = std::max(v[k], std::max(v[4 + k], v[8 + k])); }
+            float mag = 0.0f; for (int k = 0; k < 3; ++k) mag = std::max(mag, std::max(fabsf(lo[k]), fabsf(hi[k])));
+            const float pad = mag * 1e-5f + 1e-30f;
+            h[0] = lo[0] - pad; h[1] = hi[0] + pad; h[2] = lo[1] - pad; h[3] = hi[1] + pad; h[8] = lo[2] - pad; h[9] = hi[2] + pad;
+            int zero = 0; memcpy(&v[3], &zero, 4); v[7] = 0.0f; v[11] = 0.0f;
+            CK(cudaMemcpyAsync(d_tris, v, 48, cudaMemcpyHostToDevice, stream));
+        }
+        CK(cudaMemcpyAsync(d_nodes, h, 64, cudaMemcpyHostToDevice, stream));
+        CK(cudaStreamSynchronize(stream));
+        stats.num_nodes = 1; stats.num_leaves = n; stats.max_depth = 1; stats.bvh_bytes = 64 + (uint64_t)n * 48;
+        cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+        return true;
+    }
+
+    Scratch sc;
+    float4 *tri_lo, *tri_hi, *leaf_lo, *leaf_hi, *node_lo, *node_hi;
+    float* scene_bounds; uint32_t *keys[2], *vals[2], *hist; int2 *children, *ranges; int *node_parent, *leaf_parent;
+    unsigned int *flags, *counters; float* sah;
+    const uint32_t n_tiles = (n + SORT_TILE - 1) / SORT_TILE;
+    if (!sc.alloc(&tri_lo, n, err) || !sc.alloc(&tri_hi, n, err) || !sc.alloc(&leaf_lo, n, err) || !sc.alloc(&leaf_hi, n, err) ||
+        !sc.alloc(&node_lo, n, err) || !sc.alloc(&node_hi, n, err) || !sc.alloc(&scene_bounds, 12, err) ||
+        !sc.alloc(&keys[0], n, err) || !sc.alloc(&keys[1], n, err) || !sc.alloc(&vals[0], n, err) || !sc.alloc(&vals[1], n, err) ||
+        !sc.alloc(&hist, (size_t)256 * n_tiles, err) || !sc.alloc(&children, n, err) || !sc.alloc(&ranges, n, err) ||
+        !sc.alloc(&node_parent, n, err) || !sc.alloc(&leaf_parent, n, err) || !sc.alloc(&flags, n, err) ||
+        !sc.alloc(&counters, 4, err) || !sc.alloc(&sah, 1, err))
+        return false;
+
+    const float init_bounds[12] = {FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
+    CK(cudaMemcpyAsync(scene_bounds, init_bounds, sizeof(init_bounds), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemsetAsync(flags, 0, (size_t)n * sizeof(unsigned int), stream));
+    CK(cudaMemsetAsync(counters, 0, 4 * sizeof(unsigned int), stream));
+    CK(cudaMemsetAsync(sah, 0, sizeof(float), stream));
+
+    const uint32_t B = 256, G = (n + B - 1) / B;
+    k_tri_bounds<<<G, B, 0, stream>>>(d_verts, n, tri_lo, tri_hi, scene_bounds);
+    k_morton<<<G, B, 0, stream>>>(tri_lo, tri_hi, n, scene_bounds, keys[0], vals[0]);
+    int cur = 0;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = pass * 8;
+        k_sort_hist<<<n_tiles, 32, 0, stream>>>(keys[cur], n, shift, hist, n_tiles);
+        k_sort_scan<<<1, 1024, 0, stream>>>(hist, 256u * n_tiles);
+        k_sort_scatter<<<n_tiles, 32, 0, stream>>>(keys[cur], vals[cur], n, shift, hist, n_tiles, keys[cur ^ 1], vals[cur ^ 1]);
+        cur ^= 1;
+    }
+    k_hierarchy<<<G, B, 0, stream>>>(keys[cur], (int)n, children, ranges, node_parent, leaf_parent);
+    k_leaf_boxes<<<G, B, 0, stream>>>(tri_lo, tri_hi, vals[cur], n, scene_bounds, leaf_lo, leaf_hi);
+    k_refit<<<G, B, 0, stream>>>(children, node_parent, leaf_parent, leaf_lo, leaf_hi, (int)n, node_lo, node_hi, flags, counters + 2);
+    k_emit_nodes<<<G, B, 0, stream>>>(children, ranges, node_parent, leaf_lo, leaf_hi, node_lo, node_hi, (int)n, max_leaf, d_nodes, counters, sah);
+    k_emit_tris<<<G, B, 0, stream>>>(d_verts, vals[cur], n, d_tris);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ev1, stream));
+
+    unsigned int h_counters[4]; float h_sah = 0.0f; float4 root_lo, root_hi;
+    CK(cudaMemcpyAsync(h_counters, counters, sizeof(h_counters), cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(&h_sah, sah, sizeof(float), cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(&root_lo, node_lo, sizeof(float4), cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(&root_hi, node_hi, sizeof(float4), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    float ms = 0.0f;
+    CK(cudaEventElapsedTime(&ms, ev0, ev1));
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+
+    const float dx = root_hi.x - root_lo.x, dy = root_hi.y - root_lo.y, dz = root_hi.z - root_lo.z;
+    const float root_area = dx * dy + dy * dz + dz * dx;
+    stats.num_nodes = h_counters[0]; stats.num_leaves = h_counters[1]; stats.max_depth = h_counters[2];
+    stats.sah_cost = root_area > 0.0f ? h_sah / root_area : 0.0f;
+    stats.build_ms = ms;
+    stats.bvh_bytes = (uint64_t)n_nodes * 64 + (uint64_t)n * 48;
+    if (stats.max_depth >= PTB_BVH_MAX_DEPTH) {
+        err = "BVH build: tree depth " + std::to_string(stats.max_depth) + " exceeds the traversal stack (" + std::to_string(PTB_BVH_MAX_DEPTH) + ")";
+        return false;
+    }
+    return true;
+}
+
+void free_bvh(DeviceBvh& b) {
+    if (b.nodes) cudaFree(b.nodes);
+    if (b.tris) cudaFree(b.tris);
+    b = DeviceBvh();
+}
+
+}  // namespace ptb

@@ -1,0 +1,25 @@
+// bvh_build.h -- device BVH object and its builder (bvh_build.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+
+#include "../../include/ptb.h"
+
+#define PTB_BVH_MAX_DEPTH 64  // traversal stack entries (bvh.cuh: PTB_BVH_STACK)
+
+namespace ptb {
+
+struct DeviceBvh {
+    float4* nodes = nullptr;  // n_nodes x 4 float4 (64 B each), layout in bvh.cuh
+    float4* tris = nullptr;   // n_tris x 3 float4 (48 B each), leaf order
+    uint32_t n_nodes = 0, n_tris = 0;
+};
+
+// d_verts: 3 float4 per triangle (the reference's vertex buffer, optixSphere.cpp:871-894).
+bool build_bvh(const float4* d_verts, uint32_t n_tris, const ptb_build_cfg& cfg, cudaStream_t stream, DeviceBvh& out,
+               ptb_build_stats& stats, std::string& err);
+void free_bvh(DeviceBvh& b);
+
+}  // namespace ptb

@@ -1,0 +1,148 @@
+// device_math.cuh -- scalar building blocks of the sm_100a kernels.
+//
+// Everything that feeds a hit decision or a radiance value is written in a
+// fixed operation order over IEEE single-precision +,-,*,/,sqrt and the whole
+// library is compiled with -fmad=false (no FMA contraction, default
+// -prec-div/-prec-sqrt), so results are bit-identical to the CPU oracle's
+// (oracle/oracle_math.h, g++ -ffp-contract=off).  No CUDA libm transcendental
+// is used on the radiance path: sin/cos/atan2/asin are the Cephes
+// single-precision algorithms (<= 2 ulp on the ranges used), pow(x,5) is
+// ((x*x)*(x*x))*x.  Only the 8-bit display transform uses powf.
+//
+// Vector helpers follow the OptiX SDK's sutil/vec_math.h semantics the
+// reference relies on (optixSphere.cu:10): v / s multiplies by 1.0f / s,
+// normalize(v) = v * (1.0f / sqrtf(dot(v,v))), lerp(a,b,t) = a + t*(b-a),
+// reflect(i,n) = i - 2.0f*n*dot(n,i), faceforward(n,i,r) = n*copysign(1,dot(i,r)).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define PTB_DEV __device__ __forceinline__
+
+namespace ptb {
+
+PTB_DEV float3 mk3(float x, float y, float z) { return make_float3(x, y, z); }
+PTB_DEV float3 mk3(float s) { return make_float3(s, s, s); }
+PTB_DEV float3 mk3(float4 v) { return make_float3(v.x, v.y, v.z); }
+
+PTB_DEV float3 operator+(float3 a, float3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+PTB_DEV float3 operator-(float3 a, float3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+PTB_DEV float3 operator-(float3 a) { return mk3(-a.x, -a.y, -a.z); }
+PTB_DEV float3 operator*(float3 a, float3 b) { return mk3(a.x * b.x, a.y * b.y, a.z * b.z); }
+PTB_DEV float3 operator*(float3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
+PTB_DEV float3 operator*(float s, float3 a) { return mk3(s * a.x, s * a.y, s * a.z); }
+PTB_DEV float3 operator+(float3 a, float s) { return mk3(a.x + s, a.y + s, a.z + s); }
+PTB_DEV float3 operator-(float3 a, float s) { return mk3(a.x - s, a.y - s, a.z - s); }
+PTB_DEV float3 operator/(float3 a, float3 b) { return mk3(a.x / b.x, a.y / b.y, a.z / b.z); }
+PTB_DEV float3 operator/(float3 a, float s) { float inv = 1.0f / s; return a * inv; }
+PTB_DEV float dot(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+PTB_DEV float3 cross(float3 a, float3 b) {
+    return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+PTB_DEV float length(float3 a) { return sqrtf(dot(a, a)); }
+PTB_DEV float3 normalize(float3 a) { float inv = 1.0f / sqrtf(dot(a, a)); return a * inv; }
+PTB_DEV float3 lerp(float3 a, float3 b, float t) { return a + t * (b - a); }
+PTB_DEV float4 lerp(float4 a, float4 b, float t) {
+    return make_float4(a.x + t * (b.x - a.x), a.y + t * (b.y - a.y), a.z + t * (b.z - a.z), a.w + t * (b.w - a.w));
+}
+PTB_DEV float clampf(float f, float a, float b) { return fmaxf(a, fminf(f, b)); }
+PTB_DEV float3 clamp3(float3 v, float a, float b) { return mk3(clampf(v.x, a, b), clampf(v.y, a, b), clampf(v.z, a, b)); }
+PTB_DEV float3 reflect(float3 i, float3 n) { return i - 2.0f * n * dot(n, i); }
+PTB_DEV float3 faceforward(float3 n, float3 i, float3 nref) { return n * copysignf(1.0f, dot(i, nref)); }
+PTB_DEV float comp(float3 v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : v.z); }
+
+// ---- RNG (optixSphere.cu:24-35) ----------------------------------------------
+// pcg_hash returns float in the reference: the 32-bit hash is rounded to float
+// and converted back (cvt.rzi.u32.f32 saturates 2^32 to 0xFFFFFFFF).
+PTB_DEV float pcg_hash_f(uint32_t input) {
+    uint32_t state = input * 747796405u + 2891336453u;
+    uint32_t word = ((state >> ((state >> 28u) + 4u)) ^ state) * 277803737u;
+    return (float)((word >> 22u) ^ word);
+}
+PTB_DEV float myrnd(uint32_t& seed) {
+    seed = (uint32_t)pcg_hash_f(seed);
+    return (float)seed / 4294967296.0f;  // (float)UINT_MAX == 2^32
+}
+
+// ---- detmath (same algorithms as oracle/oracle_math.h) -------------------------
+PTB_DEV void det_sincosf(float xx, float* s_out, float* c_out) {
+    const float FOPI = 1.27323954473516f;
+    const float DP1 = 0.78515625f, DP2 = 2.4187564849853515625e-4f, DP3 = 3.77489497744594108e-8f;
+    float x = fabsf(xx);
+    int j = (int)(FOPI * x);
+    float y = (float)j;
+    if (j & 1) { j += 1; y += 1.0f; }
+    j &= 7;
+    x = ((x - y * DP1) - y * DP2) - y * DP3;
+    float z = x * x;
+    float ps = ((-1.9515295891e-4f * z + 8.3321608736e-3f) * z - 1.6666654611e-1f) * z * x + x;
+    float pc = ((2.443315711809948e-5f * z - 1.388731625493765e-3f) * z + 4.166664568298827e-2f) * z * z - 0.5f * z + 1.0f;
+    float s, c;
+    if (j == 0) { s = ps; c = pc; }
+    else if (j == 2) { s = pc; c = -ps; }
+    else if (j == 4) { s = -ps; c = -pc; }
+    else { s = -pc; c = ps; }
+    if (xx < 0.0f) s = -s;
+    *s_out = s; *c_out = c;
+}
+PTB_DEV float det_atan_pos(float t) {
+    float y;
+    if (t > 2.414213562373095f) { y = 1.5707963267948966f; t = -(1.0f / t); }
+    else if (t > 0.4142135623730950f) { y = 0.7853981633974483f; t = (t - 1.0f) / (t + 1.0f); }
+    else y = 0.0f;
+    float z = t * t;
+    y += (((8.05374449538e-2f * z - 1.38776856032e-1f) * z + 1.99777106478e-1f) * z - 3.33329491539e-1f) * z * t + t;
+    return y;
+}
+PTB_DEV float det_atan2f(float y, float x) {
+    const float PI_F = 3.14159265358979323846f, PIO2_F = 1.5707963267948966f;
+    if (x == 0.0f) {
+        if (y > 0.0f) return PIO2_F;
+        if (y < 0.0f) return -PIO2_F;
+        return 0.0f;
+    }
+    if (y == 0.0f) return x > 0.0f ? 0.0f : PI_F;
+    float a = det_atan_pos(fabsf(y / x));
+    if (x < 0.0f) a = PI_F - a;
+    return y < 0.0f ? -a : a;
+}
+PTB_DEV float det_asinf(float xx) {
+    float a = fabsf(xx);
+    if (a > 1.0f) a = 1.0f;
+    float z, x;
+    bool big = a > 0.5f;
+    if (big) { z = 0.5f * (1.0f - a); x = sqrtf(z); }
+    else { x = a; z = x * x; }
+    float r = ((((4.2163199048e-2f * z + 2.4181311049e-2f) * z + 4.5470025998e-2f) * z + 7.4953002686e-2f) * z + 1.6666752422e-1f) * z * x + x;
+    if (big) { r = r + r; r = 1.5707963267948966f - r; }
+    return xx < 0.0f ? -r : r;
+}
+PTB_DEV float det_pow5(float x) { float x2 = x * x; float x4 = x2 * x2; return x4 * x; }
+
+// ---- orthonormal basis (optixSphere.cu:38-61) -----------------------------------
+struct Onb {
+    float3 t, b, n;
+    PTB_DEV explicit Onb(float3 normal) {
+        n = normalize(normal);
+        float3 up = fabsf(n.y) < 0.9999f ? mk3(0.0f, 1.0f, 0.0f) : mk3(1.0f, 0.0f, 0.0f);
+        t = normalize(cross(up, n));
+        b = normalize(cross(n, t));
+    }
+    PTB_DEV float3 inverse_transform(float3 p) const { return p.x * t + p.y * n + p.z * b; }
+};
+
+// ---- warp-aggregated queue append ---------------------------------------------------
+// All 32 lanes of the warp must call this (converged); lanes with pred == false
+// append nothing.  One atomicAdd per warp, order inside the warp is preserved.
+PTB_DEV void queue_push(uint32_t* __restrict__ queue, uint32_t* __restrict__ counter, bool pred, uint32_t value) {
+    const unsigned mask = __ballot_sync(0xffffffffu, pred);
+    if (mask == 0u) return;
+    const unsigned lane = threadIdx.x & 31u;
+    const int leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if ((int)lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (pred) queue[base + (uint32_t)__popc(mask & ((1u << lane) - 1u))] = value;
+}
+
+}  // namespace ptb

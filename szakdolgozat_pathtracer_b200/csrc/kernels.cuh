@@ -1,0 +1,494 @@
+// kernels.cuh -- the wavefront stages of the integrator for sm_100a.
+//
+// The reference is an OptiX megakernel: __raygen__rg loops over 10 samples and
+// up to 21 segments per pixel, calling optixTraverse + closest-hit/miss inline
+// (optixSphere.cu:297-436).  Here the same per-pixel state machine is cut into
+// stages that each run over a compacted queue of path slots:
+//   k_raygen_init   camera ray of sample 0 for every pixel      (cu:316-360)
+//   k_trace         BVH traversal + watertight triangle tests    (cu:99-112)
+//   k_shade         closest hit: GGX metallic-roughness sampling (cu:616-801, 858-871)
+//                   + the raygen-side Russian roulette           (cu:376-395)
+//   k_miss          equirect environment lookup                  (cu:531-567)
+//   k_resolve       accumulate + exposure/tonemap/gamma/contrast (cu:400-435)
+// A slot is one pixel; its samples run one after another because the reference
+// threads one RNG stream through all samples of a pixel (cu:317, 328, 383), so a
+// finished sample regenerates the next camera ray in place (path regeneration).
+// Queues are appended with one warp-aggregated atomic per warp (queue_push).
+#pragma once
+#include "bvh.cuh"
+
+namespace ptb {
+
+struct DevTexture { const void* data; int w, h; int fmt; };  // fmt: 0 none, 1 RGBA8, 2 float4
+struct DevMaterial {
+    DevTexture tex[4];  // albedo, roughness, normal, metallic
+    float emission[3], diffuse[3], specular[3];
+    float roughness;
+    int metallic;
+    int _pad;
+};
+
+struct SceneView {
+    const float4* nodes; const float4* tris;
+    const float4* verts; const float4* normals; const float2* uvs; const uint32_t* mat_ids;
+    const DevMaterial* mats;
+    const float4* env; int env_w, env_h;
+};
+
+struct FrameView {
+    uint32_t W, H;
+    int subframe, dof;
+    float3 eye, U, V, Wv;
+    int spp, max_depth;
+    float tmin, tmax, dof_blur, focus_dist, nmap_strength;
+    float exposure_scale, inv_gamma, contrast;
+    int accumulate_mode, write_frame;
+    float4* accum; uchar4* frame; int* aux_primary;
+};
+
+// Path pool, structure of arrays, one entry per pixel slot, 16-byte records.
+struct PathView {
+    float4* ray_o;       // origin.xyz, -
+    float4* ray_d;       // direction.xyz, -
+    float4* hit;         // t, b1, b2, prim (int bits)
+    float4* atten_seed;  // attenuation.xyz, payload.seed (uint bits)
+    uint4* misc;         // raygen seed, depth (int), sample index, -
+    float4* pixsum;      // sum of finished samples .xyz
+    uint32_t n_slots;
+};
+
+// counters[iter*4 + 0] = rays to trace in iteration iter, +1 = hits, +2 = misses
+struct QueueView {
+    uint32_t* trace[2];
+    uint32_t* hit;
+    uint32_t* miss;
+    uint32_t* counters;
+    unsigned long long* trav_stats;  // [0] nodes visited, [1] triangles tested
+};
+
+#define PTB_PI_F 3.14159265358979323846f
+
+// ---- camera ray of one sample (cu:326-347) ------------------------------------------
+PTB_DEV void start_sample(const FrameView& f, uint32_t ix, uint32_t iy, uint32_t& seed, float3& origin, float3& direction) {
+    const float jx = myrnd(seed);
+    const float jy = myrnd(seed);
+    const float dx = 2.0f * (((float)ix + jx) / (float)f.W) - 1.0f;
+    const float dy = 2.0f * (((float)iy + jy) / (float)f.H) - 1.0f;
+    if (f.dof) {
+        // defocus_disk_sample (cu:279-294): the seed is passed by value, the stream does not advance
+        uint32_t s2 = seed;
+        const float r = sqrtf(myrnd(s2));
+        const float theta = (float)(2.0f * 3.14159265358979323846 * (double)myrnd(s2));
+        float sn, cs; det_sincosf(theta, &sn, &cs);
+        const float x = f.dof_blur * sqrtf(r) * cs;
+        const float y = f.dof_blur * sqrtf(r) * sn;
+        origin = x * f.U + y * f.V;
+        const float3 target = f.focus_dist * (dx * f.U + dy * f.V + f.Wv);
+        direction = normalize(target - origin);
+        origin = origin + f.eye;
+    } else {
+        origin = f.eye;
+        direction = normalize(dx * f.U + dy * f.V + f.Wv);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_raygen_init(FrameView f, PathView p, QueueView q) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) q.counters[0] = p.n_slots;
+    if (i >= p.n_slots) return;
+    const uint32_t ix = i % f.W, iy = i / f.W;
+    uint32_t seed = iy * f.W + ix + (uint32_t)f.subframe * f.W * f.H;  // cu:316
+    float3 o, d;
+    start_sample(f, ix, iy, seed, o, d);
+    p.ray_o[i] = make_float4(o.x, o.y, o.z, 0.0f);
+    p.ray_d[i] = make_float4(d.x, d.y, d.z, 0.0f);
+    p.atten_seed[i] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(seed));
+    p.misc[i] = make_uint4(seed, (uint32_t)f.max_depth, 0u, 0u);
+    p.pixsum[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    q.trace[0][i] = i;
+}
+
+// ---- traversal stage ------------------------------------------------------------------
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_trace(SceneView s, FrameView f, PathView p, QueueView q, int iter) {
+    const uint32_t n = q.counters[iter * 4 + 0];
+    const uint32_t* __restrict__ in = q.trace[iter & 1];
+    TravCounters tc; tc.nodes = 0; tc.tris = 0;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; (i & ~31u) < n; i += stride) {
+        const bool active = i < n;
+        uint32_t slot = 0;
+        bool is_hit = false;
+        if (active) {
+            slot = in[i];
+            const float4 o4 = p.ray_o[slot], d4 = p.ray_d[slot];
+            const HitRec h = bvh_closest_hit<COUNT>(s.nodes, s.tris, mk3(o4), mk3(d4), f.tmin, f.tmax, &tc);
+            p.hit[slot] = make_float4(h.t, h.b1, h.b2, __int_as_float(h.prim));
+            is_hit = h.prim >= 0;
+            if (iter == 0 && f.aux_primary) f.aux_primary[slot] = h.prim;
+        }
+        queue_push(q.hit, &q.counters[iter * 4 + 1], active && is_hit, slot);
+        queue_push(q.miss, &q.counters[iter * 4 + 2], active && !is_hit, slot);
+    }
+    if (COUNT) {
+        unsigned long long a = tc.nodes, b = tc.tris;
+        for (int off = 16; off > 0; off >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, off); b += __shfl_xor_sync(0xffffffffu, b, off); }
+        if ((threadIdx.x & 31u) == 0u) { atomicAdd(&q.trav_stats[0], a); atomicAdd(&q.trav_stats[1], b); }
+    }
+}
+
+// ---- textures ---------------------------------------------------------------------------
+// Texel by the reference's linear index y*w + x (cu:518-521, 587-590); a negative
+// index (x0 or y0 == -1, an out-of-bounds read in the reference) wraps by +w*h.
+PTB_DEV float4 fetch_texel(const void* data, int fmt, int w, int h, int x, int y) {
+    int idx = y * w + x;
+    if (idx < 0) idx += w * h;
+    if (fmt == 1) {
+        const uchar4 c = __ldg((const uchar4*)data + idx);
+        return make_float4(c.x / 255.0f, c.y / 255.0f, c.z / 255.0f, c.w / 255.0f);  // optixSphere.cpp:370-373
+    }
+    return __ldg((const float4*)data + idx);
+}
+PTB_DEV float4 bilinear(const void* data, int fmt, int w, int h, int x0, int y0, float s, float t) {
+    const int x1 = (x0 + 1) % w, y1 = (y0 + 1) % h;
+    const float4 c00 = fetch_texel(data, fmt, w, h, x0, y0), c10 = fetch_texel(data, fmt, w, h, x1, y0);
+    const float4 c01 = fetch_texel(data, fmt, w, h, x0, y1), c11 = fetch_texel(data, fmt, w, h, x1, y1);
+    const float4 c0 = lerp(c00, c10, s), c1 = lerp(c01, c11, s);
+    return lerp(c0, c1, t);
+}
+// sampleTexture (cu:569-596)
+PTB_DEV float4 sample_texture(const DevTexture& tx, float u, float v) {
+    u = u - floorf(u);
+    v = v - floorf(v);
+    const float x = u * tx.w - 0.5f, y = v * tx.h - 0.5f;
+    const int x0 = (int)floorf(x), y0 = (int)floorf(y);
+    return bilinear(tx.data, tx.fmt, tx.w, tx.h, x0, y0, x - floorf(x), y - floorf(y));
+}
+// sampleHDRI (cu:503-529)
+PTB_DEV float4 sample_env(const float4* env, int w, int h, float u, float v) {
+    const float x = u * w - 0.5f, y = v * h - 0.5f;
+    const int x0 = (int)floorf(x) % w, y0 = (int)floorf(y) % h;
+    return bilinear(env, 2, w, h, x0, y0, x - floorf(x), y - floorf(y));
+}
+// setMaterialProperty (cu:598-613)
+PTB_DEV float3 material_property(const DevTexture& tx, float3 fallback, float u, float v) {
+    if (tx.fmt != 0) return mk3(sample_texture(tx, u, v));
+    return fallback;
+}
+
+// ---- BSDF helpers (cu:244-263, 439-500) ---------------------------------------------------
+PTB_DEV float3 cosine_sample_hemisphere(float u1, float u2) {
+    const float r = sqrtf(u1);
+    const float phi = 2.0f * PTB_PI_F * u2;
+    float s, c; det_sincosf(phi, &s, &c);
+    float3 p; p.x = r * c; p.z = r * s;
+    p.y = sqrtf(fmaxf(0.0f, 1.0f - p.x * p.x - p.z * p.z));
+    return p;
+}
+PTB_DEV void burn_random_in_unit_sphere(uint32_t& seed) {
+    float3 p;
+    do {
+        const float a = myrnd(seed), b = myrnd(seed), c = myrnd(seed);
+        p = 2.0f * mk3(a, b, c) - mk3(1.0f, 1.0f, 1.0f);
+    } while (p.x * p.x + p.y * p.y + p.z * p.z >= 1.0f);
+}
+PTB_DEV float D_GGX(float3 n, float3 h, float a) {
+    const float a2 = a * a;
+    const float NdotH = fmaxf(dot(n, h), 1e-10f);
+    const float NdotH2 = NdotH * NdotH;
+    float denom = (NdotH2 * (a2 - 1.0f) + 1.0f);
+    denom = PTB_PI_F * denom * denom;
+    return a2 / denom;
+}
+PTB_DEV float G_SchlickGGX(float alpha, float3 n, float3 x) {
+    const float numerator = fabsf(dot(n, x));
+    const float k = alpha / 2.0f;
+    float denominator = fabsf(dot(n, x)) * (1.0f - k) + k;
+    denominator = fmaxf(denominator, 1e-10f);
+    return numerator / denominator;
+}
+PTB_DEV float3 Fresnel_Schlick(float cosTheta, float3 F0) {
+    cosTheta = clampf(cosTheta, 0.0f, 1.0f);
+    return F0 + (mk3(1.0f) - F0) * det_pow5(1.0f - cosTheta);
+}
+PTB_DEV float Fresnel_Schlick_float(float cosine, float refraction_index) {
+    float r0 = (1.0f - refraction_index) / (1.0f + refraction_index);
+    r0 = r0 * r0;
+    return r0 + (1.0f - r0) * det_pow5(1.0f - cosine);
+}
+PTB_DEV float3 GGX_importance_sample(float r1, float r2, float alpha) {
+    const float phi = 2.0f * PTB_PI_F * r1;
+    const float cosTheta = sqrtf((1.0f - r2) / (1.0f + (alpha * alpha - 1.0f) * r2));
+    const float sinTheta = sqrtf(1.0f - cosTheta * cosTheta);
+    float s, c; det_sincosf(phi, &s, &c);
+    return normalize(mk3(sinTheta * c, cosTheta, sinTheta * s));
+}
+
+// What closest hit / miss hand back to the raygen-side logic (Payload, optixSphere.h:33-45).
+struct Bounce {
+    float3 atten, radiance, origin, direction;
+    uint32_t seed;
+    int done;
+};
+
+// __closesthit__radiance (cu:616-801, 858-871); the glass branch cu:803-856 is unreachable.
+PTB_DEV void closest_hit(const SceneView& s, const FrameView& f, int prim_idx, float b1, float b2, float t_hit,
+                         float3 ray_orig, float3 ray_dir, int depth, Bounce& io) {
+    const DevMaterial& m = s.mats[__ldg(s.mat_ids + prim_idx)];
+    const size_t vo = (size_t)prim_idx * 3;
+    const float3 v0 = mk3(__ldg(s.verts + vo)), v1 = mk3(__ldg(s.verts + vo + 1)), v2 = mk3(__ldg(s.verts + vo + 2));
+    float3 flat_normal = normalize(cross(v1 - v0, v2 - v0));
+    flat_normal = faceforward(flat_normal, -ray_dir, flat_normal);
+
+    // getPayloadCH (cu:160-172): radiance/origin/direction/done restart from zero
+    io.radiance = mk3(0.0f); io.origin = mk3(0.0f); io.direction = mk3(0.0f); io.done = 0;
+
+    const float3 n0 = mk3(__ldg(s.normals + vo)), n1 = mk3(__ldg(s.normals + vo + 1)), n2 = mk3(__ldg(s.normals + vo + 2));
+    const float bary_beta = b1, bary_gamma = b2;
+    const float bary_alpha = 1.0f - bary_beta - bary_gamma;
+    const float2 uv0 = __ldg(s.uvs + vo), uv1 = __ldg(s.uvs + vo + 1), uv2 = __ldg(s.uvs + vo + 2);
+    const float uvx = uv0.x * bary_alpha + uv1.x * bary_beta + uv2.x * bary_gamma;
+    float uvy = uv0.y * bary_alpha + uv1.y * bary_beta + uv2.y * bary_gamma;
+    uvy = 1.0f - uvy;
+
+    float3 normal = bary_alpha * n0 + bary_beta * n1 + bary_gamma * n2;
+    if (length(normal) > 0.01f) normal = normalize(normal);
+    else { io.done = 1; return; }
+    if (dot(normal, ray_dir) > 0.0f) normal = flat_normal;
+
+    const float3 hit_pos = ray_orig + t_hit * ray_dir;
+    uint32_t seed = io.seed;
+
+    const float3 diffuse_albedo = material_property(m.tex[0], mk3(m.diffuse[0], m.diffuse[1], m.diffuse[2]), uvx, uvy);
+    float3 normal_map = material_property(m.tex[2], mk3(0.0f, 1.0f, 0.0f), uvx, uvy);
+    if (m.tex[2].fmt != 0) {
+        normal_map = normalize(2.0f * normal_map - mk3(1.0f));
+        normal_map = mk3(normal_map.x, normal_map.z, normal_map.y);
+    }
+    {
+        const Onb onb_nmap(normal);
+        normal_map = onb_nmap.inverse_transform(normal_map);
+    }
+    normal = normalize(f.nmap_strength * normal_map + (1.0f - f.nmap_strength) * normal);
+    const float3 specular_albedo = diffuse_albedo;
+    const float3 emission_color = mk3(m.emission[0], m.emission[1], m.emission[2]);
+
+    float roughness = material_property(m.tex[1], mk3(m.roughness), uvx, uvy).x;
+    const float metallicity = material_property(m.tex[3], m.metallic ? mk3(1.0f) : mk3(0.0f), uvx, uvy).x;
+    const float ior = 1.5f;
+
+    if (length(emission_color) > 0.0001f) {
+        io.radiance = io.radiance + io.atten * emission_color;
+        io.done = 1;  // seed is not advanced (cu:725-731)
+        return;
+    }
+
+    burn_random_in_unit_sphere(seed);  // cu:733
+
+    if (roughness < 0.015f) roughness = 0.015f;
+    if (roughness > 0.999f) roughness = 0.999f;
+    if (depth <= 0) io.done = 1;
+
+    float r1 = myrnd(seed);
+    float r2 = myrnd(seed);
+    const float alpha = roughness * roughness;
+    float3 half_vec = GGX_importance_sample(r1, r2, alpha);
+    const Onb onb(normal);
+    half_vec = onb.inverse_transform(half_vec);
+
+    const float3 light_dir = reflect(ray_dir, half_vec);
+    r1 = myrnd(seed);
+    r2 = myrnd(seed);
+    float3 light_dir_diffuse = cosine_sample_hemisphere(r1, r2);
+    light_dir_diffuse = onb.inverse_transform(light_dir_diffuse);
+
+    const float f0s = (float)fabs((1.0 - (double)ior) / (1.0 + (double)ior));
+    float3 F0 = mk3(f0s);
+    F0 = F0 * F0;
+    F0 = lerp(F0, specular_albedo, metallicity);
+
+    const float3 F = Fresnel_Schlick(fmaxf(dot(normal, -ray_dir), 0.0f), F0);
+    const float D = D_GGX(normal, half_vec, alpha);
+    const float G = G_SchlickGGX(alpha, normal, -ray_dir) * G_SchlickGGX(alpha, normal, light_dir);
+    const float3 brdf_specular = F * D * G / (4.0f * fabsf(dot(normal, -ray_dir)) * fabsf(dot(normal, light_dir)));
+
+    const float NdotH = fmaxf(dot(normal, half_vec), 1e-10f);
+    const float VdotH = fmaxf(dot(-ray_dir, half_vec), 1e-10f);
+    const float NdotV = fmaxf(dot(normal, -ray_dir), 0.0f);
+    const float IdotN = fabsf(dot(normal, normalize(light_dir)));
+    const float F_blend_factor = Fresnel_Schlick_float(NdotV, ior);
+
+    const float specular_probability = metallicity + (1.0f - metallicity) * F_blend_factor;
+    const float spdf = D * NdotH / (4.0f * VdotH);
+    const float dpdf = 1.0f / PTB_PI_F;
+    if (myrnd(seed) < specular_probability) io.direction = normalize(light_dir);
+    else io.direction = normalize(light_dir_diffuse);
+    const float3 brdf = specular_probability * (brdf_specular / spdf) + (1.0f - specular_probability) * (diffuse_albedo / dpdf);
+
+    if (length(brdf) >= 1e-10f) io.atten = io.atten * (brdf * IdotN);
+    io.origin = hit_pos;
+    io.seed = seed;
+}
+
+// Raygen side after a segment (cu:376-395) plus path regeneration.  Returns true
+// when the slot has another ray to trace.
+PTB_DEV bool after_segment(const FrameView& f, const PathView& p, uint32_t slot, const Bounce& b, uint32_t seed_rg,
+                           int depth, uint32_t sample) {
+    const float pr = fmaxf(b.atten.x, fmaxf(b.atten.y, b.atten.z));
+    bool done = b.done != 0;
+    if (!done) done = myrnd(seed_rg) > pr;  // short-circuit: no draw when payload.done
+    if (!done) {
+        p.ray_o[slot] = make_float4(b.origin.x, b.origin.y, b.origin.z, 0.0f);
+        p.ray_d[slot] = make_float4(b.direction.x, b.direction.y, b.direction.z, 0.0f);
+        p.atten_seed[slot] = make_float4(b.atten.x, b.atten.y, b.atten.z, __uint_as_float(b.seed));
+        p.misc[slot] = make_uint4(seed_rg, (uint32_t)(depth - 1), sample, 0u);
+        return true;
+    }
+    // cu:384-387; a path with done && !(p > 0) loops forever in the reference: it contributes 0 here
+    const float3 path_rgb = pr > 0.0f ? b.radiance / pr : mk3(0.0f);
+    float4 sum = p.pixsum[slot];
+    sum.x = sum.x + path_rgb.x; sum.y = sum.y + path_rgb.y; sum.z = sum.z + path_rgb.z;
+    p.pixsum[slot] = sum;
+    sample += 1u;
+    if (sample >= (uint32_t)f.spp) return false;
+    float3 o, d;
+    start_sample(f, slot % f.W, slot / f.W, seed_rg, o, d);
+    p.ray_o[slot] = make_float4(o.x, o.y, o.z, 0.0f);
+    p.ray_d[slot] = make_float4(d.x, d.y, d.z, 0.0f);
+    p.atten_seed[slot] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(seed_rg));
+    p.misc[slot] = make_uint4(seed_rg, (uint32_t)f.max_depth, sample, 0u);
+    return true;
+}
+
+__global__ void __launch_bounds__(128) k_shade(SceneView s, FrameView f, PathView p, QueueView q, int iter) {
+    const uint32_t n = q.counters[iter * 4 + 1];
+    const uint32_t stride = gridDim.x * blockDim.x;
+    uint32_t* __restrict__ out = q.trace[(iter + 1) & 1];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; (i & ~31u) < n; i += stride) {
+        const bool active = i < n;
+        uint32_t slot = 0;
+        bool again = false;
+        if (active) {
+            slot = q.hit[i];
+            const float4 o4 = p.ray_o[slot], d4 = p.ray_d[slot], h4 = p.hit[slot], as = p.atten_seed[slot];
+            const uint4 mi = p.misc[slot];
+            Bounce b;
+            b.atten = mk3(as); b.seed = __float_as_uint(as.w);
+            const int depth = (int)mi.y;
+            closest_hit(s, f, __float_as_int(h4.w), h4.y, h4.z, h4.x, mk3(o4), mk3(d4), depth, b);
+            again = after_segment(f, p, slot, b, mi.x, depth, mi.z);
+        }
+        queue_push(out, &q.counters[(iter + 1) * 4 + 0], active && again, slot);
+    }
+}
+
+// __miss__radiance (cu:531-567): radiance += atten * env(dir); done.
+__global__ void __launch_bounds__(128) k_miss(SceneView s, FrameView f, PathView p, QueueView q, int iter) {
+    const uint32_t n = q.counters[iter * 4 + 2];
+    const uint32_t stride = gridDim.x * blockDim.x;
+    uint32_t* __restrict__ out = q.trace[(iter + 1) & 1];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; (i & ~31u) < n; i += stride) {
+        const bool active = i < n;
+        uint32_t slot = 0;
+        bool again = false;
+        if (active) {
+            slot = q.miss[i];
+            const float4 d4 = p.ray_d[slot], as = p.atten_seed[slot];
+            const uint4 mi = p.misc[slot];
+            const float3 ray_dir = normalize(mk3(d4));
+            const float u = 0.5f + det_atan2f(ray_dir.z, ray_dir.x) / (2.0f * PTB_PI_F);
+            const float v = 0.5f - det_asinf(ray_dir.y) / PTB_PI_F;
+            const float4 hdr = sample_env(s.env, s.env_w, s.env_h, u, v);
+            Bounce b;
+            b.atten = mk3(as); b.seed = __float_as_uint(as.w);
+            // the payload's radiance is 0 here: every closest hit that leaves the path alive stored 0 (cu:160-172, 206-208)
+            b.radiance = mk3(0.0f) + b.atten * mk3(hdr);
+            b.origin = mk3(0.0f); b.direction = mk3(0.0f);
+            b.done = 1;
+            again = after_segment(f, p, slot, b, mi.x, (int)mi.y, mi.z);
+        }
+        queue_push(out, &q.counters[(iter + 1) * 4 + 0], active && again, slot);
+    }
+}
+
+// ---- accumulate / tonemap (cu:400-435) --------------------------------------------------------
+PTB_DEV float3 tonemap_curve(float3 x) {
+    const float A = 0.15f, B = 0.50f, C = 0.10f, D = 0.20f, E = 0.02f, F = 0.30f;
+    return ((x * (A * x + C * B) + D * E) / (x * (A * x + B) + D * F)) - E / F;
+}
+PTB_DEV float to_srgb1(float c) {
+    const float invGamma = 1.0f / 2.4f;
+    const float powed = powf(c, invGamma);
+    return c < 0.0031308f ? 12.92f * c : 1.055f * powed - 0.055f;
+}
+PTB_DEV unsigned char quantize8(float x) {
+    x = clampf(x, 0.0f, 1.0f);
+    const unsigned int qv = (unsigned int)(x * 256.0f);
+    return (unsigned char)(qv < 255u ? qv : 255u);
+}
+// SDK cuda/helpers.h make_color (restated): clamp -> sRGB -> quantize
+PTB_DEV uchar4 display_color(float3 accum_color, float exposure_scale, float inv_gamma, float contrast) {
+    float3 rgb = accum_color * exposure_scale;
+    rgb = tonemap_curve(rgb);
+    rgb = clamp3(rgb, 0.0f, 1.0f);
+    rgb = mk3(powf(rgb.x, inv_gamma), powf(rgb.y, inv_gamma), powf(rgb.z, inv_gamma));
+    rgb = (rgb - 0.5f) * contrast + 0.5f;
+    const float3 c = clamp3(rgb, 0.0f, 1.0f);
+    return make_uchar4(quantize8(to_srgb1(c.x)), quantize8(to_srgb1(c.y)), quantize8(to_srgb1(c.z)), 255u);
+}
+
+__global__ void __launch_bounds__(256) k_resolve(FrameView f, PathView p) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n_slots) return;
+    const float4 sum = p.pixsum[i];
+    float3 accum_color = mk3(sum) / (float)f.spp;  // cu:401
+    if (f.accumulate_mode == 1) {
+        accum_color = mk3(f.accum[i]) + accum_color;
+    } else if (f.subframe > 0) {
+        const float a = 1.0f / (float)(f.subframe + 1);
+        accum_color = lerp(mk3(f.accum[i]), accum_color, a);  // cu:403-408
+    }
+    f.accum[i] = make_float4(accum_color.x, accum_color.y, accum_color.z, 1.0f);
+    if (f.write_frame && f.frame) f.frame[i] = display_color(accum_color, f.exposure_scale, f.inv_gamma, f.contrast);
+}
+
+// stand-alone accumulate/tonemap over an already reduced accumulator (multi-GPU sample split)
+__global__ void __launch_bounds__(256) k_resolve_scaled(const float4* __restrict__ accum, float4* __restrict__ accum_out,
+                                                        uchar4* __restrict__ frame, uint32_t n, float scale,
+                                                        float exposure_scale, float inv_gamma, float contrast) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 a = accum[i];
+    const float3 c = mk3(a) * scale;
+    if (accum_out) accum_out[i] = make_float4(c.x, c.y, c.z, 1.0f);
+    if (frame) frame[i] = display_color(c, exposure_scale, inv_gamma, contrast);
+}
+
+// ---- batch ray query + device self tests ----------------------------------------------------------
+__global__ void k_trace_rays(SceneView s, const float* __restrict__ origins, const float* __restrict__ dirs, uint32_t n,
+                             float tmin, float tmax, int* __restrict__ prim, float* __restrict__ t, float* __restrict__ b1,
+                             float* __restrict__ b2) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float3 o = mk3(origins[3 * (size_t)i], origins[3 * (size_t)i + 1], origins[3 * (size_t)i + 2]);
+    const float3 d = mk3(dirs[3 * (size_t)i], dirs[3 * (size_t)i + 1], dirs[3 * (size_t)i + 2]);
+    TravCounters tc;
+    const HitRec h = bvh_closest_hit<false>(s.nodes, s.tris, o, d, tmin, tmax, &tc);
+    if (prim) prim[i] = h.prim;
+    if (t) t[i] = h.t;
+    if (b1) b1[i] = h.b1;
+    if (b2) b2[i] = h.b2;
+}
+
+__global__ void k_test_math(int op, const float* __restrict__ in, int in_stride, float* __restrict__ out, int out_stride, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* a = in + (size_t)i * in_stride;
+    float* r = out + (size_t)i * out_stride;
+    if (op == 0) { uint32_t s = __float_as_uint(a[0]); const float u = myrnd(s); r[0] = __uint_as_float(s); r[1] = u; }
+    else if (op == 1) { float sn, cs; det_sincosf(a[0], &sn, &cs); r[0] = sn; r[1] = cs; }
+    else if (op == 2) r[0] = det_atan2f(a[0], a[1]);
+    else if (op == 3) r[0] = det_asinf(a[0]);
+}
+
+}  // namespace ptb

@@ -1,0 +1,472 @@
+// renderer.cu -- device half of the C ABI (include/ptb.h): context, scene upload,
+// BVH build entry, the wavefront launch loop, output buffers.
+//
+// One ptb_launch() = one optixLaunch of the reference (optixSphere.cpp:1403-1418):
+// every pixel renders spp_per_launch samples, the result is folded into
+// Params.accum_buffer and tonemapped into Params.frame_buffer.  Internally:
+//
+//   k_raygen_init
+//   repeat spp*(max_depth+1) times:   k_trace -> k_shade, k_miss
+//   k_resolve
+//
+// All kernels of a launch go to the caller's stream without any host
+// synchronisation; queue sizes live in device memory (one counter triple per
+// iteration, zeroed by a single memset at launch start), so an iteration whose
+// queue is empty costs three no-op launches.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "bvh_build.h"
+#include "host.h"
+#include "kernels.cuh"
+
+namespace ptb {
+
+struct DeviceScene {
+    int device = 0;
+    uint64_t revision = 0;
+    uint32_t n_tris = 0;
+    float4* verts = nullptr; float4* normals = nullptr; float2* uvs = nullptr; uint32_t* mat_ids = nullptr;
+    DevMaterial* mats = nullptr; int n_mats = 0;
+    std::vector<void*> textures;
+    float4* env = nullptr; int env_w = 0, env_h = 0;
+    DeviceBvh bvh;
+    unsigned long long handle = 0;
+    ptb_context* owner = nullptr;
+};
+
+void free_device_scene_buffers(DeviceScene* d) {
+    cudaFree(d->verts); cudaFree(d->normals); cudaFree(d->uvs); cudaFree(d->mat_ids); cudaFree(d->mats); cudaFree(d->env);
+    for (void* t : d->textures) cudaFree(t);
+    d->textures.clear();
+    d->verts = d->normals = nullptr; d->uvs = nullptr; d->mat_ids = nullptr; d->mats = nullptr; d->env = nullptr;
+    free_bvh(d->bvh);
+}
+
+}  // namespace ptb
+
+using namespace ptb;
+
+struct ptb_context {
+    int device = 0;
+    int num_sms = 148;
+    // path pool + queues, sized for the largest frame seen
+    uint32_t pool_slots = 0;
+    float4 *ray_o = nullptr, *ray_d = nullptr, *hit = nullptr, *atten_seed = nullptr, *pixsum = nullptr;
+    uint4* misc = nullptr;
+    uint32_t *q_trace[2] = {nullptr, nullptr}, *q_hit = nullptr, *q_miss = nullptr;
+    uint32_t* counters = nullptr; uint32_t counters_cap = 0;  // in iterations
+    unsigned long long* trav_stats = nullptr;
+    // last launch, for ptb_launch_get_stats
+    cudaStream_t last_stream = nullptr;
+    uint32_t last_iters = 0, last_kernels = 0;
+    uint64_t last_paths = 0;
+    bool last_counted = false;
+    std::map<unsigned long long, DeviceScene*> scenes;
+    unsigned long long next_handle = 1;
+};
+
+struct ptb_output {
+    ptb_context* ctx = nullptr;
+    uint32_t w = 0, h = 0;
+    uchar4* d_pixels = nullptr;
+    std::vector<ptb_uchar4> host;
+};
+
+namespace ptb {
+void free_device_scene(DeviceScene* d) {
+    if (!d) return;
+    cudaSetDevice(d->device);
+    if (d->owner) d->owner->scenes.erase(d->handle);
+    free_device_scene_buffers(d);
+    delete d;
+}
+}  // namespace ptb
+
+namespace {
+
+int fail(int code, const std::string& msg) { set_error(msg); return code; }
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(PTB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+
+template <typename T>
+cudaError_t upload(T** dst, const void* src, size_t bytes, cudaStream_t st) {
+    cudaError_t e = cudaMalloc((void**)dst, bytes ? bytes : 16);
+    if (e != cudaSuccess) return e;
+    if (bytes) e = cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, st);
+    return e;
+}
+
+void free_pool(ptb_context* c) {
+    cudaFree(c->ray_o); cudaFree(c->ray_d); cudaFree(c->hit); cudaFree(c->atten_seed); cudaFree(c->pixsum); cudaFree(c->misc);
+    cudaFree(c->q_trace[0]); cudaFree(c->q_trace[1]); cudaFree(c->q_hit); cudaFree(c->q_miss);
+    c->ray_o = c->ray_d = c->hit = c->atten_seed = c->pixsum = nullptr; c->misc = nullptr;
+    c->q_trace[0] = c->q_trace[1] = c->q_hit = c->q_miss = nullptr;
+    c->pool_slots = 0;
+}
+
+int ensure_pool(ptb_context* c, uint32_t slots, uint32_t iters) {
+    if (slots > c->pool_slots) {
+        free_pool(c);
+        const size_t n = slots;
+        CU(cudaMalloc((void**)&c->ray_o, n * 16)); CU(cudaMalloc((void**)&c->ray_d, n * 16));
+        CU(cudaMalloc((void**)&c->hit, n * 16)); CU(cudaMalloc((void**)&c->atten_seed, n * 16));
+        CU(cudaMalloc((void**)&c->pixsum, n * 16)); CU(cudaMalloc((void**)&c->misc, n * 16));
+        CU(cudaMalloc((void**)&c->q_trace[0], n * 4)); CU(cudaMalloc((void**)&c->q_trace[1], n * 4));
+        CU(cudaMalloc((void**)&c->q_hit, n * 4)); CU(cudaMalloc((void**)&c->q_miss, n * 4));
+        c->pool_slots = slots;
+    }
+    if (iters + 2 > c->counters_cap) {
+        cudaFree(c->counters); c->counters = nullptr; c->counters_cap = 0;
+        CU(cudaMalloc((void**)&c->counters, (size_t)(iters + 2) * 4 * sizeof(uint32_t)));
+        c->counters_cap = iters + 2;
+    }
+    if (!c->trav_stats) CU(cudaMalloc((void**)&c->trav_stats, 2 * sizeof(unsigned long long)));
+    return PTB_OK;
+}
+
+SceneView scene_view(const DeviceScene* d) {
+    SceneView s;
+    s.nodes = d->bvh.nodes; s.tris = d->bvh.tris;
+    s.verts = d->verts; s.normals = d->normals; s.uvs = d->uvs; s.mat_ids = d->mat_ids; s.mats = d->mats;
+    s.env = d->env; s.env_w = d->env_w; s.env_h = d->env_h;
+    return s;
+}
+
+DeviceScene* find_scene(ptb_context* ctx, unsigned long long handle) {
+    auto it = ctx->scenes.find(handle);
+    return it == ctx->scenes.end() ? nullptr : it->second;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ptb_context_create(int device, ptb_context** out) {
+    if (!out) return fail(PTB_ERR_INVALID, "ptb_context_create: null out");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(PTB_ERR_NO_DEVICE, std::string("no CUDA device is usable (") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") +
+                                           "); ptb has no CPU path");
+    if (device < 0 || device >= count) return fail(PTB_ERR_INVALID, "ptb_context_create: device index out of range");
+    CU(cudaSetDevice(device));
+    CU(cudaFree(0));  // the reference initialises the runtime the same way (optixSphere.cpp:801)
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    ptb_context* c = new ptb_context();
+    c->device = device; c->num_sms = prop.multiProcessorCount;
+    *out = c;
+    return PTB_OK;
+}
+
+void ptb_context_destroy(ptb_context* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    // scenes stay owned by their ptb_scene; just detach them
+    for (auto& kv : ctx->scenes) kv.second->owner = nullptr;
+    free_pool(ctx);
+    cudaFree(ctx->counters); cudaFree(ctx->trav_stats);
+    delete ctx;
+}
+
+int ptb_context_synchronize(ptb_context* ctx, void* stream) {
+    if (!ctx) return fail(PTB_ERR_INVALID, "ptb_context_synchronize: null context");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    return PTB_OK;
+}
+
+int ptb_accel_build(ptb_context* ctx, ptb_scene* scene, const ptb_build_cfg* cfg_in, void* stream_, unsigned long long* handle,
+                    ptb_build_stats* stats_out) {
+    if (!ctx || !scene || !handle) return fail(PTB_ERR_INVALID, "ptb_accel_build: bad arguments");
+    if (scene->env.empty()) return fail(PTB_ERR_INVALID, "ptb_accel_build: the scene has no environment map (ptb_scene_set_env_*)");
+    if (scene->mats.empty()) return fail(PTB_ERR_INVALID, "ptb_accel_build: the scene has no materials");
+    cudaStream_t st = (cudaStream_t)stream_;
+    CU(cudaSetDevice(ctx->device));
+    ptb_build_cfg cfg;
+    if (cfg_in) cfg = *cfg_in; else ptb_default_build_cfg(&cfg);
+
+    if (scene->dev) { free_device_scene(scene->dev); scene->dev = nullptr; }
+    DeviceScene* d = new DeviceScene();
+    d->device = ctx->device; d->revision = scene->revision;
+    const uint32_t n = (uint32_t)scene->tris.size();
+    d->n_tris = n;
+
+    // Flatten to the reference's vertex/normal/texcoord arrays, 3 entries per triangle (optixSphere.cpp:845-858).
+    std::vector<ptb_float4> verts((size_t)n * 3), normals((size_t)n * 3);
+    std::vector<ptb_float2> uvs((size_t)n * 3);
+    for (uint32_t i = 0; i < n; ++i) {
+        const ptb_TriangleData& t = scene->tris[i];
+        verts[(size_t)i * 3] = t.v0; verts[(size_t)i * 3 + 1] = t.v1; verts[(size_t)i * 3 + 2] = t.v2;
+        normals[(size_t)i * 3] = t.n0; normals[(size_t)i * 3 + 1] = t.n1; normals[(size_t)i * 3 + 2] = t.n2;
+        uvs[(size_t)i * 3] = t.uv0; uvs[(size_t)i * 3 + 1] = t.uv1; uvs[(size_t)i * 3 + 2] = t.uv2;
+    }
+    cudaError_t e = cudaSuccess;
+    auto ok = [&](cudaError_t r) { if (e == cudaSuccess) e = r; return r == cudaSuccess; };
+    ok(upload(&d->verts, verts.data(), verts.size() * sizeof(ptb_float4), st));
+    ok(upload(&d->normals, normals.data(), normals.size() * sizeof(ptb_float4), st));
+    ok(upload(&d->uvs, uvs.data(), uvs.size() * sizeof(ptb_float2), st));
+    ok(upload(&d->mat_ids, scene->mat_ids.data(), scene->mat_ids.size() * sizeof(uint32_t), st));
+    ok(upload(&d->env, scene->env.data(), scene->env.size() * sizeof(float), st));
+    d->env_w = scene->env_w; d->env_h = scene->env_h;
+
+    // hit-group table (optixSphere.cpp:1196-1261); every material owns its textures
+    std::vector<DevMaterial> dm(scene->mats.size());
+    for (size_t i = 0; i < scene->mats.size() && e == cudaSuccess; ++i) {
+        const Material& m = scene->mats[i];
+        DevMaterial& o = dm[i];
+        memset(&o, 0, sizeof(o));
+        for (int c = 0; c < 3; ++c) { o.emission[c] = m.emission_color[c]; o.diffuse[c] = m.diffuse_color[c]; o.specular[c] = m.specular[c]; }
+        o.roughness = m.roughness; o.metallic = m.metallic ? 1 : 0;
+        for (int k = 0; k < TEX_COUNT; ++k) {
+            const Texture& t = m.tex[k];
+            if (!t.has) continue;
+            void* p = nullptr;
+            const size_t bytes = t.is_float ? t.rgba32f.size() * sizeof(float) : t.rgba8.size();
+            if (!ok(upload((char**)&p, t.is_float ? (const void*)t.rgba32f.data() : (const void*)t.rgba8.data(), bytes, st))) break;
+            d->textures.push_back(p);
+            o.tex[k].data = p; o.tex[k].w = t.w; o.tex[k].h = t.h; o.tex[k].fmt = t.is_float ? 2 : 1;
+        }
+    }
+    ok(upload(&d->mats, dm.data(), dm.size() * sizeof(DevMaterial), st));
+    d->n_mats = (int)dm.size();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // host staging vectors go out of scope below
+    if (e != cudaSuccess) { free_device_scene_buffers(d); delete d; return fail(PTB_ERR_CUDA, std::string("scene upload: ") + cudaGetErrorString(e)); }
+
+    ptb_build_stats stats;
+    std::string err;
+    if (!build_bvh(d->verts, n, cfg, st, d->bvh, stats, err)) { free_device_scene_buffers(d); delete d; return fail(PTB_ERR_CUDA, err); }
+    d->handle = ctx->next_handle++;
+    d->owner = ctx;
+    ctx->scenes[d->handle] = d;
+    scene->dev = d;
+    *handle = d->handle;
+    if (stats_out) *stats_out = stats;
+    return PTB_OK;
+}
+
+int ptb_accel_read(ptb_context* ctx, unsigned long long handle, float* nodes, uint32_t cap_nodes, float* tris, uint32_t cap_tris,
+                   uint32_t* n_nodes, uint32_t* n_tris) {
+    if (!ctx) return fail(PTB_ERR_INVALID, "ptb_accel_read: null context");
+    DeviceScene* d = find_scene(ctx, handle);
+    if (!d) return fail(PTB_ERR_INVALID, "ptb_accel_read: unknown handle");
+    CU(cudaSetDevice(ctx->device));
+    if (n_nodes) *n_nodes = d->bvh.n_nodes;
+    if (n_tris) *n_tris = d->bvh.n_tris;
+    if (nodes) {
+        if (cap_nodes < d->bvh.n_nodes) return fail(PTB_ERR_INVALID, "ptb_accel_read: node buffer too small");
+        CU(cudaMemcpy(nodes, d->bvh.nodes, (size_t)d->bvh.n_nodes * 64, cudaMemcpyDeviceToHost));
+    }
+    if (tris) {
+        if (cap_tris < d->bvh.n_tris) return fail(PTB_ERR_INVALID, "ptb_accel_read: triangle buffer too small");
+        CU(cudaMemcpy(tris, d->bvh.tris, (size_t)d->bvh.n_tris * 48, cudaMemcpyDeviceToHost));
+    }
+    return PTB_OK;
+}
+
+int ptb_launch(ptb_context* ctx, const ptb_Params* P, const ptb_render_cfg* cfg_in, void* stream_) {
+    if (!ctx || !P) return fail(PTB_ERR_INVALID, "ptb_launch: bad arguments");
+    ptb_render_cfg cfg;
+    if (cfg_in) cfg = *cfg_in; else ptb_default_render_cfg(&cfg);
+    if (P->image_width == 0 || P->image_height == 0) return fail(PTB_ERR_INVALID, "ptb_launch: empty image");
+    if ((uint64_t)P->image_width * P->image_height > 0x7fffffffull) return fail(PTB_ERR_INVALID, "ptb_launch: image too large");
+    if (!P->accum_buffer) return fail(PTB_ERR_INVALID, "ptb_launch: Params.accum_buffer is null");
+    if (cfg.write_frame && !P->frame_buffer) return fail(PTB_ERR_INVALID, "ptb_launch: Params.frame_buffer is null (set write_frame = 0 to skip tonemapping)");
+    if (cfg.spp_per_launch < 1 || cfg.max_depth < 0 || cfg.max_depth > 1000) return fail(PTB_ERR_INVALID, "ptb_launch: bad spp_per_launch / max_depth");
+    if (cfg.env_importance_sampling) return fail(PTB_ERR_UNSUPPORTED, "env importance sampling cannot reproduce the reference estimator and is not implemented");
+    DeviceScene* d = find_scene(ctx, P->handle);
+    if (!d) return fail(PTB_ERR_INVALID, "ptb_launch: Params.handle does not name a built acceleration structure");
+    cudaStream_t st = (cudaStream_t)stream_;
+    CU(cudaSetDevice(ctx->device));
+
+    const uint32_t slots = P->image_width * P->image_height;
+    const uint32_t iters = (uint32_t)cfg.spp_per_launch * (uint32_t)(cfg.max_depth + 1);
+    int rc = ensure_pool(ctx, slots, iters);
+    if (rc != PTB_OK) return rc;
+
+    FrameView f;
+    f.W = P->image_width; f.H = P->image_height; f.subframe = P->subframe_index; f.dof = P->dof ? 1 : 0;
+    f.eye = make_float3(P->eye.x, P->eye.y, P->eye.z); f.U = make_float3(P->U.x, P->U.y, P->U.z);
+    f.V = make_float3(P->V.x, P->V.y, P->V.z); f.Wv = make_float3(P->W.x, P->W.y, P->W.z);
+    f.spp = cfg.spp_per_launch; f.max_depth = cfg.max_depth; f.tmin = cfg.tmin; f.tmax = cfg.tmax;
+    f.dof_blur = cfg.dof_blur; f.focus_dist = cfg.focus_dist; f.nmap_strength = cfg.nmap_strength;
+    f.exposure_scale = exp2f(cfg.exposure); f.inv_gamma = 1.0f / cfg.gamma; f.contrast = cfg.contrast;
+    f.accumulate_mode = cfg.accumulate_mode; f.write_frame = cfg.write_frame;
+    f.accum = (float4*)P->accum_buffer; f.frame = (uchar4*)P->frame_buffer; f.aux_primary = cfg.aux_primary_hit;
+
+    PathView p;
+    p.ray_o = ctx->ray_o; p.ray_d = ctx->ray_d; p.hit = ctx->hit; p.atten_seed = ctx->atten_seed; p.misc = ctx->misc;
+    p.pixsum = ctx->pixsum; p.n_slots = slots;
+    QueueView q;
+    q.trace[0] = ctx->q_trace[0]; q.trace[1] = ctx->q_trace[1]; q.hit = ctx->q_hit; q.miss = ctx->q_miss;
+    q.counters = ctx->counters; q.trav_stats = ctx->trav_stats;
+    const SceneView s = scene_view(d);
+
+    CU(cudaMemsetAsync(ctx->counters, 0, (size_t)(iters + 2) * 4 * sizeof(uint32_t), st));
+    CU(cudaMemsetAsync(ctx->trav_stats, 0, 2 * sizeof(unsigned long long), st));
+    const uint32_t pix_blocks = (slots + 255u) / 256u;
+    k_raygen_init<<<pix_blocks, 256, 0, st>>>(f, p, q);
+    // Persistent-style grids: a multiple of the SM count, looping over the queue.
+    const uint32_t need = (slots + 127u) / 128u;
+    const uint32_t cap = (uint32_t)ctx->num_sms * 32u;
+    const uint32_t grid = need < cap ? need : cap;
+    uint32_t launches = 1;
+    for (uint32_t it = 0; it < iters; ++it) {
+        if (cfg.count_traversal) k_trace<true><<<grid, 128, 0, st>>>(s, f, p, q, (int)it);
+        else k_trace<false><<<grid, 128, 0, st>>>(s, f, p, q, (int)it);
+        k_shade<<<grid, 128, 0, st>>>(s, f, p, q, (int)it);
+        k_miss<<<grid, 128, 0, st>>>(s, f, p, q, (int)it);
+        launches += 3;
+    }
+    k_resolve<<<pix_blocks, 256, 0, st>>>(f, p);
+    launches += 1;
+    CU(cudaGetLastError());
+    ctx->last_stream = st; ctx->last_iters = iters; ctx->last_kernels = launches;
+    ctx->last_paths = (uint64_t)slots * (uint64_t)cfg.spp_per_launch; ctx->last_counted = cfg.count_traversal != 0;
+    return PTB_OK;
+}
+
+int ptb_launch_get_stats(ptb_context* ctx, ptb_launch_stats* out) {
+    if (!ctx || !out) return fail(PTB_ERR_INVALID, "ptb_launch_get_stats: bad arguments");
+    memset(out, 0, sizeof(*out));
+    if (!ctx->last_iters) return fail(PTB_ERR_INVALID, "ptb_launch_get_stats: no launch yet");
+    CU(cudaSetDevice(ctx->device));
+    std::vector<uint32_t> h((size_t)(ctx->last_iters + 1) * 4);
+    CU(cudaMemcpyAsync(h.data(), ctx->counters, h.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->last_stream));
+    unsigned long long tv[2] = {0, 0};
+    CU(cudaMemcpyAsync(tv, ctx->trav_stats, sizeof(tv), cudaMemcpyDeviceToHost, ctx->last_stream));
+    CU(cudaStreamSynchronize(ctx->last_stream));
+    uint32_t used = 0;
+    for (uint32_t it = 0; it < ctx->last_iters; ++it) {
+        out->segments += h[(size_t)it * 4 + 0]; out->hits += h[(size_t)it * 4 + 1]; out->misses += h[(size_t)it * 4 + 2];
+        if (h[(size_t)it * 4 + 0]) used = it + 1;
+    }
+    out->paths = ctx->last_paths; out->iterations = used; out->kernel_launches = ctx->last_kernels;
+    if (ctx->last_counted) { out->nodes_visited = tv[0]; out->tris_tested = tv[1]; }
+    return PTB_OK;
+}
+
+int ptb_resolve(ptb_context* ctx, const ptb_float4* accum, ptb_float4* accum_out, ptb_uchar4* frame, uint32_t n_pixels, float scale,
+                const ptb_render_cfg* cfg_in, void* stream_) {
+    if (!ctx || !accum || !n_pixels) return fail(PTB_ERR_INVALID, "ptb_resolve: bad arguments");
+    ptb_render_cfg cfg;
+    if (cfg_in) cfg = *cfg_in; else ptb_default_render_cfg(&cfg);
+    CU(cudaSetDevice(ctx->device));
+    k_resolve_scaled<<<(n_pixels + 255u) / 256u, 256, 0, (cudaStream_t)stream_>>>((const float4*)accum, (float4*)accum_out, (uchar4*)frame,
+                                                                                 n_pixels, scale, exp2f(cfg.exposure), 1.0f / cfg.gamma, cfg.contrast);
+    CU(cudaGetLastError());
+    return PTB_OK;
+}
+
+int ptb_trace_rays(ptb_context* ctx, unsigned long long handle, const float* d_origins, const float* d_dirs, uint32_t n, float tmin,
+                   float tmax, int32_t* d_prim, float* d_t, float* d_b1, float* d_b2, void* stream_) {
+    if (!ctx || !d_origins || !d_dirs) return fail(PTB_ERR_INVALID, "ptb_trace_rays: bad arguments");
+    DeviceScene* d = find_scene(ctx, handle);
+    if (!d) return fail(PTB_ERR_INVALID, "ptb_trace_rays: unknown handle");
+    CU(cudaSetDevice(ctx->device));
+    if (n) k_trace_rays<<<(n + 127u) / 128u, 128, 0, (cudaStream_t)stream_>>>(scene_view(d), d_origins, d_dirs, n, tmin, tmax, d_prim, d_t, d_b1, d_b2);
+    CU(cudaGetLastError());
+    return PTB_OK;
+}
+
+// ---- output buffer -------------------------------------------------------------------------
+int ptb_output_create(ptb_context* ctx, uint32_t width, uint32_t height, ptb_output** out) {
+    if (!ctx || !out || !width || !height) return fail(PTB_ERR_INVALID, "ptb_output_create: bad arguments");
+    CU(cudaSetDevice(ctx->device));
+    ptb_output* o = new ptb_output();
+    o->ctx = ctx;
+    int rc = ptb_output_resize(o, width, height);
+    if (rc != PTB_OK) { delete o; return rc; }
+    *out = o;
+    return PTB_OK;
+}
+int ptb_output_resize(ptb_output* ob, uint32_t width, uint32_t height) {
+    if (!ob || !width || !height) return fail(PTB_ERR_INVALID, "ptb_output_resize: bad arguments");
+    CU(cudaSetDevice(ob->ctx->device));
+    if (ob->d_pixels) { cudaFree(ob->d_pixels); ob->d_pixels = nullptr; }
+    CU(cudaMalloc((void**)&ob->d_pixels, (size_t)width * height * sizeof(uchar4)));
+    ob->w = width; ob->h = height; ob->host.clear();
+    return PTB_OK;
+}
+ptb_uchar4* ptb_output_map(ptb_output* ob) { return ob ? (ptb_uchar4*)ob->d_pixels : nullptr; }
+void ptb_output_unmap(ptb_output* ob, void* stream) {
+    if (!ob) return;
+    cudaSetDevice(ob->ctx->device);
+    cudaStreamSynchronize((cudaStream_t)stream);  // CUDAOutputBuffer::unmap synchronises its stream
+}
+const ptb_uchar4* ptb_output_host_ptr(ptb_output* ob) {
+    if (!ob) return nullptr;
+    cudaSetDevice(ob->ctx->device);
+    ob->host.resize((size_t)ob->w * ob->h);
+    if (cudaMemcpy(ob->host.data(), ob->d_pixels, ob->host.size() * sizeof(uchar4), cudaMemcpyDeviceToHost) != cudaSuccess) {
+        set_error("ptb_output_host_ptr: device to host copy failed");
+        return nullptr;
+    }
+    return ob->host.data();
+}
+uint32_t ptb_output_width(const ptb_output* ob) { return ob ? ob->w : 0; }
+uint32_t ptb_output_height(const ptb_output* ob) { return ob ? ob->h : 0; }
+void ptb_output_destroy(ptb_output* ob) {
+    if (!ob) return;
+    cudaSetDevice(ob->ctx->device);
+    cudaFree(ob->d_pixels);
+    delete ob;
+}
+
+// ---- device memory helpers -----------------------------------------------------------------
+int ptb_device_alloc(ptb_context* ctx, size_t bytes, void** out) {
+    if (!ctx || !out) return fail(PTB_ERR_INVALID, "ptb_device_alloc: bad arguments");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMalloc(out, bytes ? bytes : 16));
+    return PTB_OK;
+}
+int ptb_device_free(ptb_context* ctx, void* p) {
+    if (!ctx) return fail(PTB_ERR_INVALID, "ptb_device_free: null context");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaFree(p));
+    return PTB_OK;
+}
+int ptb_device_memset(ptb_context* ctx, void* p, int value, size_t bytes, void* stream) {
+    if (!ctx || !p) return fail(PTB_ERR_INVALID, "ptb_device_memset: bad arguments");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemsetAsync(p, value, bytes, (cudaStream_t)stream));
+    return PTB_OK;
+}
+int ptb_copy_to_device(ptb_context* ctx, void* dst, const void* src, size_t bytes, void* stream) {
+    if (!ctx || !dst || !src) return fail(PTB_ERR_INVALID, "ptb_copy_to_device: bad arguments");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return PTB_OK;
+}
+int ptb_copy_to_host(ptb_context* ctx, void* dst, const void* src, size_t bytes, void* stream) {
+    if (!ctx || !dst || !src) return fail(PTB_ERR_INVALID, "ptb_copy_to_host: bad arguments");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    return PTB_OK;
+}
+
+int ptb_test_device_math(ptb_context* ctx, int op, const float* in, int in_stride, float* out, int out_stride, uint32_t n) {
+    if (!ctx || !in || !out || in_stride < 1 || out_stride < 1 || op < 0 || op > 3) return fail(PTB_ERR_INVALID, "ptb_test_device_math: bad arguments");
+    CU(cudaSetDevice(ctx->device));
+    float *d_in = nullptr, *d_out = nullptr;
+    CU(cudaMalloc((void**)&d_in, (size_t)n * in_stride * sizeof(float) + 16));
+    if (cudaMalloc((void**)&d_out, (size_t)n * out_stride * sizeof(float) + 16) != cudaSuccess) { cudaFree(d_in); return fail(PTB_ERR_CUDA, "cudaMalloc failed"); }
+    cudaMemcpy(d_in, in, (size_t)n * in_stride * sizeof(float), cudaMemcpyHostToDevice);
+    cudaMemset(d_out, 0, (size_t)n * out_stride * sizeof(float));
+    if (n) k_test_math<<<(n + 255u) / 256u, 256>>>(op, d_in, in_stride, d_out, out_stride, n);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(out, d_out, (size_t)n * out_stride * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(d_in); cudaFree(d_out);
+    if (e != cudaSuccess) return fail(PTB_ERR_CUDA, std::string("ptb_test_device_math: ") + cudaGetErrorString(e));
+    return PTB_OK;
+}
+
+}  // extern "C"
