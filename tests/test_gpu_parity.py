@@ -1,0 +1,214 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle.
+
+Bars (BASELINE.json north_star): primary-hit triangle IDs bit-exact, accumulation
+buffer bit-exact (the kernels and the oracle share one fixed IEEE operation order
+and the same deterministic sin/cos/atan2/asin), 8-bit frame within 1 LSB (the
+display transform uses CUDA powf vs glibc powf).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from scenes import CAMERAS, load_config, random_rays
+
+pytestmark = pytest.mark.gpu
+
+
+def _render_gpu(ptb, ctx, handle, W, H, cfg_kw, subframes=1, dof=True, camera="default", accum0=None):
+    n = W * H
+    d_accum, d_frame, d_hits = ctx.alloc(n * 16), ctx.alloc(n * 4), ctx.alloc(n * 4)
+    try:
+        if accum0 is not None:
+            ctx.to_device(d_accum, accum0)
+        else:
+            ctx.memset(d_accum, 0, n * 16)
+        ctx.memset(d_hits, 0xFF, n * 4)
+        stats = []
+        for sf in range(subframes):
+            p = ptb.make_params(W, H, subframe_index=sf, dof=dof, **CAMERAS[camera])
+            p.accum_buffer, p.frame_buffer, p.handle = d_accum, d_frame, handle
+            cfg = ptb.default_render_cfg(aux_primary_hit=d_hits if sf == 0 else None, **cfg_kw)
+            ctx.launch(p, cfg)
+            stats.append(ctx.launch_stats())
+        accum = ctx.to_host(d_accum, (H, W, 4), np.float32)
+        frame = ctx.to_host(d_frame, (H, W, 4), np.uint8)
+        hits = ctx.to_host(d_hits, (H, W), np.int32)
+    finally:
+        for b in (d_accum, d_frame, d_hits):
+            ctx.free(b)
+    return accum, frame, hits, stats
+
+
+def _render_cpu(oh, ptb, osc, W, H, cfg_kw, subframes=1, dof=True, camera="default"):
+    accum = np.zeros((H, W, 4), np.float32)
+    hits0 = None
+    seg = 0
+    for sf in range(subframes):
+        p = ptb.make_params(W, H, subframe_index=sf, dof=dof, **CAMERAS[camera])
+        a, frame, hits, st, rc = oh.render("oracle", osc, oh.params_from_ptb(p), oh.default_config("oracle", **cfg_kw), accum=accum)
+        assert rc == 0
+        seg += st.segments
+        if sf == 0:
+            hits0 = hits
+    return accum, frame, hits0, seg
+
+
+def test_device_math_bit_exact(ptb, ctx, oh):
+    rng = np.random.default_rng(7)
+    L = oh.load("oracle")
+    # RNG incl. the 128 seeds whose hash rounds to 2^32 is covered statistically + by the CPU KAT test
+    seeds = np.concatenate([np.arange(0, 4096, dtype=np.uint32), rng.integers(0, 2**32, 60000, dtype=np.uint32)])
+    out = ctx.test_device_math(0, seeds.view(np.float32).reshape(-1, 1), 2)
+    for i in range(0, len(seeds), 97):
+        u = C.c_float()
+        nxt = L.orc_rng_next(C.c_uint32(int(seeds[i])), 1, C.byref(u))
+        assert out[i, 0:1].view(np.uint32)[0] == nxt and out[i, 1] == u.value
+    x = np.concatenate([np.linspace(0, 6.2831855, 20001, dtype=np.float32), rng.random(20000, dtype=np.float32) * 6.2831855])
+    sc = ctx.test_device_math(1, x.reshape(-1, 1), 2)
+    s, c = C.c_float(), C.c_float()
+    ref = np.zeros_like(sc)
+    for i, v in enumerate(x):
+        L.orc_sincos(C.c_float(float(v)), C.byref(s), C.byref(c))
+        ref[i] = (s.value, c.value)
+    assert np.array_equal(sc.view(np.uint32), ref.view(np.uint32))
+    assert np.abs(ref[:, 0] - np.sin(x.astype(np.float64))).max() < 3e-7
+    yx = (rng.random((20000, 2), dtype=np.float32) * 2 - 1).astype(np.float32)
+    at = ctx.test_device_math(2, yx, 1)[:, 0]
+    ref = np.array([L.orc_atan2(float(a), float(b)) for a, b in yx], np.float32)
+    assert np.array_equal(at.view(np.uint32), ref.view(np.uint32))
+    assert np.abs(ref - np.arctan2(yx[:, 0].astype(np.float64), yx[:, 1].astype(np.float64))).max() < 5e-7
+    xs = np.concatenate([np.linspace(-1, 1, 10001, dtype=np.float32), (rng.random(10000, dtype=np.float32) * 2 - 1)])
+    asn = ctx.test_device_math(3, xs.reshape(-1, 1), 1)[:, 0]
+    ref = np.array([L.orc_asin(float(a)) for a in xs], np.float32)
+    assert np.array_equal(asn.view(np.uint32), ref.view(np.uint32))
+
+
+def _check_bvh(nodes, tris, n_tris, max_leaf):
+    """Structural validation of the flattened BVH read back from the device."""
+    codes = nodes[:, 12:14].view(np.int32)
+    seen = np.zeros(n_tris, np.int32)
+    stack = [0]
+    visited = 0
+    prim_ids = tris[:, 3].view(np.int32)
+    tv = tris.reshape(-1, 3, 4)[:, :, :3]
+    while stack:
+        ni = stack.pop()
+        visited += 1
+        n = nodes[ni]
+        boxes = [(np.array([n[0], n[2], n[8]]), np.array([n[1], n[3], n[9]])), (np.array([n[4], n[6], n[10]]), np.array([n[5], n[7], n[11]]))]
+        for c in range(2):
+            code = int(codes[ni, c])
+            lo, hi = boxes[c]
+            if code >= 0:
+                # child box must contain the grandchildren boxes
+                cn = nodes[code]
+                clo = np.minimum([cn[0], cn[2], cn[8]], [cn[4], cn[6], cn[10]])
+                chi = np.maximum([cn[1], cn[3], cn[9]], [cn[5], cn[7], cn[11]])
+                assert np.all(clo >= lo) and np.all(chi <= hi)
+                stack.append(code)
+            else:
+                k = ~code
+                first, cnt = k >> 3, (k & 7) + 1
+                assert cnt <= max(max_leaf, 1) and first + cnt <= n_tris
+                seen[first:first + cnt] += 1
+                v = tv[first:first + cnt].reshape(-1, 3)
+                assert np.all(v.min(0) >= lo) and np.all(v.max(0) <= hi)
+    assert np.all(seen == 1), "every triangle must be referenced by exactly one leaf"
+    assert sorted(prim_ids.tolist()) == list(range(n_tris))
+    return visited
+
+
+@pytest.mark.parametrize("name,small", [("c1", True), ("c2", False)])
+def test_bvh_structure_and_ray_queries(ptb, ctx, oh, assets, name, small):
+    sc = load_config(ptb, assets, name, small=small)
+    handle, st = ctx.accel_build(sc)
+    assert st.num_triangles == sc.num_triangles and st.max_depth < 64
+    nodes, tris = ctx.accel_read(handle)
+    _check_bvh(nodes, tris, sc.num_triangles, 4)
+    osc = oh.OracleScene.from_ptb(sc, guard=False)
+    v = osc.vertices[:, :3]
+    # leave the 400-unit floor out of the sampling box so that rays concentrate on the mesh
+    lo, hi = v[:-6].min(0), v[:-6].max(0)
+    rng = np.random.default_rng(123)
+    o, d = random_rays(rng, 20000, lo, hi)
+    prim, t, b1, b2 = ctx.trace_rays(handle, o, d)
+    mism = 0
+    for i in range(0, len(o), 1 if name == "c1" else 10):
+        rp, rt, rb1, rb2 = oh.closest_hit("oracle", osc, o[i], d[i], use_bvh=0)
+        if rp != prim[i]:
+            mism += 1
+            continue
+        if rp >= 0:
+            assert np.float32(rt) == t[i] and np.float32(rb1) == b1[i] and np.float32(rb2) == b2[i]
+    assert mism == 0
+    assert (prim >= 0).mean() > 0.2
+
+
+def test_c1_image_bit_exact_default_config(ptb, ctx, oh, assets):
+    """Reference literals (10 spp, depth 20, DoF on), two subframes: accum bit-exact, frame within 1 LSB."""
+    sc = load_config(ptb, assets, "c1", small=True)
+    handle, _ = ctx.accel_build(sc)
+    osc = oh.OracleScene.from_ptb(sc, guard=False)
+    W, H = 160, 96
+    ga, gf, gh, gst = _render_gpu(ptb, ctx, handle, W, H, {}, subframes=2)
+    ca, cf, ch, cseg = _render_cpu(oh, ptb, osc, W, H, {}, subframes=2)
+    assert np.array_equal(gh, ch), f"{(gh != ch).sum()} primary-hit mismatches"
+    assert sum(s.segments for s in gst) == cseg
+    bad = (ga.view(np.uint32) != ca.view(np.uint32)).any(axis=2)
+    assert bad.sum() == 0, f"{bad.sum()} of {W * H} accum pixels differ; max abs diff {np.abs(ga - ca).max()}"
+    assert np.abs(gf.astype(np.int32) - cf.astype(np.int32)).max() <= 1
+
+
+@pytest.mark.parametrize("dof", [False, True])
+def test_c1_hit_ids_512(ptb, ctx, oh, assets, dof):
+    """BASELINE config 1: 512x512, 1 spp, depth 4."""
+    sc = load_config(ptb, assets, "c1", small=False)
+    handle, _ = ctx.accel_build(sc)
+    osc = oh.OracleScene.from_ptb(sc, guard=False)
+    kw = dict(spp_per_launch=1, max_depth=4)
+    ga, gf, gh, gst = _render_gpu(ptb, ctx, handle, 512, 512, kw, dof=dof)
+    ca, cf, ch, cseg = _render_cpu(oh, ptb, osc, 512, 512, kw, dof=dof)
+    assert np.array_equal(gh, ch)
+    assert gst[0].segments == cseg
+    assert np.array_equal(ga.view(np.uint32), ca.view(np.uint32))
+
+
+def test_c2_monkey_parity_crop(ptb, ctx, oh, assets):
+    """BASELINE config 2 scene (monkey + albedo map), close camera, 8 spp depth 8 at 320x180: bit-exact."""
+    sc = load_config(ptb, assets, "c2")
+    handle, st = ctx.accel_build(sc)
+    osc = oh.OracleScene.from_ptb(sc, guard=False)
+    kw = dict(spp_per_launch=8, max_depth=8)
+    W, H = 320, 180
+    ga, gf, gh, gst = _render_gpu(ptb, ctx, handle, W, H, kw, camera="monkey_close")
+    ca, cf, ch, cseg = _render_cpu(oh, ptb, osc, W, H, kw, camera="monkey_close")
+    assert (gh != ch).sum() == 0
+    assert gst[0].segments == cseg
+    bad = (ga.view(np.uint32) != ca.view(np.uint32)).any(axis=2)
+    assert bad.sum() == 0, f"{bad.sum()} of {W * H} accum pixels differ"
+    assert (gh < 15744).mean() > 0.05  # the mesh is in frame
+
+
+def test_sum_mode_and_resolve(ptb, ctx, oh, assets):
+    """accumulate_mode=1 (sample-split): accum holds the sum of launch means; ptb_resolve divides and tonemaps."""
+    sc = load_config(ptb, assets, "c1", small=True)
+    handle, _ = ctx.accel_build(sc)
+    W, H, n = 96, 64, 96 * 64
+    kw = dict(spp_per_launch=4, max_depth=6, accumulate_mode=1, write_frame=0)
+    ga, _, _, _ = _render_gpu(ptb, ctx, handle, W, H, kw, subframes=3)
+    per = [_render_gpu(ptb, ctx, handle, W, H, dict(spp_per_launch=4, max_depth=6, write_frame=0), subframes=1)[0]]
+    # subframe 0 alone equals the first term of the sum
+    d_a, d_o, d_f = ctx.alloc(n * 16), ctx.alloc(n * 16), ctx.alloc(n * 4)
+    try:
+        ctx.to_device(d_a, ga)
+        ctx.resolve(d_a, d_o, d_f, n, 1.0 / 3.0)
+        ctx.synchronize()
+        mean = ctx.to_host(d_o, (H, W, 4), np.float32)
+        frame = ctx.to_host(d_f, (H, W, 4), np.uint8)
+    finally:
+        for b in (d_a, d_o, d_f):
+            ctx.free(b)
+    assert np.allclose(mean[..., :3], ga[..., :3] * np.float32(1.0 / 3.0), rtol=0, atol=0)
+    assert frame[..., 3].min() == 255 and frame[..., :3].max() > 0
+    assert np.all(ga[..., :3] >= per[0][..., :3] - 1e-6)

@@ -1,0 +1,60 @@
+#!/usr/bin/env python3
+"""Quick device-side timing of one configuration (development aid; bench.py is the contract)."""
+import argparse
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests")); sys.path.insert(0, str(ROOT / "tools"))
+import numpy as np
+
+import make_assets
+import szakdolgozat_pathtracer_b200 as ptb
+from scenes import CAMERAS, load_config
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--config", default="c2")
+ap.add_argument("--camera", default="default")
+ap.add_argument("--width", type=int, default=1920)
+ap.add_argument("--height", type=int, default=1080)
+ap.add_argument("--spp", type=int, default=8)
+ap.add_argument("--depth", type=int, default=8)
+ap.add_argument("--launches", type=int, default=4)
+ap.add_argument("--count", type=int, default=0)
+ap.add_argument("--leaf", type=int, default=4)
+a = ap.parse_args()
+
+ctx = ptb.Context(0)
+sc = load_config(ptb, make_assets, a.config)
+t0 = time.time()
+handle, bst = ctx.accel_build(sc, ptb.default_build_cfg(max_leaf_size=a.leaf))
+print(f"build: {bst.num_triangles} tris, {bst.num_nodes} nodes, {bst.num_leaves} leaves, depth {bst.max_depth}, sah {bst.sah_cost:.2f}, "
+      f"{bst.build_ms:.3f} ms device, {1e3 * (time.time() - t0):.1f} ms wall incl. upload")
+W, H = a.width, a.height
+n = W * H
+d_accum, d_frame = ctx.alloc(n * 16), ctx.alloc(n * 4)
+ctx.memset(d_accum, 0, n * 16)
+cfg = ptb.default_render_cfg(spp_per_launch=a.spp, max_depth=a.depth, count_traversal=a.count)
+for rep in range(2):
+    seg = 0
+    ctx.synchronize()
+    t0 = time.time()
+    for sf in range(a.launches):
+        p = ptb.make_params(W, H, subframe_index=sf, dof=True, **CAMERAS[a.camera])
+        p.accum_buffer, p.frame_buffer, p.handle = d_accum, d_frame, handle
+        ctx.launch(p, cfg)
+    ctx.synchronize()
+    dt = time.time() - t0
+st = ctx.launch_stats()
+seg = st.segments * a.launches
+print(f"{a.config}/{a.camera} {W}x{H} spp {a.spp} depth {a.depth}: {dt / a.launches * 1e3:.2f} ms/launch, "
+      f"~{seg / dt / 1e6:.1f} Msegments/s (last-launch segments {st.segments}, iterations {st.iterations}, "
+      f"hits {st.hits}, misses {st.misses}), {a.spp * a.launches / dt * (n / (1920 * 1080)):.1f} 1080p-spp/s")
+if a.count:
+    print(f"nodes/seg {st.nodes_visited / st.segments:.2f}, tris/seg {st.tris_tested / st.segments:.2f}")
+frame = ctx.to_host(d_frame, (H, W, 4), np.uint8)
+out = ROOT / "gpurun_out"
+out.mkdir(exist_ok=True)
+ptb.save_image(out / f"{a.config}_{a.camera}.png", frame)
+print("mean frame", frame[..., :3].mean(axis=(0, 1)))
