@@ -1,0 +1,335 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the B200-native path-tracing core.
+
+Workload (BASELINE.json configs[1], "C2"): monkey.obj + monkey_albedo.png under the
+synthetic env2.exr (2048x1024, seed 2), 1920x1080, 64 spp, depth 8, reference camera.
+One STEP = one full 64-spp frame = 8 launches of 8 samples per pixel through the C-ABI
+call ptb_launch() (the optixLaunch of the reference's render loop, optixSphere.cpp:1403-1418).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our CUDA path
+  python bench.py --impl reference [--gpus N] [--steps K] ...    the reference's own device file compiled for the
+                                                                 host (oracle/_ref), timed on the box's CPU cores
+
+N > 1 (one process per GPU under torchrun): the scene is replicated, rank r renders
+subframes r, r+N, ... of a 64*N-spp frame (weak scaling) into a sum-mode accumulator,
+one NCCL reduce of the float4 accumulator follows, rank 0 resolves/tonemaps.
+
+Prints ONE JSON line (rank 0).  `value` = segments of all ranks / max-over-ranks device time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+for p in (ROOT, ROOT / "tests", ROOT / "tools"):
+    sys.path.insert(0, str(p))
+
+import numpy as np
+
+W, H, SPP_PER_LAUNCH, LAUNCHES_PER_STEP, DEPTH = 1920, 1080, 8, 8, 8
+WORKLOAD = "C2: monkey.obj+monkey_albedo.png, env2 2048x1024 (synthetic, seed 2), 1920x1080, 64 spp (8 launches x 8), depth 8, reference camera, DoF on"
+
+
+def measured_peaks():
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        try:
+            return float(json.loads(f.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.gpu, self.lines, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_sample(oh, ptb, osc, rows, threads=0):
+    """Times the reference's CPU implementation on a band of the C2 frame.
+    oracle/_ref (the reference's optixSphere.cu compiled for the host) when present, else the oracle port."""
+    from scenes import CAMERAS
+    kind = "reference" if oh.have_ref() else "port"
+    which = "ref" if kind == "reference" else "oracle"
+    p = ptb.make_params(W, H, subframe_index=0, dof=True, **CAMERAS["default"])
+    y0 = H // 2 - rows // 2 - 40  # the band crosses the mesh, the floor and the horizon-free part of the frame
+    if kind == "reference":
+        cfg = oh.default_config("ref", threads=threads)
+        lits = "reference literals 10 spp/launch, depth 20 (compile-time constants, optixSphere.cu:323,360)"
+    else:
+        cfg = oh.default_config("oracle", spp_per_launch=SPP_PER_LAUNCH, max_depth=DEPTH, threads=threads)
+        lits = f"{SPP_PER_LAUNCH} spp/launch, depth {DEPTH}"
+    accum = np.zeros((H, W, 4), np.float32)
+    _, _, _, st, rc = oh.render(which, osc, oh.params_from_ptb(p), cfg, accum=accum, window=(0, y0, W, y0 + rows), want_hits=False)
+    if rc not in (0, 3):
+        raise RuntimeError(f"CPU reference render failed rc={rc}")
+    sample = f"one launch over rows {y0}..{y0 + rows - 1} of the C2 1920x1080 frame ({W * rows} px), {lits}, {st.segments} segments, {st.seconds:.2f} s"
+    return dict(value=st.segments / st.seconds / 1e6, unit="Msegments/s", cores=int(st.threads), kind=kind, sample=sample), st
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import make_assets
+    import orchelp as oh
+    import szakdolgozat_pathtracer_b200 as ptb
+    from scenes import load_config
+    sc = load_config(ptb, make_assets, "c2")
+    osc = oh.OracleScene.from_ptb(sc, guard=True)
+    rows = args.ref_rows
+    for _ in range(args.warmup):
+        cpu_reference_sample(oh, ptb, osc, max(4, rows // 8))
+    seg, sec, last = 0, 0.0, None
+    for _ in range(args.steps):
+        last, st = cpu_reference_sample(oh, ptb, osc, rows)
+        seg += st.segments; sec += st.seconds
+    value = seg / sec / 1e6
+    last["value"] = value
+    line = {
+        "impl": "reference", "metric": "Msegments/s", "value": value, "unit": "Msegments/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "sample_per_step": last["sample"]},
+        "cpu_baseline": last, "e2e": {"value": value, "unit": "Msegments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ref-rows", type=int, default=48, help="rows of the frame per step of the CPU reference arm")
+    ap.add_argument("--cpu-rows", type=int, default=160, help="rows of the frame for the cpu_baseline sample of our arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+
+    import make_assets
+    import szakdolgozat_pathtracer_b200 as ptb
+    from scenes import CAMERAS, load_config
+    from szakdolgozat_pathtracer_b200 import parallel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the ptb path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    ctx = ptb.Context(local_rank)
+    if rank == 0:
+        make_assets.ensure("c2")
+    if world > 1:
+        dist.barrier()
+    sc = load_config(ptb, make_assets, "c2")
+    handle, bst = ctx.accel_build(sc)
+
+    n = W * H
+    stream = torch.cuda.current_stream().cuda_stream
+    accum = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
+    frame = torch.zeros((H, W, 4), dtype=torch.uint8, device=dev)
+    multi = world > 1
+    cfg = ptb.default_render_cfg(spp_per_launch=SPP_PER_LAUNCH, max_depth=DEPTH,
+                                 accumulate_mode=1 if multi else 0, write_frame=0 if multi else 1)
+
+    def one_step(step_index, cfg_used):
+        # a fresh 64-spp frame: the accumulator restarts (the reference resets subframe_index on camera change, cpp:267-278)
+        if multi:
+            accum.zero_()
+        for sub in parallel.subframes_for_rank(rank, world, LAUNCHES_PER_STEP * world):
+            p = ptb.make_params(W, H, subframe_index=sub, dof=True, **CAMERAS["default"])
+            p.accum_buffer, p.frame_buffer, p.handle = accum.data_ptr(), frame.data_ptr(), handle
+            ctx.launch(p, cfg_used, stream=stream)
+        if multi:
+            parallel.reduce_accumulator(accum, dst=0)
+            if rank == 0:
+                ctx.resolve(accum.data_ptr(), accum.data_ptr(), frame.data_ptr(), n, parallel.resolve_scale(LAUNCHES_PER_STEP * world), cfg_used, stream=stream)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if multi:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for s in range(args.warmup):
+        one_step(s, cfg)
+    sync_all()
+    ctx.totals(reset=True)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    for s in range(args.steps):
+        one_step(s, cfg)
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    tot = ctx.totals(reset=True)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    segs = torch.tensor([float(tot["segments"])], dtype=torch.float64, device=dev)
+    if multi:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(segs, op=dist.ReduceOp.SUM)
+    ms_max, seg_total = float(t.item()), float(segs.item())
+    value = seg_total / (ms_max * 1e-3) / 1e6
+    launches_per_launch = 3 * SPP_PER_LAUNCH * (DEPTH + 1) + 3
+    gpu_launches = launches_per_launch * LAUNCHES_PER_STEP * args.steps + (args.steps if multi and rank == 0 else 0)
+
+    # ---- stage shares + roofline of the dominant kernel (CUDA events inside ptb_launch, same stream) ----
+    cfg_prof = ptb.default_render_cfg(spp_per_launch=SPP_PER_LAUNCH, max_depth=DEPTH, accumulate_mode=cfg.accumulate_mode,
+                                      write_frame=cfg.write_frame, profile_stages=1)
+    stage = {k: 0.0 for k in ("raygen", "trace", "shade", "miss", "resolve", "total")}
+    accum.zero_()
+    for sub in parallel.subframes_for_rank(rank, world, LAUNCHES_PER_STEP * world):
+        p = ptb.make_params(W, H, subframe_index=sub, dof=True, **CAMERAS["default"])
+        p.accum_buffer, p.frame_buffer, p.handle = accum.data_ptr(), frame.data_ptr(), handle
+        ctx.launch(p, cfg_prof, stream=stream)
+        for kk, v in ctx.stage_ms().items():
+            stage[kk] += v
+    # traversal work per segment, from one instrumented launch of the same subframe 0
+    cfg_cnt = ptb.default_render_cfg(spp_per_launch=SPP_PER_LAUNCH, max_depth=DEPTH, write_frame=0, count_traversal=1)
+    p = ptb.make_params(W, H, subframe_index=0, dof=True, **CAMERAS["default"])
+    scratch = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
+    p.accum_buffer, p.frame_buffer, p.handle = scratch.data_ptr(), frame.data_ptr(), handle
+    ctx.launch(p, cfg_cnt, stream=stream)
+    lst = ctx.launch_stats()
+    nodes_per_seg = lst.nodes_visited / max(lst.segments, 1)
+    tris_per_seg = lst.tris_tested / max(lst.segments, 1)
+    seg_per_step = seg_total / (args.steps * world)
+    # k_trace algorithmic bytes per segment: queue index 4 + ray 32 read, hit record 16 + queue append 4 written,
+    # 64 B per node visited, 48 B per triangle tested
+    trace_bytes_per_seg = 4 + 32 + 16 + 4 + 64.0 * nodes_per_seg + 48.0 * tris_per_seg
+    trace_launches = LAUNCHES_PER_STEP * SPP_PER_LAUNCH * (DEPTH + 1)
+    peak, peak_src = measured_peaks()
+    trace_s = stage["trace"] * 1e-3
+    achieved = trace_bytes_per_seg * seg_per_step / trace_s / 1e9 if trace_s > 0 else 0.0
+    traffic = None
+    tf = ROOT / "profiles" / "k_trace_dram_bytes_per_launch.json"
+    if tf.exists():
+        try:
+            traffic = json.loads(tf.read_text())["dram_bytes_per_launch"]
+        except Exception:
+            traffic = None
+    roofline = {
+        "kernel": "k_trace", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": traffic, "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": trace_bytes_per_seg * seg_per_step / trace_launches,
+        "avg_launch_ms": stage["trace"] / trace_launches, "nodes_per_segment": nodes_per_seg, "tris_per_segment": tris_per_seg,
+        "note": "BVH (1.1 MB) and textures (4 MB) are L2-resident, so this kernel is latency/L2-bound; the fraction is of the HBM copy peak",
+        "stage_ms_per_step": {k: v for k, v in stage.items()},
+        "stage_share": {k: (stage[k] / stage["total"] if stage["total"] > 0 else 0.0) for k in ("raygen", "trace", "shade", "miss", "resolve")},
+    }
+
+    # ---- end to end through the C ABI with HOST buffers (pinned): accum in, accum + frame out, every step ----
+    h_accum = torch.zeros((H, W, 4), dtype=torch.float32).pin_memory()
+    h_frame = torch.zeros((H, W, 4), dtype=torch.uint8).pin_memory()
+    import ctypes as C
+    L = ptb.lib()
+
+    def e2e_step():
+        L.ptb_copy_to_device(ctx._h, C.c_void_p(accum.data_ptr()), C.c_void_p(h_accum.data_ptr()), C.c_size_t(n * 16), C.c_void_p(stream))
+        one_step(0, cfg)
+        if rank == 0:
+            L.ptb_copy_to_host(ctx._h, C.c_void_p(h_accum.data_ptr()), C.c_void_p(accum.data_ptr()), C.c_size_t(n * 16), C.c_void_p(stream))
+            L.ptb_copy_to_host(ctx._h, C.c_void_p(h_frame.data_ptr()), C.c_void_p(frame.data_ptr()), C.c_size_t(n * 4), C.c_void_p(stream))
+
+    e2e_step()
+    sync_all()
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        e2e_step()
+    sync_all()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if multi:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = seg_total / float(t.item()) / 1e6
+    e2e = {"value": e2e_value, "unit": "Msegments/s", "h2d_bytes_per_step": n * 16, "d2h_bytes_per_step": n * 16 + n * 4,
+           "timing": "host wall clock around K steps incl. pinned h2d/d2h copies and a stream sync per step"}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import orchelp as oh
+        osc = oh.OracleScene.from_ptb(sc, guard=True)
+        cpu_baseline, _ = cpu_reference_sample(oh, ptb, osc, args.cpu_rows)
+
+    if rank == 0:
+        line = {
+            "metric": "Msegments/s", "value": value, "unit": "Msegments/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "spp_per_step_per_gpu": SPP_PER_LAUNCH * LAUNCHES_PER_STEP,
+                       "l2": "no flush: path pool + queues are 232 MB per launch (> 126 MB L2) and are rewritten every iteration",
+                       "multi_gpu": "scene replicated, subframes split by rank, NCCL reduce of the float4 accumulator" if multi else "single GPU, reference accumulate mode",
+                       "bvh": {"triangles": bst.num_triangles, "nodes": bst.num_nodes, "max_depth": bst.max_depth, "sah": bst.sah_cost, "build_ms": bst.build_ms}},
+            "spp_per_s_1080p": SPP_PER_LAUNCH * LAUNCHES_PER_STEP * world * args.steps / (ms_max * 1e-3),
+            "segments_per_step": seg_total / args.steps,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line))
+    if multi:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -118,6 +118,7 @@ typedef struct ptb_render_cfg {
     int32_t write_frame;      /* 1: tonemap into Params.frame_buffer (optixSphere.cu:411-435); 0: skip */
     int32_t env_importance_sampling; /* 0 = reference estimator (BSDF sampling only).  Reserved. */
     int32_t count_traversal;  /* 1: also count BVH nodes visited / triangles tested (slower) */
+    int32_t profile_stages;   /* 1: bracket every stage kernel with CUDA events (ptb_launch_get_stage_ms) */
     int32_t* aux_primary_hit; /* optional DEVICE int32[W*H]: primitive hit by the first segment of sample 0, -1 = miss */
 } ptb_render_cfg;
 
@@ -216,6 +217,13 @@ void ptb_default_render_cfg(ptb_render_cfg* cfg);
 int ptb_launch(ptb_context* ctx, const ptb_Params* params, const ptb_render_cfg* cfg, void* stream);
 /* synchronises the stream of the last launch and returns its counters */
 int ptb_launch_get_stats(ptb_context* ctx, ptb_launch_stats* out);
+/* running totals over every launch of this context since the last reset, summed on the device at the
+ * end of each launch (no host synchronisation inside ptb_launch): out[0] segments, [1] hits, [2] misses,
+ * [3] launches.  Synchronises the last stream. */
+int ptb_context_get_totals(ptb_context* ctx, uint64_t out[4], int reset);
+/* device time per stage of the last launch that had profile_stages = 1, in ms:
+ * out[0] raygen, [1] traversal, [2] shade, [3] miss, [4] accumulate/tonemap, [5] whole launch */
+int ptb_launch_get_stage_ms(ptb_context* ctx, float out[6]);
 /* accumulate/tonemap stage on its own (optixSphere.cu:401-435): frame = tonemap(accum * scale).
  * Used after a multi-GPU reduce of sum-mode accumulators. */
 int ptb_resolve(ptb_context* ctx, const ptb_float4* accum, ptb_float4* accum_out, ptb_uchar4* frame, uint32_t n_pixels,
@@ -253,6 +261,11 @@ int ptb_image_load_float4(const char* path, float** pixels, int* w, int* h);
  * the bottom image row, optixSphere.cu:332,400) when flip_y != 0 */
 int ptb_save_image(const char* path, const ptb_uchar4* pixels, int w, int h, int flip_y);
 void ptb_free(void* p);
+/* The OBJ reader on its own (what tinyobj::LoadObj(triangulate=true) hands to the reference,
+ * optixSphere.cpp:431, 447-515): per face vertex, in file/fan order, 10 words =
+ * vx vy vz nx ny nz tx ty (float32, raw: unscaled, normals not normalised) + has_normal, has_texcoord (int32).
+ * *records is released with ptb_free(). */
+int ptb_obj_read(const char* path, void** records, uint64_t* n_face_vertices);
 
 /* ---- device self-test hooks used by the parity tests --------------------------- */
 /* op: 0 rng (in: seed as uint bits -> out: next seed bits, u), 1 sincos (x -> s, c),

@@ -46,7 +46,7 @@ class Float4(C.Structure):
 class TriangleData(C.Structure):
     _fields_ = [(n, C.c_float * 4) for n in ("v0", "v1", "v2", "n0", "n1", "n2")] + [
         (n, C.c_float * 2) for n in ("uv0", "uv1", "uv2")
-    ]
+    ] + [("_tail_pad", C.c_float * 2)]  # float4 members make the struct 16-byte aligned: sizeof == 128
 
 
 class Params(C.Structure):
@@ -76,7 +76,7 @@ class RenderCfg(C.Structure):
         ("dof_blur", C.c_float), ("focus_dist", C.c_float), ("nmap_strength", C.c_float),
         ("exposure", C.c_float), ("gamma", C.c_float), ("contrast", C.c_float),
         ("accumulate_mode", C.c_int32), ("write_frame", C.c_int32), ("env_importance_sampling", C.c_int32),
-        ("count_traversal", C.c_int32), ("aux_primary_hit", C.c_void_p),
+        ("count_traversal", C.c_int32), ("profile_stages", C.c_int32), ("aux_primary_hit", C.c_void_p),
     ]
 
 
@@ -116,11 +116,11 @@ EXPORTS = [
     "ptb_scene_set_env_pixels", "ptb_scene_destroy", "ptb_scene_num_triangles", "ptb_scene_num_materials",
     "ptb_scene_copy_triangles", "ptb_scene_copy_material_ids", "ptb_scene_get_material", "ptb_scene_copy_texture",
     "ptb_scene_env_size", "ptb_scene_copy_env", "ptb_default_build_cfg", "ptb_accel_build", "ptb_accel_read",
-    "ptb_camera_uvw", "ptb_params_default_camera", "ptb_default_render_cfg", "ptb_launch", "ptb_launch_get_stats",
+    "ptb_camera_uvw", "ptb_params_default_camera", "ptb_default_render_cfg", "ptb_launch", "ptb_launch_get_stats", "ptb_launch_get_stage_ms", "ptb_context_get_totals",
     "ptb_resolve", "ptb_trace_rays", "ptb_output_create", "ptb_output_resize", "ptb_output_map", "ptb_output_unmap",
     "ptb_output_host_ptr", "ptb_output_width", "ptb_output_height", "ptb_output_destroy", "ptb_device_alloc",
     "ptb_device_free", "ptb_device_memset", "ptb_copy_to_device", "ptb_copy_to_host", "ptb_image_load_rgba8",
-    "ptb_image_load_float4", "ptb_save_image", "ptb_free", "ptb_test_device_math",
+    "ptb_image_load_float4", "ptb_save_image", "ptb_free", "ptb_obj_read", "ptb_test_device_math",
 ]
 
 _lib = None
@@ -346,6 +346,16 @@ class Context:
         _check(lib().ptb_launch_get_stats(self._h, C.byref(st)))
         return st
 
+    def totals(self, reset=False) -> dict:
+        out = (C.c_uint64 * 4)()
+        _check(lib().ptb_context_get_totals(self._h, out, int(bool(reset))))
+        return dict(zip(("segments", "hits", "misses", "launches"), [int(x) for x in out]))
+
+    def stage_ms(self) -> dict:
+        out = (C.c_float * 6)()
+        _check(lib().ptb_launch_get_stage_ms(self._h, out))
+        return dict(zip(("raygen", "trace", "shade", "miss", "resolve", "total"), [float(x) for x in out]))
+
     def resolve(self, accum_ptr, accum_out_ptr, frame_ptr, n_pixels, scale, cfg: RenderCfg | None = None, stream=0):
         _check(lib().ptb_resolve(self._h, C.c_void_p(accum_ptr), C.c_void_p(accum_out_ptr), C.c_void_p(frame_ptr), C.c_uint32(n_pixels),
                                  C.c_float(scale), C.byref(cfg) if cfg is not None else None, C.c_void_p(stream)))
@@ -453,6 +463,16 @@ def load_image_float4(path) -> np.ndarray:
     _check(lib().ptb_image_load_float4(os.fsencode(str(path)), C.byref(px), C.byref(w), C.byref(h)))
     out = np.ctypeslib.as_array(px, shape=(h.value, w.value, 4)).copy()
     lib().ptb_free(px)
+    return out
+
+
+def obj_read(path) -> np.ndarray:
+    """Raw face-vertex stream of the OBJ reader: uint32 words [n, 10] (8 float32 + 2 int32 flags per face vertex)."""
+    rec, n = C.c_void_p(), C.c_uint64()
+    _check(lib().ptb_obj_read(os.fsencode(str(path)), C.byref(rec), C.byref(n)))
+    buf = (C.c_uint32 * (n.value * 10)).from_address(rec.value)
+    out = np.frombuffer(buf, np.uint32).reshape(-1, 10).copy()
+    lib().ptb_free(rec)
     return out
 
 

@@ -54,7 +54,7 @@ void ptb_default_render_cfg(ptb_render_cfg* cfg) {
     cfg->spp_per_launch = 10; cfg->max_depth = 20; cfg->tmin = 0.01f; cfg->tmax = 1e16f;
     cfg->dof_blur = 0.01f; cfg->focus_dist = 1.0f; cfg->nmap_strength = 0.4f;
     cfg->exposure = -0.5f; cfg->gamma = 2.2f; cfg->contrast = 1.25f;
-    cfg->accumulate_mode = 0; cfg->write_frame = 1; cfg->env_importance_sampling = 0; cfg->count_traversal = 0;
+    cfg->accumulate_mode = 0; cfg->write_frame = 1; cfg->env_importance_sampling = 0; cfg->count_traversal = 0; cfg->profile_stages = 0;
     cfg->aux_primary_hit = nullptr;
 }
 
@@ -248,5 +248,26 @@ int ptb_save_image(const char* path, const ptb_uchar4* pixels, int w, int h, int
     return ok ? PTB_OK : fail(PTB_ERR_IO, err);
 }
 void ptb_free(void* p) { free(p); }
+
+int ptb_obj_read(const char* path, void** records, uint64_t* n_face_vertices) {
+    if (!path || !records || !n_face_vertices) return fail(PTB_ERR_INVALID, "ptb_obj_read: bad arguments");
+    ObjMesh mesh; std::string err;
+    if (!load_obj(path, mesh, err)) return fail(PTB_ERR_IO, err);
+    const size_t n = mesh.indices.size();
+    uint32_t* out = (uint32_t*)calloc(n ? n : 1, 40);
+    if (!out) return fail(PTB_ERR_INVALID, "out of memory");
+    for (size_t i = 0; i < n; ++i) {
+        const ObjIndex& ix = mesh.indices[i];
+        float rec[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        int32_t flags[2] = {0, 0};
+        for (int k = 0; k < 3; ++k) rec[k] = mesh.v[3 * (size_t)ix.v + k];
+        if (ix.vn >= 0) { flags[0] = 1; for (int k = 0; k < 3; ++k) rec[3 + k] = mesh.vn[3 * (size_t)ix.vn + k]; }
+        if (!mesh.vt.empty() && ix.vt >= 0) { flags[1] = 1; rec[6] = mesh.vt[2 * (size_t)ix.vt]; rec[7] = mesh.vt[2 * (size_t)ix.vt + 1]; }
+        memcpy(out + i * 10, rec, 32);
+        memcpy(out + i * 10 + 8, flags, 8);
+    }
+    *records = out; *n_face_vertices = n;
+    return PTB_OK;
+}
 
 }  // extern "C"

@@ -452,6 +452,21 @@ __global__ void __launch_bounds__(256) k_resolve(FrameView f, PathView p) {
     if (f.write_frame && f.frame) f.frame[i] = display_color(accum_color, f.exposure_scale, f.inv_gamma, f.contrast);
 }
 
+// Folds the per-iteration queue sizes of one launch into the context's running totals
+// (segments = rays traced, hits, misses, launches), so throughput can be counted without a
+// host round trip per launch.
+__global__ void __launch_bounds__(256) k_fold_counters(const uint32_t* __restrict__ counters, uint32_t iters,
+                                                       unsigned long long* __restrict__ totals) {
+    unsigned long long s[3] = {0ull, 0ull, 0ull};
+    for (uint32_t it = threadIdx.x; it < iters; it += blockDim.x)
+        for (int k = 0; k < 3; ++k) s[k] += counters[(size_t)it * 4 + k];
+    for (int k = 0; k < 3; ++k) {
+        for (int off = 16; off > 0; off >>= 1) s[k] += __shfl_xor_sync(0xffffffffu, s[k], off);
+        if ((threadIdx.x & 31u) == 0u && s[k]) atomicAdd(&totals[k], s[k]);
+    }
+    if (threadIdx.x == 0) atomicAdd(&totals[3], 1ull);
+}
+
 // stand-alone accumulate/tonemap over an already reduced accumulator (multi-GPU sample split)
 __global__ void __launch_bounds__(256) k_resolve_scaled(const float4* __restrict__ accum, float4* __restrict__ accum_out,
                                                         uchar4* __restrict__ frame, uint32_t n, float scale,

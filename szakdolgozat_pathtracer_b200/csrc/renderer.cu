@@ -63,11 +63,15 @@ struct ptb_context {
     uint32_t *q_trace[2] = {nullptr, nullptr}, *q_hit = nullptr, *q_miss = nullptr;
     uint32_t* counters = nullptr; uint32_t counters_cap = 0;  // in iterations
     unsigned long long* trav_stats = nullptr;
+    unsigned long long* totals = nullptr;  // segments, hits, misses, launches since the last reset
     // last launch, for ptb_launch_get_stats
     cudaStream_t last_stream = nullptr;
     uint32_t last_iters = 0, last_kernels = 0;
     uint64_t last_paths = 0;
     bool last_counted = false;
+    // stage profiling (profile_stages): events[0] start, then 3 per iteration, then after resolve
+    std::vector<cudaEvent_t> events;
+    uint32_t prof_iters = 0;  // iterations of the last profiled launch, 0 = none
     std::map<unsigned long long, DeviceScene*> scenes;
     unsigned long long next_handle = 1;
 };
@@ -127,6 +131,10 @@ int ensure_pool(ptb_context* c, uint32_t slots, uint32_t iters) {
         c->counters_cap = iters + 2;
     }
     if (!c->trav_stats) CU(cudaMalloc((void**)&c->trav_stats, 2 * sizeof(unsigned long long)));
+    if (!c->totals) {
+        CU(cudaMalloc((void**)&c->totals, 4 * sizeof(unsigned long long)));
+        CU(cudaMemset(c->totals, 0, 4 * sizeof(unsigned long long)));
+    }
     return PTB_OK;
 }
 
@@ -172,7 +180,8 @@ void ptb_context_destroy(ptb_context* ctx) {
     // scenes stay owned by their ptb_scene; just detach them
     for (auto& kv : ctx->scenes) kv.second->owner = nullptr;
     free_pool(ctx);
-    cudaFree(ctx->counters); cudaFree(ctx->trav_stats);
+    cudaFree(ctx->counters); cudaFree(ctx->trav_stats); cudaFree(ctx->totals);
+    for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     delete ctx;
 }
 
@@ -312,7 +321,15 @@ int ptb_launch(ptb_context* ctx, const ptb_Params* P, const ptb_render_cfg* cfg_
     CU(cudaMemsetAsync(ctx->counters, 0, (size_t)(iters + 2) * 4 * sizeof(uint32_t), st));
     CU(cudaMemsetAsync(ctx->trav_stats, 0, 2 * sizeof(unsigned long long), st));
     const uint32_t pix_blocks = (slots + 255u) / 256u;
+    const bool prof = cfg.profile_stages != 0;
+    if (prof) {
+        const size_t need_ev = (size_t)iters * 3 + 4;
+        while (ctx->events.size() < need_ev) { cudaEvent_t e; CU(cudaEventCreate(&e)); ctx->events.push_back(e); }
+        CU(cudaEventRecord(ctx->events[0], st));
+    }
+    ctx->prof_iters = 0;
     k_raygen_init<<<pix_blocks, 256, 0, st>>>(f, p, q);
+    if (prof) CU(cudaEventRecord(ctx->events[1], st));
     // Persistent-style grids: a multiple of the SM count, looping over the queue.
     const uint32_t need = (slots + 127u) / 128u;
     const uint32_t cap = (uint32_t)ctx->num_sms * 32u;
@@ -321,12 +338,17 @@ int ptb_launch(ptb_context* ctx, const ptb_Params* P, const ptb_render_cfg* cfg_
     for (uint32_t it = 0; it < iters; ++it) {
         if (cfg.count_traversal) k_trace<true><<<grid, 128, 0, st>>>(s, f, p, q, (int)it);
         else k_trace<false><<<grid, 128, 0, st>>>(s, f, p, q, (int)it);
+        if (prof) CU(cudaEventRecord(ctx->events[2 + (size_t)it * 3 + 0], st));
         k_shade<<<grid, 128, 0, st>>>(s, f, p, q, (int)it);
+        if (prof) CU(cudaEventRecord(ctx->events[2 + (size_t)it * 3 + 1], st));
         k_miss<<<grid, 128, 0, st>>>(s, f, p, q, (int)it);
+        if (prof) CU(cudaEventRecord(ctx->events[2 + (size_t)it * 3 + 2], st));
         launches += 3;
     }
     k_resolve<<<pix_blocks, 256, 0, st>>>(f, p);
-    launches += 1;
+    k_fold_counters<<<1, 256, 0, st>>>(ctx->counters, iters, ctx->totals);
+    launches += 2;
+    if (prof) { CU(cudaEventRecord(ctx->events[2 + (size_t)iters * 3], st)); ctx->prof_iters = iters; }
     CU(cudaGetLastError());
     ctx->last_stream = st; ctx->last_iters = iters; ctx->last_kernels = launches;
     ctx->last_paths = (uint64_t)slots * (uint64_t)cfg.spp_per_launch; ctx->last_counted = cfg.count_traversal != 0;
@@ -350,6 +372,40 @@ int ptb_launch_get_stats(ptb_context* ctx, ptb_launch_stats* out) {
     }
     out->paths = ctx->last_paths; out->iterations = used; out->kernel_launches = ctx->last_kernels;
     if (ctx->last_counted) { out->nodes_visited = tv[0]; out->tris_tested = tv[1]; }
+    return PTB_OK;
+}
+
+int ptb_context_get_totals(ptb_context* ctx, uint64_t out[4], int reset) {
+    if (!ctx || !out) return fail(PTB_ERR_INVALID, "ptb_context_get_totals: bad arguments");
+    for (int i = 0; i < 4; ++i) out[i] = 0;
+    if (!ctx->totals) return PTB_OK;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->last_stream));
+    unsigned long long h[4];
+    CU(cudaMemcpy(h, ctx->totals, sizeof(h), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 4; ++i) out[i] = h[i];
+    if (reset) CU(cudaMemset(ctx->totals, 0, sizeof(h)));
+    return PTB_OK;
+}
+
+int ptb_launch_get_stage_ms(ptb_context* ctx, float out[6]) {
+    if (!ctx || !out) return fail(PTB_ERR_INVALID, "ptb_launch_get_stage_ms: bad arguments");
+    if (!ctx->prof_iters) return fail(PTB_ERR_INVALID, "ptb_launch_get_stage_ms: the last launch did not set profile_stages");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->last_stream));
+    for (int i = 0; i < 6; ++i) out[i] = 0.0f;
+    float ms = 0.0f;
+    const std::vector<cudaEvent_t>& ev = ctx->events;
+    CU(cudaEventElapsedTime(&ms, ev[0], ev[1])); out[0] = ms;
+    for (uint32_t it = 0; it < ctx->prof_iters; ++it) {
+        const size_t b = 2 + (size_t)it * 3;
+        CU(cudaEventElapsedTime(&ms, ev[b - 1], ev[b])); out[1] += ms;
+        CU(cudaEventElapsedTime(&ms, ev[b], ev[b + 1])); out[2] += ms;
+        CU(cudaEventElapsedTime(&ms, ev[b + 1], ev[b + 2])); out[3] += ms;
+    }
+    const size_t last = 2 + (size_t)ctx->prof_iters * 3;
+    CU(cudaEventElapsedTime(&ms, ev[last - 1], ev[last])); out[4] = ms;
+    CU(cudaEventElapsedTime(&ms, ev[0], ev[last])); out[5] = ms;
     return PTB_OK;
 }
 

@@ -1,0 +1,56 @@
+#!/usr/bin/env python3
+"""Generates the committed golden fixtures under tests/golden/ from the REFERENCE ITSELF, run here:
+  * abi_layout.json        sizeof/offsetof of optixSphere.h, printed by oracle/_ref/ref_probe (real CUDA vector types)
+  * obj_<name>.json        triangle count + sha256 of the face-vertex stream tiny_obj_loader.h produces for each OBJ
+  * ref_c1_small.npz       accum / frame / primary-hit buffers rendered by oracle/_ref/libref_pt.so (the reference's
+                           optixSphere.cu compiled for the host) on the C1-small scene, reference literals, 2 subframes
+Needs /root/reference (oracle/_ref is built from it); the fixtures then travel to boxes that do not have it.
+"""
+import hashlib
+import json
+import subprocess
+import sys
+import tempfile
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+for p in (ROOT, ROOT / "tests", ROOT / "tools"):
+    sys.path.insert(0, str(p))
+import numpy as np
+
+import make_assets
+import orchelp as oh
+import szakdolgozat_pathtracer_b200 as ptb
+from scenes import load_config
+
+GOLD = ROOT / "tests" / "golden"
+GOLD.mkdir(parents=True, exist_ok=True)
+oh.build_oracle()
+assert oh.have_ref(), "oracle/_ref is missing: /root/reference must be present to regenerate the fixtures"
+
+layout = json.loads(subprocess.run([str(oh.REF_PROBE), "layout"], capture_output=True, text=True, check=True).stdout)
+layout.pop("end")
+(GOLD / "abi_layout.json").write_text(json.dumps(layout, indent=1) + "\n")
+
+for name in ("test", "monkey", "suitcase", "fish", "tower"):
+    with tempfile.NamedTemporaryFile(suffix=".bin") as tf:
+        info = json.loads(subprocess.run([str(oh.REF_PROBE), "obj", str(ROOT / "assets" / f"{name}.obj"), tf.name],
+                                         capture_output=True, text=True, check=True).stdout)
+        raw = Path(tf.name).read_bytes()
+    info["sha256_face_vertex_stream"] = hashlib.sha256(raw).hexdigest()
+    (GOLD / f"obj_{name}.json").write_text(json.dumps(info, indent=1) + "\n")
+
+sc = load_config(ptb, make_assets, "c1", small=True)
+osc = oh.OracleScene.from_ptb(sc, guard=True)
+W, H = 96, 64
+accum = np.zeros((H, W, 4), np.float32)
+hits0 = None
+for sf in range(2):
+    p = ptb.make_params(W, H, subframe_index=sf, dof=True)
+    accum, frame, hits, st, rc = oh.render("ref", osc, oh.params_from_ptb(p), oh.default_config("ref"), accum=accum)
+    assert rc == 0
+    if sf == 0:
+        hits0 = hits.copy()
+        seg0 = int(st.segments)
+np.savez_compressed(GOLD / "ref_c1_small.npz", accum=accum, frame=frame, hits=hits0, segments0=np.int64(seg0))
+print("golden fixtures written to", GOLD)
