@@ -36,6 +36,11 @@ extern "C" {
 #define PTB_ERR_UNSUPPORTED 4
 #define PTB_ERR_NO_DEVICE 5
 
+#define PTB_PIPELINE_QUEUES 1
+#define PTB_PIPELINE_CHUNK_STAGES 2
+#define PTB_PIPELINE_CHUNK_FUSED 3
+#define PTB_PIPELINE_DEFAULT PTB_PIPELINE_CHUNK_FUSED
+
 /* ---- data layouts shared with the reference (optixSphere.h) ---------------
  * Layout-identical to the CUDA vector types the reference uses; the sizes and
  * offsets are pinned by tests against oracle/_ref/ref_probe. */
@@ -119,6 +124,14 @@ typedef struct ptb_render_cfg {
     int32_t env_importance_sampling; /* 0 = reference estimator (BSDF sampling only).  Reserved. */
     int32_t count_traversal;  /* 1: also count BVH nodes visited / triangles tested (slower) */
     int32_t profile_stages;   /* 1: bracket every stage kernel with CUDA events (ptb_launch_get_stage_ms) */
+    int32_t subframes_per_launch; /* default 1.  n > 1: this one call renders subframes subframe_index .. +n-1 as ONE
+                                 wavefront of n*W*H path slots (results are bit-identical to n consecutive calls;
+                                 the path pool grows to n*W*H*96 bytes).  Keeps the GPU full through the tail of the
+                                 per-pixel sample chains. */
+    int32_t pipeline;         /* 0 = default.  1: global ray queues, one kernel per stage and iteration;
+                                 2: block-local wavefront over chunks of the path pool, one kernel per stage and
+                                    iteration; 3: the same stages fused into one persistent kernel per launch.
+                                 All three produce bit-identical results. */
     int32_t* aux_primary_hit; /* optional DEVICE int32[W*H]: primitive hit by the first segment of sample 0, -1 = miss */
 } ptb_render_cfg;
 

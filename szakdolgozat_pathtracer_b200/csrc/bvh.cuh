@@ -81,74 +81,99 @@ PTB_DEV bool ray_tri(float3 org, const RayShear& rs, float3 p0, float3 p1, float
 
 struct TravCounters { uint32_t nodes, tris; };
 
-// Conservative slab test of one child box against [tmin, tbest].  Boxes are
-// padded at build time and the far distance is widened by 2 ulp, so a box is
-// never rejected when one of its triangles would pass ray_tri.
-PTB_DEV bool slab(float lox, float hix, float loy, float hiy, float loz, float hiz, float3 o, float3 id, float tmin,
+// Conservative slab test of one child box against [tmin, tbest].  Leaf boxes are padded at build time
+// (bvh_build.cu: k_leaf_boxes) and the far distance is widened, so a box is never rejected when one of its
+// triangles would pass ray_tri.  tminp = tmin * 0.999.
+PTB_DEV bool slab(float lox, float hix, float loy, float hiy, float loz, float hiz, float3 o, float3 id, float tminp,
                   float tbest, float* tnear) {
-    float t0 = (lox - o.x) * id.x, t1 = (hix - o.x) * id.x;
-    float lo = fminf(t0, t1), hi = fmaxf(t0, t1);
-    t0 = (loy - o.y) * id.y; t1 = (hiy - o.y) * id.y;
-    lo = fmaxf(lo, fminf(t0, t1)); hi = fminf(hi, fmaxf(t0, t1));
-    t0 = (loz - o.z) * id.z; t1 = (hiz - o.z) * id.z;
-    lo = fmaxf(lo, fminf(t0, t1)); hi = fminf(hi, fmaxf(t0, t1));
-    hi = hi * 1.0000005f;
-    lo = fmaxf(lo * 0.9999995f, tmin * 0.999f);
+    const float x0 = (lox - o.x) * id.x, x1 = (hix - o.x) * id.x;
+    const float y0 = (loy - o.y) * id.y, y1 = (hiy - o.y) * id.y;
+    const float z0 = (loz - o.z) * id.z, z1 = (hiz - o.z) * id.z;
+    const float lo = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), tminp));
+    const float hi = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1)) * 1.000001f;
     *tnear = lo;
     return lo <= hi && lo <= tbest;
+}
+
+#define PTB_TRAV_SENTINEL 0x7fffffff
+
+// Traversal state of one ray.  The stack lives in the caller's local memory (one entry per tree level; the
+// builder rejects trees deeper than PTB_BVH_STACK).
+struct Trav {
+    float3 o, id;
+    RayShear rs;
+    float tmin, tminp, tmax;
+    HitRec best;
+    int node;  // current internal node (>= 0), leaf code (< 0) or PTB_TRAV_SENTINEL when finished
+    int sp;
+};
+
+PTB_DEV void trav_begin(Trav& t, int* stack, float3 o, float3 d, float tmin, float tmax) {
+    t.o = o; t.id = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    t.rs = ray_shear(d);
+    t.tmin = tmin; t.tminp = tmin * 0.999f; t.tmax = tmax;
+    t.best.t = tmax; t.best.b1 = 0.0f; t.best.b2 = 0.0f; t.best.prim = -1;
+    stack[0] = PTB_TRAV_SENTINEL;
+    t.sp = 1;
+    t.node = 0;
+}
+
+// Runs at most `budget` steps ("while-while": descend through internal nodes until a leaf is reached, then test
+// the leaf's triangles).  Returns true when the ray is finished.
+template <bool COUNT>
+PTB_DEV bool trav_run(Trav& t, int* stack, const float4* __restrict__ nodes, const float4* __restrict__ tris, int budget,
+                      TravCounters* cnt) {
+    while (budget > 0) {
+        while ((unsigned)t.node < (unsigned)PTB_TRAV_SENTINEL && budget > 0) {
+            const float4* np = nodes + (size_t)t.node * 4;
+            const float4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
+            if (COUNT) cnt->nodes++;
+            float tn0, tn1;
+            const bool h0 = slab(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, t.o, t.id, t.tminp, t.best.t, &tn0);
+            const bool h1 = slab(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, t.o, t.id, t.tminp, t.best.t, &tn1);
+            const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+            if (h0 && h1) {
+                const bool swap = tn1 < tn0;  // nearer child first, the other one goes on the stack
+                stack[t.sp++] = swap ? c0 : c1;
+                t.node = swap ? c1 : c0;
+            } else if (h0) t.node = c0;
+            else if (h1) t.node = c1;
+            else t.node = stack[--t.sp];
+            --budget;
+        }
+        if (t.node == PTB_TRAV_SENTINEL) return true;
+        if (t.node < 0) {
+            const int code = ~t.node;
+            const int first = code >> 3, count = (code & 7) + 1;
+            for (int i = 0; i < count; ++i) {
+                const float4* tp = tris + (size_t)(first + i) * 3;
+                const float4 a = __ldg(tp + 0), b = __ldg(tp + 1), c = __ldg(tp + 2);
+                if (COUNT) cnt->tris++;
+                float th, b1, b2;
+                // test against the ray's own tmax so that ties can be resolved by prim id
+                if (ray_tri(t.o, t.rs, mk3(a), mk3(b), mk3(c), t.tmin, t.tmax, &th, &b1, &b2)) {
+                    const int prim = __float_as_int(a.w);
+                    if (th < t.best.t || (th == t.best.t && t.best.prim >= 0 && prim < t.best.prim)) {
+                        t.best.t = th; t.best.b1 = b1; t.best.b2 = b2; t.best.prim = prim;
+                    }
+                }
+            }
+            t.node = stack[--t.sp];
+            budget -= 2;
+            if (t.node == PTB_TRAV_SENTINEL) return true;
+        }
+    }
+    return false;
 }
 
 template <bool COUNT>
 PTB_DEV HitRec bvh_closest_hit(const float4* __restrict__ nodes, const float4* __restrict__ tris, float3 o, float3 d,
                                float tmin, float tmax, TravCounters* cnt) {
-    HitRec best; best.t = tmax; best.b1 = 0.0f; best.b2 = 0.0f; best.prim = -1;
-    const RayShear rs = ray_shear(d);
-    const float3 id = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-    int stack[PTB_BVH_STACK];  // one entry per level; the builder rejects trees deeper than the stack
-    int sp = 0;
-    int node = 0;  // current internal node (>= 0) or leaf code (< 0)
-    const int SENTINEL = 0x7fffffff;
-    stack[sp++] = SENTINEL;
-    while (node != SENTINEL) {
-        if (node >= 0) {
-            const float4 n0 = __ldg(nodes + (size_t)node * 4 + 0);
-            const float4 n1 = __ldg(nodes + (size_t)node * 4 + 1);
-            const float4 n2 = __ldg(nodes + (size_t)node * 4 + 2);
-            const float4 n3 = __ldg(nodes + (size_t)node * 4 + 3);
-            if (COUNT) cnt->nodes++;
-            float tn0, tn1;
-            const bool h0 = slab(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, o, id, tmin, best.t, &tn0);
-            const bool h1 = slab(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, o, id, tmin, best.t, &tn1);
-            const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
-            if (h0 && h1) {
-                // nearer child first, the other one goes on the stack
-                const bool swap = tn1 < tn0;
-                stack[sp++] = swap ? c0 : c1;
-                node = swap ? c1 : c0;
-            } else if (h0) node = c0;
-            else if (h1) node = c1;
-            else node = stack[--sp];
-        } else {
-            const int code = ~node;
-            const int first = code >> 3, count = (code & 7) + 1;
-            for (int i = 0; i < count; ++i) {
-                const float4 a = __ldg(tris + (size_t)(first + i) * 3 + 0);
-                const float4 b = __ldg(tris + (size_t)(first + i) * 3 + 1);
-                const float4 c = __ldg(tris + (size_t)(first + i) * 3 + 2);
-                if (COUNT) cnt->tris++;
-                float t, b1, b2;
-                // test against the ray's own tmax so that ties can be resolved by prim id
-                if (ray_tri(o, rs, mk3(a), mk3(b), mk3(c), tmin, tmax, &t, &b1, &b2)) {
-                    const int prim = __float_as_int(a.w);
-                    if (t < best.t || (t == best.t && best.prim >= 0 && prim < best.prim)) {
-                        best.t = t; best.b1 = b1; best.b2 = b2; best.prim = prim;
-                    }
-                }
-            }
-            node = stack[--sp];
-        }
-    }
-    return best;
+    int stack[PTB_BVH_STACK];
+    Trav t;
+    trav_begin(t, stack, o, d, tmin, tmax);
+    while (!trav_run<COUNT>(t, stack, nodes, tris, 1 << 20, cnt)) {}
+    return t.best;
 }
 
 }  // namespace ptb

@@ -1,0 +1,239 @@
+// chunked.cuh -- the block-local wavefront: the stages of kernels.cuh run over CHUNKS of the path pool.
+//
+// Why (profiles/r1_v2_*): with global queues appended by atomics, the slot order of a queue degrades with
+// every bounce, so k_shade / k_miss gather their 16-byte path-state records from half-used 32-byte sectors all
+// over a pool that is larger than L2 (1.6 GB at 8 subframes): both kernels sat at ~45 % of HBM peak, stalled on
+// long-scoreboard, with an L2 hit rate below 30 % even for the 2 MB of geometry.
+//
+// Layout: one status byte per slot (ST_TRACE / ST_HIT / ST_MISS / ST_DONE).  A block owns PTB_CHUNK
+// consecutive slots.  Every stage first compacts the slots of its chunk that are in the wanted state into a list
+// in shared memory (8 status bytes per thread, warp ballot-free popcount + block scan; the list is ascending, so
+// the state accesses that follow are coalesced and fully use their sectors), then runs the stage body over that
+// list with all lanes busy:
+//   trace   lanes fetch rays from the shared list dynamically (shared-memory atomic per warp) and advance them
+//           in quanta (trav_run), as in k_trace
+//   shade   closest hit + Russian roulette + path regeneration
+//   miss    environment lookup + path regeneration
+// Two drivers share the stage bodies:
+//   k_chunk_trace / k_chunk_shade / k_chunk_miss   one kernel per stage and wavefront iteration
+//   k_chunk_fused                                  a block loops trace -> shade -> miss over ITS chunk until every
+//                                                  pixel of the chunk has finished its samples: one launch, the
+//                                                  chunk's 96 KB of path state stays in L2/L1 between stages.
+// Counters (segments, hits, misses) are summed per block and added to the context totals once per block.
+#pragma once
+#include "kernels.cuh"
+
+namespace ptb {
+
+#define PTB_CHUNK 1024           // slots per block
+#define PTB_CHUNK_THREADS 128    // 8 slots per thread in the compaction step
+
+enum SlotStatus : unsigned char { ST_DONE = 0, ST_TRACE = 1, ST_HIT = 2, ST_MISS = 3 };
+
+struct ChunkShared {
+    unsigned short list[PTB_CHUNK];  // slot offsets inside the chunk, ascending
+    unsigned int warp_sums[PTB_CHUNK_THREADS / 32];
+    unsigned int n;                  // list length
+    unsigned int next;               // dynamic fetch cursor of the trace stage
+    unsigned int count[4];           // per-block totals: segments, hits, misses, -
+};
+
+// Compacts the offsets of the chunk's slots whose status == want into sh.list (ascending).  Block-uniform result.
+PTB_DEV unsigned int chunk_build_list(ChunkShared& sh, const unsigned char* __restrict__ status, uint32_t base,
+                                      uint32_t n_slots, unsigned char want) {
+    const unsigned int tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t first = base + tid * 8u;
+    unsigned long long bytes = 0ull;
+    if (first + 8u <= n_slots) bytes = *reinterpret_cast<const unsigned long long*>(status + first);
+    else for (uint32_t k = 0; k < 8u; ++k) if (first + k < n_slots) bytes |= (unsigned long long)status[first + k] << (8u * k);
+    unsigned int match = 0;  // bit k set when byte k == want
+#pragma unroll
+    for (int k = 0; k < 8; ++k) match |= (((bytes >> (8 * k)) & 0xffull) == (unsigned long long)want ? 1u : 0u) << k;
+    if (first + 8u > n_slots) for (uint32_t k = 0; k < 8u; ++k) if (first + k >= n_slots) match &= ~(1u << k);
+    const unsigned int mine = (unsigned int)__popc(match);
+    unsigned int incl = mine;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) { const unsigned int y = __shfl_up_sync(0xffffffffu, incl, off); if ((int)lane >= off) incl += y; }
+    if (lane == 31u) sh.warp_sums[warp] = incl;
+    __syncthreads();
+    unsigned int warp_off = 0, total = 0;
+#pragma unroll
+    for (unsigned int w = 0; w < PTB_CHUNK_THREADS / 32; ++w) { const unsigned int v = sh.warp_sums[w]; if (w < warp) warp_off += v; total += v; }
+    unsigned int pos = warp_off + incl - mine;
+    unsigned int m = match;
+    while (m) { const int k = __ffs(m) - 1; m &= m - 1u; sh.list[pos++] = (unsigned short)(tid * 8u + (unsigned int)k); }
+    if (tid == 0) { sh.n = total; sh.next = 0; }
+    __syncthreads();
+    return total;
+}
+
+// ---- stage bodies over one chunk ---------------------------------------------------------------------------
+template <bool COUNT, int QUANTUM>
+PTB_DEV void chunk_stage_trace(ChunkShared& sh, const SceneView& s, const FrameView& f, const PathView& p,
+                               unsigned char* __restrict__ status, uint32_t base, unsigned int n, bool first_iteration,
+                               TravCounters& tc) {
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int stack[PTB_BVH_STACK];
+    Trav t;
+    t.node = PTB_TRAV_SENTINEL; t.sp = 0; t.best.prim = -1; t.best.t = 0.0f; t.best.b1 = 0.0f; t.best.b2 = 0.0f;
+    uint32_t slot = 0;
+    bool have = false, exhausted = false;
+    unsigned int hits = 0;
+    for (;;) {
+        __syncwarp();
+        if (!exhausted) {
+            const unsigned need = __ballot_sync(0xffffffffu, !have);
+            if (need) {
+                const int leader = __ffs(need) - 1;
+                const unsigned int cnt = (unsigned int)__popc(need);
+                unsigned int b0 = 0;
+                if ((int)lane == leader) b0 = atomicAdd(&sh.next, cnt);
+                b0 = __shfl_sync(0xffffffffu, b0, leader);
+                const unsigned int idx = b0 + (unsigned int)__popc(need & lt_mask);
+                if (!have && idx < n) {
+                    slot = base + sh.list[idx];
+                    const float4 o4 = p.ray_o[slot], d4 = p.ray_d[slot];
+                    trav_begin(t, stack, mk3(o4), mk3(d4), f.tmin, f.tmax);
+                    have = true;
+                }
+                if (b0 + cnt >= n) exhausted = true;  // warp-uniform
+            }
+        }
+        if (!__any_sync(0xffffffffu, have)) break;
+        if (have && trav_run<COUNT>(t, stack, s.nodes, s.tris, QUANTUM, &tc)) {
+            have = false;
+            p.hit[slot] = make_float4(t.best.t, t.best.b1, t.best.b2, __int_as_float(t.best.prim));
+            const bool is_hit = t.best.prim >= 0;
+            status[slot] = is_hit ? ST_HIT : ST_MISS;
+            hits += is_hit ? 1u : 0u;
+            if (first_iteration && f.aux_primary && slot < f.n_pixels) f.aux_primary[slot] = t.best.prim;
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) hits += __shfl_xor_sync(0xffffffffu, hits, off);
+    if (lane == 0u && hits) atomicAdd(&sh.count[1], hits);
+}
+
+PTB_DEV void chunk_stage_shade(ChunkShared& sh, const SceneView& s, const FrameView& f, const PathView& p,
+                               unsigned char* __restrict__ status, uint32_t base, unsigned int n) {
+    for (unsigned int i = threadIdx.x; i < n; i += PTB_CHUNK_THREADS) {
+        const uint32_t slot = base + sh.list[i];
+        const float4 o4 = p.ray_o[slot], d4 = p.ray_d[slot], h4 = p.hit[slot], as = p.atten_seed[slot];
+        const uint4 mi = p.misc[slot];
+        Bounce b;
+        b.atten = mk3(as); b.seed = __float_as_uint(as.w);
+        const int depth = (int)mi.y;
+        closest_hit(s, f, __float_as_int(h4.w), h4.y, h4.z, h4.x, mk3(o4), mk3(d4), depth, b);
+        status[slot] = after_segment(f, p, slot, b, mi.x, depth, mi.z) ? ST_TRACE : ST_DONE;
+    }
+}
+
+PTB_DEV void chunk_stage_miss(ChunkShared& sh, const SceneView& s, const FrameView& f, const PathView& p,
+                              unsigned char* __restrict__ status, uint32_t base, unsigned int n) {
+    for (unsigned int i = threadIdx.x; i < n; i += PTB_CHUNK_THREADS) {
+        const uint32_t slot = base + sh.list[i];
+        const float4 d4 = p.ray_d[slot], as = p.atten_seed[slot];
+        const uint4 mi = p.misc[slot];
+        const float3 ray_dir = normalize(mk3(d4));
+        const float u = 0.5f + det_atan2f(ray_dir.z, ray_dir.x) / (2.0f * PTB_PI_F);
+        const float v = 0.5f - det_asinf(ray_dir.y) / PTB_PI_F;
+        const float4 hdr = sample_env(s.env, s.env_w, s.env_h, u, v);
+        Bounce b;
+        b.atten = mk3(as); b.seed = __float_as_uint(as.w);
+        b.radiance = mk3(0.0f) + b.atten * mk3(hdr);
+        b.origin = mk3(0.0f); b.direction = mk3(0.0f);
+        b.done = 1;
+        status[slot] = after_segment(f, p, slot, b, mi.x, (int)mi.y, mi.z) ? ST_TRACE : ST_DONE;
+    }
+}
+
+PTB_DEV void chunk_flush_counts(ChunkShared& sh, unsigned long long* __restrict__ totals, unsigned long long* trav_stats,
+                                const TravCounters& tc, bool count) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (sh.count[0]) atomicAdd(&totals[0], (unsigned long long)sh.count[0]);
+        if (sh.count[1]) atomicAdd(&totals[1], (unsigned long long)sh.count[1]);
+        if (sh.count[0] - sh.count[1]) atomicAdd(&totals[2], (unsigned long long)(sh.count[0] - sh.count[1]));
+    }
+    if (count) {
+        unsigned long long a = tc.nodes, b = tc.tris;
+        for (int off = 16; off > 0; off >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, off); b += __shfl_xor_sync(0xffffffffu, b, off); }
+        if ((threadIdx.x & 31u) == 0u) { atomicAdd(&trav_stats[0], a); atomicAdd(&trav_stats[1], b); }
+    }
+}
+
+// ---- drivers ------------------------------------------------------------------------------------------------
+// camera rays of sample 0 (the raygen stage) for the chunked pool: same as k_raygen_init + status
+__global__ void __launch_bounds__(256) k_chunk_raygen(FrameView f, PathView p, unsigned char* __restrict__ status) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n_slots) return;
+    const uint32_t pix = i % f.n_pixels, sub = i / f.n_pixels;
+    const uint32_t ix = pix % f.W, iy = pix / f.W;
+    uint32_t seed = iy * f.W + ix + ((uint32_t)f.subframe + sub) * f.W * f.H;  // cu:316
+    float3 o, d;
+    start_sample(f, ix, iy, seed, o, d);
+    p.ray_o[i] = make_float4(o.x, o.y, o.z, 0.0f);
+    p.ray_d[i] = make_float4(d.x, d.y, d.z, 0.0f);
+    p.atten_seed[i] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(seed));
+    p.misc[i] = make_uint4(seed, (uint32_t)f.max_depth, 0u, 0u);
+    p.pixsum[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    status[i] = ST_TRACE;
+}
+
+template <bool COUNT, int QUANTUM>
+__global__ void __launch_bounds__(PTB_CHUNK_THREADS) k_chunk_trace(SceneView s, FrameView f, PathView p, unsigned char* status,
+                                                                  unsigned long long* totals, unsigned long long* trav_stats, int iter) {
+    __shared__ ChunkShared sh;
+    const uint32_t base = blockIdx.x * PTB_CHUNK;
+    if (threadIdx.x < 4) sh.count[threadIdx.x] = 0;
+    const unsigned int n = chunk_build_list(sh, status, base, p.n_slots, ST_TRACE);
+    if (n == 0) return;
+    if (threadIdx.x == 0) sh.count[0] = n;
+    TravCounters tc; tc.nodes = 0; tc.tris = 0;
+    chunk_stage_trace<COUNT, QUANTUM>(sh, s, f, p, status, base, n, iter == 0, tc);
+    chunk_flush_counts(sh, totals, trav_stats, tc, COUNT);
+}
+
+__global__ void __launch_bounds__(PTB_CHUNK_THREADS) k_chunk_shade(SceneView s, FrameView f, PathView p, unsigned char* status) {
+    __shared__ ChunkShared sh;
+    const uint32_t base = blockIdx.x * PTB_CHUNK;
+    const unsigned int n = chunk_build_list(sh, status, base, p.n_slots, ST_HIT);
+    if (n) chunk_stage_shade(sh, s, f, p, status, base, n);
+}
+
+__global__ void __launch_bounds__(PTB_CHUNK_THREADS) k_chunk_miss(SceneView s, FrameView f, PathView p, unsigned char* status) {
+    __shared__ ChunkShared sh;
+    const uint32_t base = blockIdx.x * PTB_CHUNK;
+    const unsigned int n = chunk_build_list(sh, status, base, p.n_slots, ST_MISS);
+    if (n) chunk_stage_miss(sh, s, f, p, status, base, n);
+}
+
+// One block = one chunk, from the first camera ray to the last sample of its pixels.
+// totals[3] is not touched here (launch count is added by k_fold_counters' sibling on the host path).
+template <bool COUNT, int QUANTUM>
+__global__ void __launch_bounds__(PTB_CHUNK_THREADS) k_chunk_fused(SceneView s, FrameView f, PathView p, unsigned char* status,
+                                                                  unsigned long long* totals, unsigned long long* trav_stats,
+                                                                  unsigned int* max_iters_seen) {
+    __shared__ ChunkShared sh;
+    const uint32_t base = blockIdx.x * PTB_CHUNK;
+    if (threadIdx.x < 4) sh.count[threadIdx.x] = 0;
+    TravCounters tc; tc.nodes = 0; tc.tris = 0;
+    unsigned int iter = 0;
+    for (;; ++iter) {
+        const unsigned int nt = chunk_build_list(sh, status, base, p.n_slots, ST_TRACE);
+        if (nt == 0) break;
+        if (threadIdx.x == 0) sh.count[0] += nt;
+        chunk_stage_trace<COUNT, QUANTUM>(sh, s, f, p, status, base, nt, iter == 0, tc);
+        __syncthreads();  // status / hit records of this chunk are block-visible from here on
+        const unsigned int nh = chunk_build_list(sh, status, base, p.n_slots, ST_HIT);
+        if (nh) chunk_stage_shade(sh, s, f, p, status, base, nh);
+        __syncthreads();
+        const unsigned int nm = chunk_build_list(sh, status, base, p.n_slots, ST_MISS);
+        if (nm) chunk_stage_miss(sh, s, f, p, status, base, nm);
+        __syncthreads();
+    }
+    chunk_flush_counts(sh, totals, trav_stats, tc, COUNT);
+    if (threadIdx.x == 0) atomicMax(max_iters_seen, iter);
+}
+
+}  // namespace ptb

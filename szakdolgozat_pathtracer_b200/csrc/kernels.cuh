@@ -37,7 +37,9 @@ struct SceneView {
 
 struct FrameView {
     uint32_t W, H;
-    int subframe, dof;
+    uint32_t n_pixels;   // W * H
+    int n_subframes;     // subframes rendered by this launch as ONE wavefront (slot = sub * n_pixels + pixel)
+    int subframe, dof;   // subframe = index of the first one
     float3 eye, U, V, Wv;
     int spp, max_depth;
     float tmin, tmax, dof_blur, focus_dist, nmap_strength;
@@ -57,7 +59,7 @@ struct PathView {
     uint32_t n_slots;
 };
 
-// counters[iter*4 + 0] = rays to trace in iteration iter, +1 = hits, +2 = misses
+// counters[iter*4 + 0] = rays to trace in iteration iter, +1 = hits, +2 = misses, +3 = k_trace's work counter
 struct QueueView {
     uint32_t* trace[2];
     uint32_t* hit;
@@ -96,8 +98,9 @@ __global__ void __launch_bounds__(256) k_raygen_init(FrameView f, PathView p, Qu
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) q.counters[0] = p.n_slots;
     if (i >= p.n_slots) return;
-    const uint32_t ix = i % f.W, iy = i / f.W;
-    uint32_t seed = iy * f.W + ix + (uint32_t)f.subframe * f.W * f.H;  // cu:316
+    const uint32_t pix = i % f.n_pixels, sub = i / f.n_pixels;
+    const uint32_t ix = pix % f.W, iy = pix / f.W;
+    uint32_t seed = iy * f.W + ix + ((uint32_t)f.subframe + sub) * f.W * f.H;  // cu:316
     float3 o, d;
     start_sample(f, ix, iy, seed, o, d);
     p.ray_o[i] = make_float4(o.x, o.y, o.z, 0.0f);
@@ -109,31 +112,66 @@ __global__ void __launch_bounds__(256) k_raygen_init(FrameView f, PathView p, Qu
 }
 
 // ---- traversal stage ------------------------------------------------------------------
-template <bool COUNT>
+// Persistent warps with dynamic ray fetch.  Every lane owns at most one ray; the warp alternates between
+//   (1) flush: lanes whose ray finished write the hit record and append the slot to the hit or miss queue
+//       (one warp-aggregated atomic per queue),
+//   (2) fetch: idle lanes take the next rays from the iteration's work counter (one atomic per warp),
+//   (3) run:   every lane advances its ray by at most QUANTUM traversal steps (trav_run, while-while),
+// so a lane that finishes early idles for at most one quantum instead of until the slowest ray of its warp
+// is done.  counters[iter*4+3] is the work counter (zeroed with the other counters at launch start).
+template <bool COUNT, int QUANTUM>
 __global__ void __launch_bounds__(128) k_trace(SceneView s, FrameView f, PathView p, QueueView q, int iter) {
     const uint32_t n = q.counters[iter * 4 + 0];
+    if (n == 0) return;
     const uint32_t* __restrict__ in = q.trace[iter & 1];
+    uint32_t* work = &q.counters[iter * 4 + 3];
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
     TravCounters tc; tc.nodes = 0; tc.tris = 0;
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; (i & ~31u) < n; i += stride) {
-        const bool active = i < n;
-        uint32_t slot = 0;
-        bool is_hit = false;
-        if (active) {
-            slot = in[i];
-            const float4 o4 = p.ray_o[slot], d4 = p.ray_d[slot];
-            const HitRec h = bvh_closest_hit<COUNT>(s.nodes, s.tris, mk3(o4), mk3(d4), f.tmin, f.tmax, &tc);
-            p.hit[slot] = make_float4(h.t, h.b1, h.b2, __int_as_float(h.prim));
-            is_hit = h.prim >= 0;
-            if (iter == 0 && f.aux_primary) f.aux_primary[slot] = h.prim;
+    int stack[PTB_BVH_STACK];
+    Trav t;
+    t.node = PTB_TRAV_SENTINEL; t.sp = 0; t.best.prim = -1; t.best.t = 0.0f; t.best.b1 = 0.0f; t.best.b2 = 0.0f;
+    uint32_t slot = 0;
+    bool have = false, pending = false, exhausted = false;
+    for (;;) {
+        __syncwarp();
+        if (__any_sync(0xffffffffu, pending)) {
+            const bool is_hit = t.best.prim >= 0;
+            if (pending) {
+                p.hit[slot] = make_float4(t.best.t, t.best.b1, t.best.b2, __int_as_float(t.best.prim));
+                if (iter == 0 && f.aux_primary && slot < f.n_pixels) f.aux_primary[slot] = t.best.prim;
+            }
+            queue_push(q.hit, &q.counters[iter * 4 + 1], pending && is_hit, slot);
+            queue_push(q.miss, &q.counters[iter * 4 + 2], pending && !is_hit, slot);
+            pending = false;
         }
-        queue_push(q.hit, &q.counters[iter * 4 + 1], active && is_hit, slot);
-        queue_push(q.miss, &q.counters[iter * 4 + 2], active && !is_hit, slot);
+        if (!exhausted) {
+            const unsigned need = __ballot_sync(0xffffffffu, !have);
+            if (need) {
+                const int leader = __ffs(need) - 1;
+                const uint32_t cnt = (uint32_t)__popc(need);
+                uint32_t base = 0;
+                if ((int)lane == leader) base = atomicAdd(work, cnt);
+                base = __shfl_sync(0xffffffffu, base, leader);
+                const uint32_t idx = base + (uint32_t)__popc(need & lt_mask);
+                if (!have && idx < n) {
+                    slot = in[idx];
+                    const float4 o4 = p.ray_o[slot], d4 = p.ray_d[slot];
+                    trav_begin(t, stack, mk3(o4), mk3(d4), f.tmin, f.tmax);
+                    have = true;
+                }
+                if (base + cnt >= n) exhausted = true;  // warp-uniform
+            }
+        }
+        if (!__any_sync(0xffffffffu, have)) break;
+        if (have) {
+            if (trav_run<COUNT>(t, stack, s.nodes, s.tris, QUANTUM, &tc)) { have = false; pending = true; }
+        }
     }
     if (COUNT) {
         unsigned long long a = tc.nodes, b = tc.tris;
         for (int off = 16; off > 0; off >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, off); b += __shfl_xor_sync(0xffffffffu, b, off); }
-        if ((threadIdx.x & 31u) == 0u) { atomicAdd(&q.trav_stats[0], a); atomicAdd(&q.trav_stats[1], b); }
+        if (lane == 0u) { atomicAdd(&q.trav_stats[0], a); atomicAdd(&q.trav_stats[1], b); }
     }
 }
 
@@ -352,7 +390,8 @@ PTB_DEV bool after_segment(const FrameView& f, const PathView& p, uint32_t slot,
     sample += 1u;
     if (sample >= (uint32_t)f.spp) return false;
     float3 o, d;
-    start_sample(f, slot % f.W, slot / f.W, seed_rg, o, d);
+    const uint32_t pix = slot % f.n_pixels;
+    start_sample(f, pix % f.W, pix / f.W, seed_rg, o, d);
     p.ray_o[slot] = make_float4(o.x, o.y, o.z, 0.0f);
     p.ray_d[slot] = make_float4(d.x, d.y, d.z, 0.0f);
     p.atten_seed[slot] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(seed_rg));
@@ -439,16 +478,21 @@ PTB_DEV uchar4 display_color(float3 accum_color, float exposure_scale, float inv
 
 __global__ void __launch_bounds__(256) k_resolve(FrameView f, PathView p) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= p.n_slots) return;
-    const float4 sum = p.pixsum[i];
-    float3 accum_color = mk3(sum) / (float)f.spp;  // cu:401
-    if (f.accumulate_mode == 1) {
-        accum_color = mk3(f.accum[i]) + accum_color;
-    } else if (f.subframe > 0) {
-        const float a = 1.0f / (float)(f.subframe + 1);
-        accum_color = lerp(mk3(f.accum[i]), accum_color, a);  // cu:403-408
+    if (i >= f.n_pixels) return;
+    // the subframes of this launch are folded in order, exactly as consecutive launches would do it
+    float3 accum_color = mk3(0.0f);
+    for (int sub = 0; sub < f.n_subframes; ++sub) {
+        const float4 sum = p.pixsum[(size_t)sub * f.n_pixels + i];
+        accum_color = mk3(sum) / (float)f.spp;  // cu:401
+        const int subframe = f.subframe + sub;
+        if (f.accumulate_mode == 1) {
+            accum_color = mk3(f.accum[i]) + accum_color;
+        } else if (subframe > 0) {
+            const float a = 1.0f / (float)(subframe + 1);
+            accum_color = lerp(mk3(f.accum[i]), accum_color, a);  // cu:403-408
+        }
+        f.accum[i] = make_float4(accum_color.x, accum_color.y, accum_color.z, 1.0f);
     }
-    f.accum[i] = make_float4(accum_color.x, accum_color.y, accum_color.z, 1.0f);
     if (f.write_frame && f.frame) f.frame[i] = display_color(accum_color, f.exposure_scale, f.inv_gamma, f.contrast);
 }
 
@@ -464,7 +508,12 @@ __global__ void __launch_bounds__(256) k_fold_counters(const uint32_t* __restric
         for (int off = 16; off > 0; off >>= 1) s[k] += __shfl_xor_sync(0xffffffffu, s[k], off);
         if ((threadIdx.x & 31u) == 0u && s[k]) atomicAdd(&totals[k], s[k]);
     }
-    if (threadIdx.x == 0) atomicAdd(&totals[3], 1ull);
+}
+
+// launch totals (segments, hits, misses) -> running totals of the context, launches += 1
+__global__ void k_fold_totals(const unsigned long long* __restrict__ launch_totals, unsigned long long* __restrict__ totals) {
+    if (threadIdx.x < 3) atomicAdd(&totals[threadIdx.x], launch_totals[threadIdx.x]);
+    if (threadIdx.x == 3) atomicAdd(&totals[3], 1ull);
 }
 
 // stand-alone accumulate/tonemap over an already reduced accumulator (multi-GPU sample split)

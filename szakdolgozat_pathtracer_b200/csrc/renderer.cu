@@ -17,6 +17,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -24,7 +25,7 @@
 
 #include "bvh_build.h"
 #include "host.h"
-#include "kernels.cuh"
+#include "chunked.cuh"
 
 namespace ptb {
 
@@ -64,6 +65,9 @@ struct ptb_context {
     uint32_t* counters = nullptr; uint32_t counters_cap = 0;  // in iterations
     unsigned long long* trav_stats = nullptr;
     unsigned long long* totals = nullptr;  // segments, hits, misses, launches since the last reset
+    unsigned long long* launch_totals = nullptr;  // the same for the launch in flight ([3]: iterations of the fused pipeline)
+    unsigned char* status = nullptr;       // one byte per slot (chunked pipelines)
+    int last_pipeline = 0;
     // last launch, for ptb_launch_get_stats
     cudaStream_t last_stream = nullptr;
     uint32_t last_iters = 0, last_kernels = 0;
@@ -108,7 +112,8 @@ cudaError_t upload(T** dst, const void* src, size_t bytes, cudaStream_t st) {
 
 void free_pool(ptb_context* c) {
     cudaFree(c->ray_o); cudaFree(c->ray_d); cudaFree(c->hit); cudaFree(c->atten_seed); cudaFree(c->pixsum); cudaFree(c->misc);
-    cudaFree(c->q_trace[0]); cudaFree(c->q_trace[1]); cudaFree(c->q_hit); cudaFree(c->q_miss);
+    cudaFree(c->q_trace[0]); cudaFree(c->q_trace[1]); cudaFree(c->q_hit); cudaFree(c->q_miss); cudaFree(c->status);
+    c->status = nullptr;
     c->ray_o = c->ray_d = c->hit = c->atten_seed = c->pixsum = nullptr; c->misc = nullptr;
     c->q_trace[0] = c->q_trace[1] = c->q_hit = c->q_miss = nullptr;
     c->pool_slots = 0;
@@ -123,6 +128,7 @@ int ensure_pool(ptb_context* c, uint32_t slots, uint32_t iters) {
         CU(cudaMalloc((void**)&c->pixsum, n * 16)); CU(cudaMalloc((void**)&c->misc, n * 16));
         CU(cudaMalloc((void**)&c->q_trace[0], n * 4)); CU(cudaMalloc((void**)&c->q_trace[1], n * 4));
         CU(cudaMalloc((void**)&c->q_hit, n * 4)); CU(cudaMalloc((void**)&c->q_miss, n * 4));
+        CU(cudaMalloc((void**)&c->status, n + 64));
         c->pool_slots = slots;
     }
     if (iters + 2 > c->counters_cap) {
@@ -135,6 +141,7 @@ int ensure_pool(ptb_context* c, uint32_t slots, uint32_t iters) {
         CU(cudaMalloc((void**)&c->totals, 4 * sizeof(unsigned long long)));
         CU(cudaMemset(c->totals, 0, 4 * sizeof(unsigned long long)));
     }
+    if (!c->launch_totals) CU(cudaMalloc((void**)&c->launch_totals, 4 * sizeof(unsigned long long)));
     return PTB_OK;
 }
 
@@ -180,7 +187,7 @@ void ptb_context_destroy(ptb_context* ctx) {
     // scenes stay owned by their ptb_scene; just detach them
     for (auto& kv : ctx->scenes) kv.second->owner = nullptr;
     free_pool(ctx);
-    cudaFree(ctx->counters); cudaFree(ctx->trav_stats); cudaFree(ctx->totals);
+    cudaFree(ctx->counters); cudaFree(ctx->trav_stats); cudaFree(ctx->totals); cudaFree(ctx->launch_totals);
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     delete ctx;
 }
@@ -295,13 +302,16 @@ int ptb_launch(ptb_context* ctx, const ptb_Params* P, const ptb_render_cfg* cfg_
     cudaStream_t st = (cudaStream_t)stream_;
     CU(cudaSetDevice(ctx->device));
 
-    const uint32_t slots = P->image_width * P->image_height;
+    const int n_sub = cfg.subframes_per_launch < 1 ? 1 : cfg.subframes_per_launch;
+    const uint32_t n_pixels = P->image_width * P->image_height;
+    if ((uint64_t)n_pixels * (uint64_t)n_sub > 0x7fffffffull) return fail(PTB_ERR_INVALID, "ptb_launch: subframes_per_launch * pixels too large");
+    const uint32_t slots = n_pixels * (uint32_t)n_sub;
     const uint32_t iters = (uint32_t)cfg.spp_per_launch * (uint32_t)(cfg.max_depth + 1);
     int rc = ensure_pool(ctx, slots, iters);
     if (rc != PTB_OK) return rc;
 
     FrameView f;
-    f.W = P->image_width; f.H = P->image_height; f.subframe = P->subframe_index; f.dof = P->dof ? 1 : 0;
+    f.W = P->image_width; f.H = P->image_height; f.n_pixels = n_pixels; f.n_subframes = n_sub; f.subframe = P->subframe_index; f.dof = P->dof ? 1 : 0;
     f.eye = make_float3(P->eye.x, P->eye.y, P->eye.z); f.U = make_float3(P->U.x, P->U.y, P->U.z);
     f.V = make_float3(P->V.x, P->V.y, P->V.z); f.Wv = make_float3(P->W.x, P->W.y, P->W.z);
     f.spp = cfg.spp_per_launch; f.max_depth = cfg.max_depth; f.tmin = cfg.tmin; f.tmax = cfg.tmax;
@@ -318,8 +328,16 @@ int ptb_launch(ptb_context* ctx, const ptb_Params* P, const ptb_render_cfg* cfg_
     q.counters = ctx->counters; q.trav_stats = ctx->trav_stats;
     const SceneView s = scene_view(d);
 
+    static const int env_tq = getenv("PTB_TRACE_QUANTUM") ? atoi(getenv("PTB_TRACE_QUANTUM")) : 0;
+    static const int env_tb = getenv("PTB_TRACE_BLOCKS_PER_SM") ? atoi(getenv("PTB_TRACE_BLOCKS_PER_SM")) : 0;
+    static const int env_pipe = getenv("PTB_PIPELINE") ? atoi(getenv("PTB_PIPELINE")) : -1;
+    const int tq = env_tq;
+    int pipeline = cfg.pipeline > 0 ? cfg.pipeline : (env_pipe >= 0 ? env_pipe : PTB_PIPELINE_DEFAULT);
+    if (pipeline < PTB_PIPELINE_QUEUES || pipeline > PTB_PIPELINE_CHUNK_FUSED) return fail(PTB_ERR_INVALID, "ptb_launch: unknown pipeline");
+
     CU(cudaMemsetAsync(ctx->counters, 0, (size_t)(iters + 2) * 4 * sizeof(uint32_t), st));
     CU(cudaMemsetAsync(ctx->trav_stats, 0, 2 * sizeof(unsigned long long), st));
+    CU(cudaMemsetAsync(ctx->launch_totals, 0, 4 * sizeof(unsigned long long), st));
     const uint32_t pix_blocks = (slots + 255u) / 256u;
     const bool prof = cfg.profile_stages != 0;
     if (prof) {
@@ -328,30 +346,72 @@ int ptb_launch(ptb_context* ctx, const ptb_Params* P, const ptb_render_cfg* cfg_
         CU(cudaEventRecord(ctx->events[0], st));
     }
     ctx->prof_iters = 0;
-    k_raygen_init<<<pix_blocks, 256, 0, st>>>(f, p, q);
-    if (prof) CU(cudaEventRecord(ctx->events[1], st));
-    // Persistent-style grids: a multiple of the SM count, looping over the queue.
-    const uint32_t need = (slots + 127u) / 128u;
-    const uint32_t cap = (uint32_t)ctx->num_sms * 32u;
-    const uint32_t grid = need < cap ? need : cap;
-    uint32_t launches = 1;
-    for (uint32_t it = 0; it < iters; ++it) {
-        if (cfg.count_traversal) k_trace<true><<<grid, 128, 0, st>>>(s, f, p, q, (int)it);
-        else k_trace<false><<<grid, 128, 0, st>>>(s, f, p, q, (int)it);
-        if (prof) CU(cudaEventRecord(ctx->events[2 + (size_t)it * 3 + 0], st));
-        k_shade<<<grid, 128, 0, st>>>(s, f, p, q, (int)it);
-        if (prof) CU(cudaEventRecord(ctx->events[2 + (size_t)it * 3 + 1], st));
-        k_miss<<<grid, 128, 0, st>>>(s, f, p, q, (int)it);
-        if (prof) CU(cudaEventRecord(ctx->events[2 + (size_t)it * 3 + 2], st));
-        launches += 3;
+    uint32_t launches = 0;
+    uint32_t prof_iters = iters;
+    if (pipeline == PTB_PIPELINE_QUEUES) {
+        // global queues, one kernel per stage and iteration (kernels.cuh)
+        k_raygen_init<<<pix_blocks, 256, 0, st>>>(f, p, q);
+        if (prof) CU(cudaEventRecord(ctx->events[1], st));
+        const uint32_t need = (slots + 127u) / 128u;
+        const uint32_t cap = (uint32_t)ctx->num_sms * 32u;
+        const uint32_t grid = need < cap ? need : cap;
+        const uint32_t tcap = (uint32_t)ctx->num_sms * (uint32_t)(env_tb > 0 ? env_tb : 10);  // k_trace is persistent
+        const uint32_t tgrid = need < tcap ? need : tcap;
+        launches = 1;
+        for (uint32_t it = 0; it < iters; ++it) {
+            if (cfg.count_traversal) k_trace<true, 16><<<tgrid, 128, 0, st>>>(s, f, p, q, (int)it);
+            else if (tq == 4) k_trace<false, 4><<<tgrid, 128, 0, st>>>(s, f, p, q, (int)it);
+            else if (tq == 8) k_trace<false, 8><<<tgrid, 128, 0, st>>>(s, f, p, q, (int)it);
+            else if (tq == 32) k_trace<false, 32><<<tgrid, 128, 0, st>>>(s, f, p, q, (int)it);
+            else k_trace<false, 16><<<tgrid, 128, 0, st>>>(s, f, p, q, (int)it);
+            if (prof) CU(cudaEventRecord(ctx->events[2 + (size_t)it * 3 + 0], st));
+            k_shade<<<grid, 128, 0, st>>>(s, f, p, q, (int)it);
+            if (prof) CU(cudaEventRecord(ctx->events[2 + (size_t)it * 3 + 1], st));
+            k_miss<<<grid, 128, 0, st>>>(s, f, p, q, (int)it);
+            if (prof) CU(cudaEventRecord(ctx->events[2 + (size_t)it * 3 + 2], st));
+            launches += 3;
+        }
+        k_fold_counters<<<1, 256, 0, st>>>(ctx->counters, iters, ctx->launch_totals);
+        launches += 1;
+    } else {
+        // block-local wavefront over chunks of the path pool (chunked.cuh)
+        const uint32_t chunks = (slots + PTB_CHUNK - 1u) / PTB_CHUNK;
+        k_chunk_raygen<<<pix_blocks, 256, 0, st>>>(f, p, ctx->status);
+        if (prof) CU(cudaEventRecord(ctx->events[1], st));
+        launches = 1;
+        if (pipeline == PTB_PIPELINE_CHUNK_STAGES) {
+            for (uint32_t it = 0; it < iters; ++it) {
+                if (cfg.count_traversal) k_chunk_trace<true, 16><<<chunks, PTB_CHUNK_THREADS, 0, st>>>(s, f, p, ctx->status, ctx->launch_totals, ctx->trav_stats, (int)it);
+                else if (tq == 8) k_chunk_trace<false, 8><<<chunks, PTB_CHUNK_THREADS, 0, st>>>(s, f, p, ctx->status, ctx->launch_totals, ctx->trav_stats, (int)it);
+                else k_chunk_trace<false, 16><<<chunks, PTB_CHUNK_THREADS, 0, st>>>(s, f, p, ctx->status, ctx->launch_totals, ctx->trav_stats, (int)it);
+                if (prof) CU(cudaEventRecord(ctx->events[2 + (size_t)it * 3 + 0], st));
+                k_chunk_shade<<<chunks, PTB_CHUNK_THREADS, 0, st>>>(s, f, p, ctx->status);
+                if (prof) CU(cudaEventRecord(ctx->events[2 + (size_t)it * 3 + 1], st));
+                k_chunk_miss<<<chunks, PTB_CHUNK_THREADS, 0, st>>>(s, f, p, ctx->status);
+                if (prof) CU(cudaEventRecord(ctx->events[2 + (size_t)it * 3 + 2], st));
+                launches += 3;
+            }
+        } else {
+            unsigned int* max_iters = (unsigned int*)(ctx->launch_totals + 3);
+            if (cfg.count_traversal) k_chunk_fused<true, 16><<<chunks, PTB_CHUNK_THREADS, 0, st>>>(s, f, p, ctx->status, ctx->launch_totals, ctx->trav_stats, max_iters);
+            else if (tq == 8) k_chunk_fused<false, 8><<<chunks, PTB_CHUNK_THREADS, 0, st>>>(s, f, p, ctx->status, ctx->launch_totals, ctx->trav_stats, max_iters);
+            else k_chunk_fused<false, 16><<<chunks, PTB_CHUNK_THREADS, 0, st>>>(s, f, p, ctx->status, ctx->launch_totals, ctx->trav_stats, max_iters);
+            launches += 1;
+            prof_iters = 0;
+            if (prof) {  // a single kernel: everything between raygen and resolve is reported as "trace"
+                CU(cudaEventRecord(ctx->events[2], st)); CU(cudaEventRecord(ctx->events[3], st)); CU(cudaEventRecord(ctx->events[4], st));
+                prof_iters = 1;
+            }
+        }
     }
-    k_resolve<<<pix_blocks, 256, 0, st>>>(f, p);
-    k_fold_counters<<<1, 256, 0, st>>>(ctx->counters, iters, ctx->totals);
+    k_resolve<<<(n_pixels + 255u) / 256u, 256, 0, st>>>(f, p);
+    k_fold_totals<<<1, 32, 0, st>>>(ctx->launch_totals, ctx->totals);
     launches += 2;
-    if (prof) { CU(cudaEventRecord(ctx->events[2 + (size_t)iters * 3], st)); ctx->prof_iters = iters; }
+    if (prof) { CU(cudaEventRecord(ctx->events[2 + (size_t)prof_iters * 3], st)); ctx->prof_iters = prof_iters; }
     CU(cudaGetLastError());
-    ctx->last_stream = st; ctx->last_iters = iters; ctx->last_kernels = launches;
-    ctx->last_paths = (uint64_t)slots * (uint64_t)cfg.spp_per_launch; ctx->last_counted = cfg.count_traversal != 0;
+    ctx->last_stream = st; ctx->last_iters = iters; ctx->last_kernels = launches; ctx->last_pipeline = pipeline;
+    ctx->last_paths = (uint64_t)slots * (uint64_t)cfg.spp_per_launch;  // slots already counts the batched subframes
+    ctx->last_counted = cfg.count_traversal != 0;
     return PTB_OK;
 }
 
@@ -362,14 +422,14 @@ int ptb_launch_get_stats(ptb_context* ctx, ptb_launch_stats* out) {
     CU(cudaSetDevice(ctx->device));
     std::vector<uint32_t> h((size_t)(ctx->last_iters + 1) * 4);
     CU(cudaMemcpyAsync(h.data(), ctx->counters, h.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->last_stream));
-    unsigned long long tv[2] = {0, 0};
+    unsigned long long tv[2] = {0, 0}, lt[4] = {0, 0, 0, 0};
     CU(cudaMemcpyAsync(tv, ctx->trav_stats, sizeof(tv), cudaMemcpyDeviceToHost, ctx->last_stream));
+    CU(cudaMemcpyAsync(lt, ctx->launch_totals, sizeof(lt), cudaMemcpyDeviceToHost, ctx->last_stream));
     CU(cudaStreamSynchronize(ctx->last_stream));
+    out->segments = lt[0]; out->hits = lt[1]; out->misses = lt[2];
     uint32_t used = 0;
-    for (uint32_t it = 0; it < ctx->last_iters; ++it) {
-        out->segments += h[(size_t)it * 4 + 0]; out->hits += h[(size_t)it * 4 + 1]; out->misses += h[(size_t)it * 4 + 2];
-        if (h[(size_t)it * 4 + 0]) used = it + 1;
-    }
+    if (ctx->last_pipeline == PTB_PIPELINE_CHUNK_FUSED) used = (uint32_t)(lt[3] & 0xffffffffull);
+    else for (uint32_t it = 0; it < ctx->last_iters; ++it) if (h[(size_t)it * 4 + 0]) used = it + 1;
     out->paths = ctx->last_paths; out->iterations = used; out->kernel_launches = ctx->last_kernels;
     if (ctx->last_counted) { out->nodes_visited = tv[0]; out->tris_tested = tv[1]; }
     return PTB_OK;

@@ -14,6 +14,18 @@ from scenes import CAMERAS, load_config, random_rays
 
 pytestmark = pytest.mark.gpu
 
+# every parity test runs on all three pipelines (global queues / chunked stages / chunked fused): the results must be
+# bit-identical because a slot's arithmetic never depends on the order in which slots are processed
+PIPELINE = 0
+
+
+@pytest.fixture(autouse=True, params=[1, 2, 3], ids=["queues", "chunk-stages", "chunk-fused"])
+def _pipeline(request):
+    global PIPELINE
+    PIPELINE = request.param
+    yield
+    PIPELINE = 0
+
 
 def _render_gpu(ptb, ctx, handle, W, H, cfg_kw, subframes=1, dof=True, camera="default", accum0=None):
     n = W * H
@@ -28,7 +40,7 @@ def _render_gpu(ptb, ctx, handle, W, H, cfg_kw, subframes=1, dof=True, camera="d
         for sf in range(subframes):
             p = ptb.make_params(W, H, subframe_index=sf, dof=dof, **CAMERAS[camera])
             p.accum_buffer, p.frame_buffer, p.handle = d_accum, d_frame, handle
-            cfg = ptb.default_render_cfg(aux_primary_hit=d_hits if sf == 0 else None, **cfg_kw)
+            cfg = ptb.default_render_cfg(aux_primary_hit=d_hits if sf == 0 else None, pipeline=PIPELINE, **cfg_kw)
             ctx.launch(p, cfg)
             stats.append(ctx.launch_stats())
         accum = ctx.to_host(d_accum, (H, W, 4), np.float32)
@@ -212,3 +224,28 @@ def test_sum_mode_and_resolve(ptb, ctx, oh, assets):
     assert np.allclose(mean[..., :3], ga[..., :3] * np.float32(1.0 / 3.0), rtol=0, atol=0)
     assert frame[..., 3].min() == 255 and frame[..., :3].max() > 0
     assert np.all(ga[..., :3] >= per[0][..., :3] - 1e-6)
+
+
+def test_batched_subframes_bit_identical_to_consecutive_launches(ptb, ctx, assets):
+    """subframes_per_launch = n renders n subframes as one wavefront; accum/frame must equal n consecutive launches."""
+    sc = load_config(ptb, assets, "c1", small=True)
+    handle, _ = ctx.accel_build(sc)
+    W, H, n = 200, 120, 200 * 120
+    kw = dict(spp_per_launch=3, max_depth=6)
+    seq_a, seq_f, _, seq_st = _render_gpu(ptb, ctx, handle, W, H, kw, subframes=5)
+    d_accum, d_frame = ctx.alloc(n * 16), ctx.alloc(n * 4)
+    try:
+        ctx.memset(d_accum, 0, n * 16)
+        seg = 0
+        for first, cnt in ((0, 3), (3, 2)):  # two batches: 3 + 2 subframes
+            p = ptb.make_params(W, H, subframe_index=first, dof=True)
+            p.accum_buffer, p.frame_buffer, p.handle = d_accum, d_frame, handle
+            ctx.launch(p, ptb.default_render_cfg(subframes_per_launch=cnt, pipeline=PIPELINE, **kw))
+            seg += ctx.launch_stats().segments
+        a = ctx.to_host(d_accum, (H, W, 4), np.float32)
+        f = ctx.to_host(d_frame, (H, W, 4), np.uint8)
+    finally:
+        ctx.free(d_accum); ctx.free(d_frame)
+    assert seg == sum(s.segments for s in seq_st)
+    assert np.array_equal(a.view(np.uint32), seq_a.view(np.uint32))
+    assert np.array_equal(f, seq_f)

@@ -23,6 +23,9 @@ ap.add_argument("--depth", type=int, default=8)
 ap.add_argument("--launches", type=int, default=4)
 ap.add_argument("--count", type=int, default=0)
 ap.add_argument("--leaf", type=int, default=4)
+ap.add_argument("--batch", type=int, default=1, help="subframes_per_launch")
+ap.add_argument("--stages", type=int, default=0)
+ap.add_argument("--pipeline", type=int, default=0)
 a = ap.parse_args()
 
 ctx = ptb.Context(0)
@@ -35,12 +38,13 @@ W, H = a.width, a.height
 n = W * H
 d_accum, d_frame = ctx.alloc(n * 16), ctx.alloc(n * 4)
 ctx.memset(d_accum, 0, n * 16)
-cfg = ptb.default_render_cfg(spp_per_launch=a.spp, max_depth=a.depth, count_traversal=a.count)
+cfg = ptb.default_render_cfg(spp_per_launch=a.spp, max_depth=a.depth, count_traversal=a.count, subframes_per_launch=a.batch,
+                             profile_stages=a.stages, pipeline=a.pipeline)
 for rep in range(2):
     seg = 0
     ctx.synchronize()
     t0 = time.time()
-    for sf in range(a.launches):
+    for sf in range(0, a.launches * a.batch, a.batch):
         p = ptb.make_params(W, H, subframe_index=sf, dof=True, **CAMERAS[a.camera])
         p.accum_buffer, p.frame_buffer, p.handle = d_accum, d_frame, handle
         ctx.launch(p, cfg)
@@ -50,7 +54,9 @@ st = ctx.launch_stats()
 seg = st.segments * a.launches
 print(f"{a.config}/{a.camera} {W}x{H} spp {a.spp} depth {a.depth}: {dt / a.launches * 1e3:.2f} ms/launch, "
       f"~{seg / dt / 1e6:.1f} Msegments/s (last-launch segments {st.segments}, iterations {st.iterations}, "
-      f"hits {st.hits}, misses {st.misses}), {a.spp * a.launches / dt * (n / (1920 * 1080)):.1f} 1080p-spp/s")
+      f"hits {st.hits}, misses {st.misses}), {a.spp * a.launches * a.batch / dt * (n / (1920 * 1080)):.1f} 1080p-spp/s")
+if a.stages:
+    print("stage ms (last launch):", {k: round(v, 3) for k, v in ctx.stage_ms().items()})
 if a.count:
     print(f"nodes/seg {st.nodes_visited / st.segments:.2f}, tris/seg {st.tris_tested / st.segments:.2f}")
 frame = ctx.to_host(d_frame, (H, W, 4), np.uint8)
