@@ -3,8 +3,9 @@
 
 Workload (BASELINE.json configs[1], "C2"): monkey.obj + monkey_albedo.png under the
 synthetic env2.exr (2048x1024, seed 2), 1920x1080, 64 spp, depth 8, reference camera.
-One STEP = one full 64-spp frame = 8 launches of 8 samples per pixel through the C-ABI
-call ptb_launch() (the optixLaunch of the reference's render loop, optixSphere.cpp:1403-1418).
+One STEP = one full 64-spp frame = 8 subframes of 8 samples per pixel, rendered by ONE C-ABI call
+ptb_launch() with subframes_per_launch = 8 (bit-identical to 8 consecutive calls, i.e. to 8 optixLaunch
+iterations of the reference's render loop, optixSphere.cpp:1390-1437; tests/test_gpu_parity.py checks it).
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            our CUDA path
   python bench.py --impl reference [--gpus N] [--steps K] ...    the reference's own device file compiled for the
@@ -34,7 +35,7 @@ for p in (ROOT, ROOT / "tests", ROOT / "tools"):
 import numpy as np
 
 W, H, SPP_PER_LAUNCH, LAUNCHES_PER_STEP, DEPTH = 1920, 1080, 8, 8, 8
-WORKLOAD = "C2: monkey.obj+monkey_albedo.png, env2 2048x1024 (synthetic, seed 2), 1920x1080, 64 spp (8 launches x 8), depth 8, reference camera, DoF on"
+WORKLOAD = "C2: monkey.obj+monkey_albedo.png, env2 2048x1024 (synthetic, seed 2), 1920x1080, 64 spp (8 subframes x 8), depth 8, reference camera, DoF on"
 
 
 def measured_peaks():
@@ -148,6 +149,7 @@ def main():
     ap.add_argument("--ref-rows", type=int, default=48, help="rows of the frame per step of the CPU reference arm")
     ap.add_argument("--cpu-rows", type=int, default=160, help="rows of the frame for the cpu_baseline sample of our arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pipeline", type=int, default=2, help="1 global queues, 2 chunked stage kernels (default), 3 chunked fused")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -184,17 +186,19 @@ def main():
     accum = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
     frame = torch.zeros((H, W, 4), dtype=torch.uint8, device=dev)
     multi = world > 1
-    cfg = ptb.default_render_cfg(spp_per_launch=SPP_PER_LAUNCH, max_depth=DEPTH,
-                                 accumulate_mode=1 if multi else 0, write_frame=0 if multi else 1)
+    # the whole 64-spp frame of this rank is ONE wavefront: 8 subframes x 1920 x 1080 path slots
+    cfg = ptb.default_render_cfg(spp_per_launch=SPP_PER_LAUNCH, max_depth=DEPTH, subframes_per_launch=LAUNCHES_PER_STEP,
+                                 pipeline=args.pipeline, accumulate_mode=1 if multi else 0, write_frame=0 if multi else 1)
 
     def one_step(step_index, cfg_used):
         # a fresh 64-spp frame: the accumulator restarts (the reference resets subframe_index on camera change, cpp:267-278)
         if multi:
             accum.zero_()
-        for sub in parallel.subframes_for_rank(rank, world, LAUNCHES_PER_STEP * world):
-            p = ptb.make_params(W, H, subframe_index=sub, dof=True, **CAMERAS["default"])
-            p.accum_buffer, p.frame_buffer, p.handle = accum.data_ptr(), frame.data_ptr(), handle
-            ctx.launch(p, cfg_used, stream=stream)
+        # rank r renders the contiguous block of subframes [r*8, r*8+8) of the 64*N-spp frame
+        first = parallel.subframe_block_for_rank(rank, world, LAUNCHES_PER_STEP * world)[0]
+        p = ptb.make_params(W, H, subframe_index=first, dof=True, **CAMERAS["default"])
+        p.accum_buffer, p.frame_buffer, p.handle = accum.data_ptr(), frame.data_ptr(), handle
+        ctx.launch(p, cfg_used, stream=stream)
         if multi:
             parallel.reduce_accumulator(accum, dst=0)
             if rank == 0:
@@ -230,22 +234,20 @@ def main():
         dist.all_reduce(segs, op=dist.ReduceOp.SUM)
     ms_max, seg_total = float(t.item()), float(segs.item())
     value = seg_total / (ms_max * 1e-3) / 1e6
-    launches_per_launch = 3 * SPP_PER_LAUNCH * (DEPTH + 1) + 3
-    gpu_launches = launches_per_launch * LAUNCHES_PER_STEP * args.steps + (args.steps if multi and rank == 0 else 0)
+    gpu_launches = int(ctx.launch_stats().kernel_launches) * args.steps + (args.steps if multi and rank == 0 else 0)
 
     # ---- stage shares + roofline of the dominant kernel (CUDA events inside ptb_launch, same stream) ----
-    cfg_prof = ptb.default_render_cfg(spp_per_launch=SPP_PER_LAUNCH, max_depth=DEPTH, accumulate_mode=cfg.accumulate_mode,
-                                      write_frame=cfg.write_frame, profile_stages=1)
+    cfg_prof = ptb.default_render_cfg(spp_per_launch=SPP_PER_LAUNCH, max_depth=DEPTH, subframes_per_launch=LAUNCHES_PER_STEP,
+                                      pipeline=args.pipeline, accumulate_mode=cfg.accumulate_mode, write_frame=cfg.write_frame, profile_stages=1)
     stage = {k: 0.0 for k in ("raygen", "trace", "shade", "miss", "resolve", "total")}
-    accum.zero_()
-    for sub in parallel.subframes_for_rank(rank, world, LAUNCHES_PER_STEP * world):
-        p = ptb.make_params(W, H, subframe_index=sub, dof=True, **CAMERAS["default"])
-        p.accum_buffer, p.frame_buffer, p.handle = accum.data_ptr(), frame.data_ptr(), handle
-        ctx.launch(p, cfg_prof, stream=stream)
+    prof_reps = max(1, min(args.steps, 3))
+    for _ in range(prof_reps):
+        accum.zero_()
+        one_step(0, cfg_prof)
         for kk, v in ctx.stage_ms().items():
-            stage[kk] += v
+            stage[kk] += v / prof_reps
     # traversal work per segment, from one instrumented launch of the same subframe 0
-    cfg_cnt = ptb.default_render_cfg(spp_per_launch=SPP_PER_LAUNCH, max_depth=DEPTH, write_frame=0, count_traversal=1)
+    cfg_cnt = ptb.default_render_cfg(spp_per_launch=SPP_PER_LAUNCH, max_depth=DEPTH, write_frame=0, count_traversal=1, pipeline=args.pipeline)
     p = ptb.make_params(W, H, subframe_index=0, dof=True, **CAMERAS["default"])
     scratch = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
     p.accum_buffer, p.frame_buffer, p.handle = scratch.data_ptr(), frame.data_ptr(), handle
@@ -257,7 +259,7 @@ def main():
     # k_trace algorithmic bytes per segment: queue index 4 + ray 32 read, hit record 16 + queue append 4 written,
     # 64 B per node visited, 48 B per triangle tested
     trace_bytes_per_seg = 4 + 32 + 16 + 4 + 64.0 * nodes_per_seg + 48.0 * tris_per_seg
-    trace_launches = LAUNCHES_PER_STEP * SPP_PER_LAUNCH * (DEPTH + 1)
+    trace_launches = SPP_PER_LAUNCH * (DEPTH + 1)  # one k_chunk_trace per wavefront iteration
     peak, peak_src = measured_peaks()
     trace_s = stage["trace"] * 1e-3
     achieved = trace_bytes_per_seg * seg_per_step / trace_s / 1e9 if trace_s > 0 else 0.0
@@ -269,7 +271,7 @@ def main():
         except Exception:
             traffic = None
     roofline = {
-        "kernel": "k_trace", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "kernel": "k_chunk_trace", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "traffic": traffic, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": trace_bytes_per_seg * seg_per_step / trace_launches,
         "avg_launch_ms": stage["trace"] / trace_launches, "nodes_per_segment": nodes_per_seg, "tris_per_segment": tris_per_seg,
@@ -317,7 +319,9 @@ def main():
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "spp_per_step_per_gpu": SPP_PER_LAUNCH * LAUNCHES_PER_STEP,
-                       "l2": "no flush: path pool + queues are 232 MB per launch (> 126 MB L2) and are rewritten every iteration",
+                       "l2": "no flush: the path pool of one step is 8 x 1920 x 1080 slots x 97 B = 1.6 GB (> 126 MB L2) and is rewritten every iteration",
+                       "pipeline": {1: "global queues", 2: "block-local wavefront, one kernel per stage and iteration", 3: "block-local wavefront, fused persistent kernel"}[args.pipeline],
+                       "subframes_per_launch": LAUNCHES_PER_STEP,
                        "multi_gpu": "scene replicated, subframes split by rank, NCCL reduce of the float4 accumulator" if multi else "single GPU, reference accumulate mode",
                        "bvh": {"triangles": bst.num_triangles, "nodes": bst.num_nodes, "max_depth": bst.max_depth, "sah": bst.sah_cost, "build_ms": bst.build_ms}},
             "spp_per_s_1080p": SPP_PER_LAUNCH * LAUNCHES_PER_STEP * world * args.steps / (ms_max * 1e-3),

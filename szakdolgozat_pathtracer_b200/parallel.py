@@ -16,6 +16,16 @@ def subframes_for_rank(rank: int, world: int, n_subframes: int, first: int = 0) 
     return list(range(first + rank, first + n_subframes, world))
 
 
+def subframe_block_for_rank(rank: int, world: int, n_subframes: int, first: int = 0) -> list[int]:
+    """Contiguous split: rank r gets subframes [first + r*k, first + (r+1)*k), k = ceil(n/world) (the last ranks may get
+    fewer or none).  Used when a rank renders its share as ONE batched launch (subframes_per_launch = len(result))."""
+    if world < 1 or not (0 <= rank < world) or n_subframes < 0:
+        raise ValueError("bad rank/world/n_subframes")
+    k = -(-n_subframes // world)
+    lo, hi = min(rank * k, n_subframes), min((rank + 1) * k, n_subframes)
+    return list(range(first + lo, first + hi))
+
+
 def resolve_scale(n_subframes: int) -> float:
     """Factor that turns the reduced sum of launch means into the frame mean."""
     if n_subframes < 1:
