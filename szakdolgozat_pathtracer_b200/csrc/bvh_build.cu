@@ -28,6 +28,7 @@
 #include <vector>
 
 #include "bvh_build.h"
+#include "bvh_refine.cuh"
 #include "device_math.cuh"
 
 namespace ptb {
@@ -227,7 +228,7 @@ __global__ void k_leaf_boxes(const float4* __restrict__ tri_lo, const float4* __
 __global__ void k_refit(const int2* __restrict__ children, const int* __restrict__ node_parent,
                         const int* __restrict__ leaf_parent, const float4* __restrict__ leaf_lo,
                         const float4* __restrict__ leaf_hi, int n, float4* __restrict__ node_lo, float4* __restrict__ node_hi,
-                        unsigned int* __restrict__ flags, unsigned int* __restrict__ max_depth) {
+                        unsigned int* __restrict__ flags) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int node = leaf_parent[i];
@@ -245,10 +246,6 @@ __global__ void k_refit(const int2* __restrict__ children, const int* __restrict
         __threadfence();
         node = node_parent[node];
     }
-    // depth of this leaf (number of internal nodes above it)
-    unsigned int depth = 0;
-    for (int p = leaf_parent[i]; p >= 0; p = node_parent[p]) depth++;
-    atomicMax(max_depth, depth);
 }
 
 __device__ __forceinline__ float half_area(float4 lo, float4 hi) {
@@ -256,18 +253,17 @@ __device__ __forceinline__ float half_area(float4 lo, float4 hi) {
     return dx * dy + dy * dz + dz * dx;
 }
 
-// Final layout.  A child subtree with <= max_leaf triangles becomes one leaf
-// (its triangles are contiguous in sorted order); nodes below it stay unused.
+// Final layout.  A child whose collapse flag is set becomes one leaf made of its (contiguous) triangle range;
+// nodes below it stay unused.
 // stats: [0] live nodes, [1] leaves, sah: sum of area-weighted costs (Ct = Ci = 1).
 __global__ void k_emit_nodes(const int2* __restrict__ children, const int2* __restrict__ ranges,
                              const int* __restrict__ node_parent, const float4* __restrict__ leaf_lo,
                              const float4* __restrict__ leaf_hi, const float4* __restrict__ node_lo,
-                             const float4* __restrict__ node_hi, int n, int max_leaf, float4* __restrict__ out_nodes,
-                             unsigned int* __restrict__ stats, float* __restrict__ sah) {
+                             const float4* __restrict__ node_hi, const unsigned char* __restrict__ collapse, int n,
+                             float4* __restrict__ out_nodes, unsigned int* __restrict__ stats, float* __restrict__ sah) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
-    const int2 r = ranges[i];
-    const bool live = (i == 0) || (r.y - r.x + 1 > max_leaf);
+    const bool live = (i == 0) || !collapse[i];
     if (!live) {
         // keep the slot well defined (never referenced)
         const float qnan = __int_as_float(0x7fc00000);
@@ -289,7 +285,7 @@ __global__ void k_emit_nodes(const int2* __restrict__ children, const int2* __re
             lo[c] = node_lo[child]; hi[c] = node_hi[child];
             const int2 cr = ranges[child];
             const int cnt = cr.y - cr.x + 1;
-            if (cnt <= max_leaf) { code[c] = ~((cr.x << 3) | (cnt - 1)); leaves_here++; cost += half_area(lo[c], hi[c]) * (float)cnt; }
+            if (collapse[child]) { code[c] = ~((cr.x << 3) | (cnt - 1)); leaves_here++; cost += half_area(lo[c], hi[c]) * (float)cnt; }
             else code[c] = child;
         }
     }
@@ -331,6 +327,7 @@ bool build_bvh(const float4* d_verts, uint32_t n, const ptb_build_cfg& cfg, cuda
     memset(&stats, 0, sizeof(stats));
     stats.num_triangles = n;
     const int max_leaf = cfg.max_leaf_size < 1 ? 1 : (cfg.max_leaf_size > 8 ? 8 : cfg.max_leaf_size);
+    const bool refine = cfg.sah_refine != 0;
     if (n >= (1u << 28)) { err = "BVH build: more than 2^28 triangles"; return false; }
 
     const uint32_t n_nodes = n >= 2 ? n - 1 : 1;
@@ -372,14 +369,14 @@ bool build_bvh(const float4* d_verts, uint32_t n, const ptb_build_cfg& cfg, cuda
     Scratch sc;
     float4 *tri_lo, *tri_hi, *leaf_lo, *leaf_hi, *node_lo, *node_hi;
     float* scene_bounds; uint32_t *keys[2], *vals[2], *hist; int2 *children, *ranges; int *node_parent, *leaf_parent;
-    unsigned int *flags, *counters; float* sah;
+    unsigned int *flags, *counters; float* sah; unsigned char* collapse; int* treelets;
     const uint32_t n_tiles = (n + SORT_TILE - 1) / SORT_TILE;
     if (!sc.alloc(&tri_lo, n, err) || !sc.alloc(&tri_hi, n, err) || !sc.alloc(&leaf_lo, n, err) || !sc.alloc(&leaf_hi, n, err) ||
         !sc.alloc(&node_lo, n, err) || !sc.alloc(&node_hi, n, err) || !sc.alloc(&scene_bounds, 12, err) ||
         !sc.alloc(&keys[0], n, err) || !sc.alloc(&keys[1], n, err) || !sc.alloc(&vals[0], n, err) || !sc.alloc(&vals[1], n, err) ||
         !sc.alloc(&hist, (size_t)256 * n_tiles, err) || !sc.alloc(&children, n, err) || !sc.alloc(&ranges, n, err) ||
         !sc.alloc(&node_parent, n, err) || !sc.alloc(&leaf_parent, n, err) || !sc.alloc(&flags, n, err) ||
-        !sc.alloc(&counters, 4, err) || !sc.alloc(&sah, 1, err))
+        !sc.alloc(&counters, 4, err) || !sc.alloc(&sah, 1, err) || !sc.alloc(&collapse, n, err) || !sc.alloc(&treelets, n, err))
         return false;
 
     const float init_bounds[12] = {FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
@@ -401,8 +398,20 @@ bool build_bvh(const float4* d_verts, uint32_t n, const ptb_build_cfg& cfg, cuda
     }
     k_hierarchy<<<G, B, 0, stream>>>(keys[cur], (int)n, children, ranges, node_parent, leaf_parent);
     k_leaf_boxes<<<G, B, 0, stream>>>(tri_lo, tri_hi, vals[cur], n, scene_bounds, leaf_lo, leaf_hi);
-    k_refit<<<G, B, 0, stream>>>(children, node_parent, leaf_parent, leaf_lo, leaf_hi, (int)n, node_lo, node_hi, flags, counters + 2);
-    k_emit_nodes<<<G, B, 0, stream>>>(children, ranges, node_parent, leaf_lo, leaf_hi, node_lo, node_hi, (int)n, max_leaf, d_nodes, counters, sah);
+    k_refit<<<G, B, 0, stream>>>(children, node_parent, leaf_parent, leaf_lo, leaf_hi, (int)n, node_lo, node_hi, flags);
+    k_mark_collapse<<<G, B, 0, stream>>>(ranges, (int)n, max_leaf, collapse);
+    if (refine) {
+        // binned-SAH rebuild of every subtree of <= treelet_size triangles (bvh_refine.cuh); counters[3] = #treelets
+        int tmax = cfg.treelet_size > 0 ? cfg.treelet_size : PTB_TREELET_MAX;
+        if (tmax > PTB_TREELET_MAX) tmax = PTB_TREELET_MAX;
+        if (tmax < 8) tmax = 8;
+        k_find_treelets<<<G, B, 0, stream>>>(ranges, node_parent, (int)n, tmax, treelets, counters + 3);
+        const uint32_t rb = std::min<uint32_t>((n + 1) / 2, 148u * 16u);
+        k_refine_treelets<<<rb, 32 * PTB_REFINE_WARPS, 0, stream>>>(treelets, counters + 3, max_leaf, children, ranges, node_parent, leaf_parent,
+                                                                   leaf_lo, leaf_hi, node_lo, node_hi, vals[cur], collapse);
+    }
+    k_tree_depth<<<G, B, 0, stream>>>(node_parent, leaf_parent, collapse, (int)n, counters + 2);
+    k_emit_nodes<<<G, B, 0, stream>>>(children, ranges, node_parent, leaf_lo, leaf_hi, node_lo, node_hi, collapse, (int)n, d_nodes, counters, sah);
     k_emit_tris<<<G, B, 0, stream>>>(d_verts, vals[cur], n, d_tris);
     CK(cudaGetLastError());
     CK(cudaEventRecord(ev1, stream));

@@ -1,0 +1,249 @@
+// bvh_refine.cuh -- binned-SAH refinement of the LBVH, in place.
+//
+// The Karras tree orders triangles along the Morton curve, so every subtree covers a CONTIGUOUS range [a,b] of the
+// sorted triangles and owns the internal-node slots a+1..b-1 plus its own root slot (a or b).  A "treelet" is a
+// maximal subtree with at most PTB_TREELET_MAX triangles.  One warp rebuilds one treelet top-down with the binned
+// surface-area heuristic (16 bins x 3 axes, Ct = Ci = 1) entirely in shared memory:
+//   * lanes 0..15 / 16..31 own one bin of axis 0 / 1 (then axis 2) and scan the node's triangles;
+//   * 45 (axis, plane) candidates are evaluated by the lanes, the best one is found with shuffles;
+//   * the triangle order is partitioned with ballots (stable), so child ranges stay contiguous;
+//   * a node with <= max_leaf triangles becomes a leaf when that is cheaper than its best split.
+// The rebuilt nodes reuse the treelet's own slots; unused slots are marked dead.  The levels above the treelets keep
+// the LBVH topology.  Traversal results do not depend on the tree (hit rule in bvh.cuh), only its cost does.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ptb {
+
+#define PTB_TREELET_MAX 256
+#define PTB_SAH_BINS 16
+#define PTB_REFINE_WARPS 2
+
+struct TreeletTask { unsigned short begin, end; int slot; };
+
+struct TreeletShared {
+    float lo[3][PTB_TREELET_MAX], hi[3][PTB_TREELET_MAX];
+    unsigned int vals[PTB_TREELET_MAX];
+    unsigned short perm[PTB_TREELET_MAX], tmp[PTB_TREELET_MAX];
+    float bin_lo[3][PTB_SAH_BINS][3], bin_hi[3][PTB_SAH_BINS][3];
+    unsigned int bin_cnt[3][PTB_SAH_BINS];
+    TreeletTask stack[PTB_TREELET_MAX];
+};
+
+// collapse[i] = 1: node i is not an internal node of the final tree (its parent, if live, points at a leaf made of
+// ranges[i]); default for the plain LBVH: every subtree of <= max_leaf triangles collapses.
+__global__ void k_mark_collapse(const int2* __restrict__ ranges, int n, int max_leaf, unsigned char* __restrict__ collapse) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    const int2 r = ranges[i];
+    collapse[i] = (i != 0 && r.y - r.x + 1 <= max_leaf) ? 1 : 0;
+}
+
+__global__ void k_find_treelets(const int2* __restrict__ ranges, const int* __restrict__ node_parent, int n, int treelet_max,
+                                int* __restrict__ list, unsigned int* __restrict__ count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    const int2 r = ranges[i];
+    if (r.y - r.x + 1 > treelet_max) return;
+    const int p = node_parent[i];
+    if (p >= 0) { const int2 pr = ranges[p]; if (pr.y - pr.x + 1 <= treelet_max) return; }
+    list[atomicAdd(count, 1u)] = i;
+}
+
+__device__ __forceinline__ float box_half_area(const float* lo, const float* hi) {
+    const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+    return dx * dy + dy * dz + dz * dx;
+}
+
+__global__ void __launch_bounds__(32 * PTB_REFINE_WARPS)
+k_refine_treelets(const int* __restrict__ list, const unsigned int* __restrict__ count, int max_leaf, int2* __restrict__ children,
+                  int2* __restrict__ ranges, int* __restrict__ node_parent, int* __restrict__ leaf_parent,
+                  float4* __restrict__ leaf_lo, float4* __restrict__ leaf_hi, float4* __restrict__ node_lo,
+                  float4* __restrict__ node_hi, uint32_t* __restrict__ sorted_vals, unsigned char* __restrict__ collapse) {
+    __shared__ TreeletShared shared[PTB_REFINE_WARPS];
+    const unsigned lane = threadIdx.x & 31u;
+    TreeletShared& sh = shared[threadIdx.x >> 5];
+    const unsigned int n_treelets = *count;
+    const unsigned int total_warps = gridDim.x * PTB_REFINE_WARPS;
+    for (unsigned int tl = blockIdx.x * PTB_REFINE_WARPS + (threadIdx.x >> 5); tl < n_treelets; tl += total_warps) {
+        const int root = list[tl];
+        const int2 rr = ranges[root];
+        const int a = rr.x, k = rr.y - rr.x + 1;
+        __syncwarp();
+        for (int i = (int)lane; i < k; i += 32) {
+            const float4 l = leaf_lo[a + i], h = leaf_hi[a + i];
+            sh.lo[0][i] = l.x; sh.lo[1][i] = l.y; sh.lo[2][i] = l.z;
+            sh.hi[0][i] = h.x; sh.hi[1][i] = h.y; sh.hi[2][i] = h.z;
+            sh.vals[i] = sorted_vals[a + i];
+            sh.perm[i] = (unsigned short)i;
+        }
+        // every slot of the treelet except its root starts dead
+        for (int s = a + 1 + (int)lane; s <= a + k - 2; s += 32) { collapse[s] = 1; ranges[s] = make_int2(0, -1); }
+        int next_free = a + 1;
+        int sp = 0;
+        if (lane == 0) { sh.stack[0].begin = 0; sh.stack[0].end = (unsigned short)k; sh.stack[0].slot = root; }
+        sp = 1;
+        __syncwarp();
+        while (sp > 0) {
+            --sp;
+            const int begin = sh.stack[sp].begin, end = sh.stack[sp].end, slot = sh.stack[sp].slot;
+            const int n = end - begin;
+            __syncwarp();
+            // node box and centroid box
+            float nlo[3] = {3.4e38f, 3.4e38f, 3.4e38f}, nhi[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+            float clo[3] = {3.4e38f, 3.4e38f, 3.4e38f}, chi[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+            for (int j = begin + (int)lane; j < end; j += 32) {
+                const int id = sh.perm[j];
+                for (int ax = 0; ax < 3; ++ax) {
+                    const float l = sh.lo[ax][id], h = sh.hi[ax][id], c = 0.5f * (l + h);
+                    nlo[ax] = fminf(nlo[ax], l); nhi[ax] = fmaxf(nhi[ax], h);
+                    clo[ax] = fminf(clo[ax], c); chi[ax] = fmaxf(chi[ax], c);
+                }
+            }
+            for (int off = 16; off > 0; off >>= 1)
+                for (int ax = 0; ax < 3; ++ax) {
+                    nlo[ax] = fminf(nlo[ax], __shfl_xor_sync(0xffffffffu, nlo[ax], off));
+                    nhi[ax] = fmaxf(nhi[ax], __shfl_xor_sync(0xffffffffu, nhi[ax], off));
+                    clo[ax] = fminf(clo[ax], __shfl_xor_sync(0xffffffffu, clo[ax], off));
+                    chi[ax] = fmaxf(chi[ax], __shfl_xor_sync(0xffffffffu, chi[ax], off));
+                }
+            if (lane == 0) {
+                node_lo[slot] = make_float4(nlo[0], nlo[1], nlo[2], 0.0f);
+                node_hi[slot] = make_float4(nhi[0], nhi[1], nhi[2], 0.0f);
+                ranges[slot] = make_int2(a + begin, a + end - 1);
+            }
+            const float node_area = box_half_area(nlo, nhi);
+            // binning: two passes, lane owns (axis, bin)
+            for (int pass = 0; pass < 2; ++pass) {
+                const int ax = pass == 0 ? (int)(lane >> 4) : 2;
+                const int mybin = (int)(lane & 15u);
+                const bool owner = pass == 0 || lane < 16u;
+                const float ext = chi[ax] - clo[ax];
+                const float scale = ext > 0.0f ? (float)PTB_SAH_BINS / ext : 0.0f;
+                float bl[3] = {3.4e38f, 3.4e38f, 3.4e38f}, bh[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+                unsigned int cnt = 0;
+                if (owner) {
+                    for (int j = begin; j < end; ++j) {
+                        const int id = sh.perm[j];
+                        const float c = 0.5f * (sh.lo[ax][id] + sh.hi[ax][id]);
+                        int b = (int)((c - clo[ax]) * scale);
+                        b = b < 0 ? 0 : (b > PTB_SAH_BINS - 1 ? PTB_SAH_BINS - 1 : b);
+                        if (b == mybin) {
+                            cnt++;
+                            for (int d = 0; d < 3; ++d) { bl[d] = fminf(bl[d], sh.lo[d][id]); bh[d] = fmaxf(bh[d], sh.hi[d][id]); }
+                        }
+                    }
+                    sh.bin_cnt[ax][mybin] = cnt;
+                    for (int d = 0; d < 3; ++d) { sh.bin_lo[ax][mybin][d] = bl[d]; sh.bin_hi[ax][mybin][d] = bh[d]; }
+                }
+            }
+            __syncwarp();
+            // 45 candidates (axis, plane): split after bin `plane`
+            float best_cost = 3.4e38f; int best_cand = -1; unsigned int best_nl = 0;
+            for (int cand = (int)lane; cand < 3 * (PTB_SAH_BINS - 1); cand += 32) {
+                const int ax = cand / (PTB_SAH_BINS - 1), plane = cand % (PTB_SAH_BINS - 1);
+                if (!(chi[ax] - clo[ax] > 0.0f)) continue;
+                float ll[3] = {3.4e38f, 3.4e38f, 3.4e38f}, lh[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+                float rl[3] = {3.4e38f, 3.4e38f, 3.4e38f}, rh[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+                unsigned int nl = 0, nr = 0;
+                for (int b = 0; b < PTB_SAH_BINS; ++b) {
+                    const unsigned int c = sh.bin_cnt[ax][b];
+                    if (!c) continue;
+                    if (b <= plane) { nl += c; for (int d = 0; d < 3; ++d) { ll[d] = fminf(ll[d], sh.bin_lo[ax][b][d]); lh[d] = fmaxf(lh[d], sh.bin_hi[ax][b][d]); } }
+                    else { nr += c; for (int d = 0; d < 3; ++d) { rl[d] = fminf(rl[d], sh.bin_lo[ax][b][d]); rh[d] = fmaxf(rh[d], sh.bin_hi[ax][b][d]); } }
+                }
+                if (nl == 0 || nr == 0) continue;
+                const float cost = box_half_area(ll, lh) * (float)nl + box_half_area(rl, rh) * (float)nr;
+                if (cost < best_cost) { best_cost = cost; best_cand = cand; best_nl = nl; }
+            }
+            for (int off = 16; off > 0; off >>= 1) {
+                const float oc = __shfl_xor_sync(0xffffffffu, best_cost, off);
+                const int ocand = __shfl_xor_sync(0xffffffffu, best_cand, off);
+                const unsigned int onl = __shfl_xor_sync(0xffffffffu, best_nl, off);
+                if (ocand >= 0 && (best_cand < 0 || oc < best_cost || (oc == best_cost && ocand < best_cand))) { best_cost = oc; best_cand = ocand; best_nl = onl; }
+            }
+            const float leaf_cost = node_area * (float)n;
+            const float split_cost = best_cand >= 0 ? node_area + best_cost : 3.4e38f;
+            if (n <= max_leaf && slot != 0 && (best_cand < 0 || leaf_cost <= split_cost)) {
+                if (lane == 0) collapse[slot] = 1;
+                for (int j = begin + (int)lane; j < end; j += 32) leaf_parent[a + j] = slot;  // keeps the depth walk exact
+                continue;
+            }
+            if (lane == 0) collapse[slot] = 0;
+            int mid;
+            if (best_cand >= 0) {
+                const int ax = best_cand / (PTB_SAH_BINS - 1), plane = best_cand % (PTB_SAH_BINS - 1);
+                const float ext = chi[ax] - clo[ax];
+                const float scale = (float)PTB_SAH_BINS / ext;
+                int nleft = 0, nright = 0;
+                for (int base = begin; base < end; base += 32) {
+                    const int j = base + (int)lane;
+                    const bool act = j < end;
+                    int id = 0; bool left = false;
+                    if (act) {
+                        id = sh.perm[j];
+                        const float c = 0.5f * (sh.lo[ax][id] + sh.hi[ax][id]);
+                        int b = (int)((c - clo[ax]) * scale);
+                        b = b < 0 ? 0 : (b > PTB_SAH_BINS - 1 ? PTB_SAH_BINS - 1 : b);
+                        left = b <= plane;
+                    }
+                    const unsigned lm = __ballot_sync(0xffffffffu, act && left), rm = __ballot_sync(0xffffffffu, act && !left);
+                    const unsigned lt = (1u << lane) - 1u;
+                    if (act) {
+                        const int dst = left ? begin + nleft + __popc(lm & lt) : begin + (int)best_nl + nright + __popc(rm & lt);
+                        sh.tmp[dst] = (unsigned short)id;
+                    }
+                    nleft += __popc(lm); nright += __popc(rm);
+                }
+                __syncwarp();
+                for (int j = begin + (int)lane; j < end; j += 32) sh.perm[j] = sh.tmp[j];
+                mid = begin + (int)best_nl;
+            } else {
+                mid = begin + n / 2;  // all centroids coincide: object median in Morton order
+            }
+            __syncwarp();
+            // children
+            int child[2];
+            const int cb[2] = {begin, mid}, ce[2] = {mid, end};
+            for (int c = 0; c < 2; ++c) {
+                const int cn = ce[c] - cb[c];
+                if (cn == 1) {
+                    child[c] = ~(a + cb[c]);
+                    if (lane == 0) leaf_parent[a + cb[c]] = slot;
+                } else {
+                    const int cslot = next_free++;
+                    child[c] = cslot;
+                    if (lane == 0) {
+                        node_parent[cslot] = slot;
+                        sh.stack[sp].begin = (unsigned short)cb[c]; sh.stack[sp].end = (unsigned short)ce[c]; sh.stack[sp].slot = cslot;
+                    }
+                    sp++;
+                }
+            }
+            if (lane == 0) children[slot] = make_int2(child[0], child[1]);
+            __syncwarp();
+        }
+        // the new triangle order of the treelet
+        __syncwarp();
+        for (int i = (int)lane; i < k; i += 32) {
+            const int id = sh.perm[i];
+            leaf_lo[a + i] = make_float4(sh.lo[0][id], sh.lo[1][id], sh.lo[2][id], 0.0f);
+            leaf_hi[a + i] = make_float4(sh.hi[0][id], sh.hi[1][id], sh.hi[2][id], 0.0f);
+            sorted_vals[a + i] = sh.vals[id];
+        }
+        __syncwarp();
+    }
+}
+
+// depth of the final tree (levels of live internal nodes above the deepest leaf)
+__global__ void k_tree_depth(const int* __restrict__ node_parent, const int* __restrict__ leaf_parent,
+                             const unsigned char* __restrict__ collapse, int n, unsigned int* __restrict__ max_depth) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned int depth = 0;
+    for (int p = leaf_parent[i]; p >= 0; p = node_parent[p]) if (!collapse[p]) depth++;
+    atomicMax(max_depth, depth);
+}
+
+}  // namespace ptb

@@ -258,7 +258,14 @@ int ptb_accel_build(ptb_context* ctx, ptb_scene* scene, const ptb_build_cfg* cfg
 
     ptb_build_stats stats;
     std::string err;
-    if (!build_bvh(d->verts, n, cfg, st, d->bvh, stats, err)) { free_device_scene_buffers(d); delete d; return fail(PTB_ERR_CUDA, err); }
+    bool built = build_bvh(d->verts, n, cfg, st, d->bvh, stats, err);
+    if (!built && cfg.sah_refine) {
+        // an SAH treelet can in principle grow deeper than the traversal stack: fall back to the plain LBVH (depth <= 62)
+        free_bvh(d->bvh);
+        cfg.sah_refine = 0;
+        built = build_bvh(d->verts, n, cfg, st, d->bvh, stats, err);
+    }
+    if (!built) { free_device_scene_buffers(d); delete d; return fail(PTB_ERR_CUDA, err); }
     d->handle = ctx->next_handle++;
     d->owner = ctx;
     ctx->scenes[d->handle] = d;

@@ -131,13 +131,19 @@ def _check_bvh(nodes, tris, n_tris, max_leaf):
     return visited
 
 
+@pytest.mark.parametrize("refine", [0, 1], ids=["lbvh", "lbvh+sah"])
 @pytest.mark.parametrize("name,small", [("c1", True), ("c2", False)])
-def test_bvh_structure_and_ray_queries(ptb, ctx, oh, assets, name, small):
+def test_bvh_structure_and_ray_queries(ptb, ctx, oh, assets, name, small, refine):
+    if PIPELINE != 2:
+        pytest.skip("the BVH does not depend on the render pipeline")
     sc = load_config(ptb, assets, name, small=small)
-    handle, st = ctx.accel_build(sc)
+    handle, st = ctx.accel_build(sc, ptb.default_build_cfg(sah_refine=refine))
     assert st.num_triangles == sc.num_triangles and st.max_depth < 64
     nodes, tris = ctx.accel_read(handle)
-    _check_bvh(nodes, tris, sc.num_triangles, 4)
+    assert _check_bvh(nodes, tris, sc.num_triangles, 4) == st.num_nodes
+    if refine and name == "c2":
+        _, st0 = ctx.accel_build(ptb_scene_again := load_config(ptb, assets, name, small=small), ptb.default_build_cfg(sah_refine=0))
+        assert st.sah_cost < st0.sah_cost, (st.sah_cost, st0.sah_cost)
     osc = oh.OracleScene.from_ptb(sc, guard=False)
     v = osc.vertices[:, :3]
     # leave the 400-unit floor out of the sampling box so that rays concentrate on the mesh
