@@ -95,7 +95,7 @@ def cpu_reference_sample(oh, ptb, osc, rows, threads=0):
     kind = "reference" if oh.have_ref() else "port"
     which = "ref" if kind == "reference" else "oracle"
     p = ptb.make_params(W, H, subframe_index=0, dof=True, **CAMERAS["default"])
-    y0 = H // 2 - rows // 2 - 40  # the band crosses the mesh, the floor and the horizon-free part of the frame
+    y0 = max(0, min(H - rows, H // 2 - rows // 2 - 40))  # a band around the mesh; rows == H is the whole frame
     if kind == "reference":
         cfg = oh.default_config("ref", threads=threads)
         lits = "reference literals 10 spp/launch, depth 20 (compile-time constants, optixSphere.cu:323,360)"
@@ -146,10 +146,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--ref-rows", type=int, default=48, help="rows of the frame per step of the CPU reference arm")
-    ap.add_argument("--cpu-rows", type=int, default=160, help="rows of the frame for the cpu_baseline sample of our arm")
+    ap.add_argument("--ref-rows", type=int, default=1080, help="rows of the frame per step of the CPU reference arm")
+    ap.add_argument("--cpu-rows", type=int, default=1080, help="rows of the frame for the cpu_baseline sample of our arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--pipeline", type=int, default=2, help="1 global queues, 2 chunked stage kernels (default), 3 chunked fused")
+    ap.add_argument("--pipeline", type=int, default=3, help="1 global queues, 2 chunked stage kernels, 3 chunked fused (default)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -236,17 +236,26 @@ def main():
     value = seg_total / (ms_max * 1e-3) / 1e6
     gpu_launches = int(ctx.launch_stats().kernel_launches) * args.steps + (args.steps if multi and rank == 0 else 0)
 
-    # ---- stage shares + roofline of the dominant kernel (CUDA events inside ptb_launch, same stream) ----
-    cfg_prof = ptb.default_render_cfg(spp_per_launch=SPP_PER_LAUNCH, max_depth=DEPTH, subframes_per_launch=LAUNCHES_PER_STEP,
-                                      pipeline=args.pipeline, accumulate_mode=cfg.accumulate_mode, write_frame=cfg.write_frame, profile_stages=1)
-    stage = {k: 0.0 for k in ("raygen", "trace", "shade", "miss", "resolve", "total")}
-    prof_reps = max(1, min(args.steps, 3))
-    for _ in range(prof_reps):
-        accum.zero_()
-        one_step(0, cfg_prof)
-        for kk, v in ctx.stage_ms().items():
-            stage[kk] += v / prof_reps
-    # traversal work per segment, from one instrumented launch of the same subframe 0
+    # ---- roofline of the dominant kernel + stage shares (CUDA events inside ptb_launch, same stream) ----
+    # (1) the timed pipeline with profile_stages: for the fused pipeline "trace" is the one persistent kernel
+    def profiled(pipeline):
+        cfgp = ptb.default_render_cfg(spp_per_launch=SPP_PER_LAUNCH, max_depth=DEPTH, subframes_per_launch=LAUNCHES_PER_STEP,
+                                      pipeline=pipeline, accumulate_mode=cfg.accumulate_mode, write_frame=cfg.write_frame, profile_stages=1)
+        acc = {k: 0.0 for k in ("raygen", "trace", "shade", "miss", "resolve", "total")}
+        reps = max(1, min(args.steps, 3))
+        for _ in range(reps):
+            accum.zero_()
+            first = parallel.subframe_block_for_rank(rank, world, LAUNCHES_PER_STEP * world)[0]
+            pp = ptb.make_params(W, H, subframe_index=first, dof=True, **CAMERAS["default"])
+            pp.accum_buffer, pp.frame_buffer, pp.handle = accum.data_ptr(), frame.data_ptr(), handle
+            ctx.launch(pp, cfgp, stream=stream)
+            for kk, v in ctx.stage_ms().items():
+                acc[kk] += v / reps
+        return acc
+    stage = profiled(args.pipeline)
+    # (2) per-stage split from the same stages run as separate kernels (pipeline 2); explains where the time goes
+    stage_split = profiled(2) if args.pipeline == 3 else stage
+    # traversal work per segment, from one instrumented launch of subframe 0
     cfg_cnt = ptb.default_render_cfg(spp_per_launch=SPP_PER_LAUNCH, max_depth=DEPTH, write_frame=0, count_traversal=1, pipeline=args.pipeline)
     p = ptb.make_params(W, H, subframe_index=0, dof=True, **CAMERAS["default"])
     scratch = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
@@ -255,29 +264,40 @@ def main():
     lst = ctx.launch_stats()
     nodes_per_seg = lst.nodes_visited / max(lst.segments, 1)
     tris_per_seg = lst.tris_tested / max(lst.segments, 1)
+    hit_frac = lst.hits / max(lst.segments, 1)
     seg_per_step = seg_total / (args.steps * world)
-    # k_trace algorithmic bytes per segment: queue index 4 + ray 32 read, hit record 16 + queue append 4 written,
-    # 64 B per node visited, 48 B per triangle tested
-    trace_bytes_per_seg = 4 + 32 + 16 + 4 + 64.0 * nodes_per_seg + 48.0 * tris_per_seg
-    trace_launches = SPP_PER_LAUNCH * (DEPTH + 1)  # one k_chunk_trace per wavefront iteration
+    # Algorithmic bytes per segment:
+    #   traversal stage: list 4 + ray 32 read, hit record 16 + status 1 written, 64 B per node, 48 B per triangle
+    #   shade (per hit): 80 state read + 64 written + 120 attributes;  miss: 48 read + 64 env taps + 32 pixsum + 64 regenerated ray
+    trace_bytes_per_seg = 4 + 32 + 16 + 1 + 64.0 * nodes_per_seg + 48.0 * tris_per_seg
+    shade_bytes_per_seg = hit_frac * (80 + 64 + 120) + (1.0 - hit_frac) * (48 + 64 + 32 + 64)
     peak, peak_src = measured_peaks()
-    trace_s = stage["trace"] * 1e-3
-    achieved = trace_bytes_per_seg * seg_per_step / trace_s / 1e9 if trace_s > 0 else 0.0
+    if args.pipeline == 3:
+        kernel, kernel_ms, launches_k = "k_chunk_fused", stage["trace"], 1
+        bytes_per_seg = trace_bytes_per_seg + shade_bytes_per_seg
+    else:
+        kernel, kernel_ms = ("k_chunk_trace" if args.pipeline == 2 else "k_trace"), stage["trace"]
+        launches_k = SPP_PER_LAUNCH * (DEPTH + 1)
+        bytes_per_seg = trace_bytes_per_seg
+    achieved = bytes_per_seg * seg_per_step / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
     traffic = None
-    tf = ROOT / "profiles" / "k_trace_dram_bytes_per_launch.json"
+    tf = ROOT / "profiles" / "dominant_kernel_dram_bytes.json"
     if tf.exists():
         try:
-            traffic = json.loads(tf.read_text())["dram_bytes_per_launch"]
+            traffic = json.loads(tf.read_text()).get(kernel, {}).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
     roofline = {
-        "kernel": "k_chunk_trace", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "kernel": kernel, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "traffic": traffic, "peak_source": peak_src,
-        "algorithmic_bytes_per_launch": trace_bytes_per_seg * seg_per_step / trace_launches,
-        "avg_launch_ms": stage["trace"] / trace_launches, "nodes_per_segment": nodes_per_seg, "tris_per_segment": tris_per_seg,
-        "note": "BVH (1.1 MB) and textures (4 MB) are L2-resident, so this kernel is latency/L2-bound; the fraction is of the HBM copy peak",
-        "stage_ms_per_step": {k: v for k, v in stage.items()},
-        "stage_share": {k: (stage[k] / stage["total"] if stage["total"] > 0 else 0.0) for k in ("raygen", "trace", "shade", "miss", "resolve")},
+        "algorithmic_bytes_per_segment": bytes_per_seg, "algorithmic_bytes_per_launch": bytes_per_seg * seg_per_step / launches_k,
+        "avg_launch_ms": kernel_ms / launches_k, "launches_per_step": launches_k,
+        "nodes_per_segment": nodes_per_seg, "tris_per_segment": tris_per_seg, "hit_fraction": hit_frac,
+        "note": "BVH (1.4 MB) and textures (4 MB) are L2-resident and the fused kernel keeps a chunk's path state in L1/L2 between stages, "
+                "so most algorithmic bytes never reach HBM: ncu shows the kernels issue-bound (profiles/), the fraction is of the HBM copy peak",
+        "share_of_step": kernel_ms / stage["total"] if stage["total"] > 0 else None,
+        "stage_ms_per_step_separate_kernels": {k: v for k, v in stage_split.items()},
+        "stage_share_separate_kernels": {k: (stage_split[k] / stage_split["total"] if stage_split["total"] > 0 else 0.0) for k in ("raygen", "trace", "shade", "miss", "resolve")},
     }
 
     # ---- end to end through the C ABI with HOST buffers (pinned): accum in, accum + frame out, every step ----

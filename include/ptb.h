@@ -188,6 +188,10 @@ int ptb_context_synchronize(ptb_context* ctx, void* stream);
 int ptb_scene_load_obj(const char* const* files, int n_files, float scale, uint32_t material_seed, ptb_scene** out);
 /* raw variant: triangles as the reference holds them before flattening */
 int ptb_scene_create(const ptb_TriangleData* tris, uint32_t n_tris, const uint32_t* mat_ids, ptb_scene** out);
+/* the reference's asset-free demo scene (createSceneGeometry with loadFromFile = false, optixSphere.cpp:295-353,
+ * 650-751): a 20x20 ground quad + three UV spheres (16 stacks x 32 slices, radius 1) with four fixed materials.
+ * Dead code in the reference (loadFromFile is hard-coded true, optixSphere.cpp:829); kept as a regression scene. */
+int ptb_scene_create_demo(ptb_scene** out);
 /* hit-group table: optixSphere.cpp:1196-1261 */
 int ptb_scene_set_materials(ptb_scene* scene, const ptb_HitGroupData* mats, int n);
 /* environment: sutil::loadImage(exr) + MissData (optixSphere.cpp:835-836, 1161-1188) */

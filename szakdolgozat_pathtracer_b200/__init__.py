@@ -112,7 +112,7 @@ class MaterialInfo(C.Structure):
 # Every symbol include/ptb.h declares (tests check that the library exports all of them).
 EXPORTS = [
     "ptb_last_error", "ptb_version", "ptb_context_create", "ptb_context_destroy", "ptb_context_synchronize",
-    "ptb_scene_load_obj", "ptb_scene_create", "ptb_scene_set_materials", "ptb_scene_set_env_file",
+    "ptb_scene_load_obj", "ptb_scene_create", "ptb_scene_create_demo", "ptb_scene_set_materials", "ptb_scene_set_env_file",
     "ptb_scene_set_env_pixels", "ptb_scene_destroy", "ptb_scene_num_triangles", "ptb_scene_num_materials",
     "ptb_scene_copy_triangles", "ptb_scene_copy_material_ids", "ptb_scene_get_material", "ptb_scene_copy_texture",
     "ptb_scene_env_size", "ptb_scene_copy_env", "ptb_default_build_cfg", "ptb_accel_build", "ptb_accel_read",
@@ -222,6 +222,13 @@ class Scene:
         arr = (C.c_char_p * len(files))(*[os.fsencode(str(f)) for f in files])
         h = C.c_void_p()
         _check(lib().ptb_scene_load_obj(arr, len(files), C.c_float(scale), C.c_uint32(material_seed), C.byref(h)))
+        return cls(h.value)
+
+    @classmethod
+    def demo(cls):
+        """The reference's procedural scene (optixSphere.cpp:650-751): ground quad + three UV spheres."""
+        h = C.c_void_p()
+        _check(lib().ptb_scene_create_demo(C.byref(h)))
         return cls(h.value)
 
     @classmethod

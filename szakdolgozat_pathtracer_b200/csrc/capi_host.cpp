@@ -92,6 +92,56 @@ int ptb_scene_create(const ptb_TriangleData* tris, uint32_t n_tris, const uint32
     return PTB_OK;
 }
 
+// createSceneGeometry, loadFromFile == false (optixSphere.cpp:650-751) with generateSphereMesh (295-353).
+int ptb_scene_create_demo(ptb_scene** out) {
+    if (!out) return fail(PTB_ERR_INVALID, "ptb_scene_create_demo: null out");
+    ptb_scene* s = new ptb_scene();
+    auto f4 = [](float x, float y, float z, float w) { ptb_float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; };
+    auto push = [&](ptb_float4 a, ptb_float4 b, ptb_float4 c, ptb_float4 na, ptb_float4 nb, ptb_float4 nc, uint32_t mat) {
+        ptb_TriangleData t; memset(&t, 0, sizeof(t));
+        t.v0 = a; t.v1 = b; t.v2 = c; t.n0 = na; t.n1 = nb; t.n2 = nc;
+        s->tris.push_back(t); s->mat_ids.push_back(mat);
+    };
+    const float colors[4][3] = {{0.5f, 0.5f, 0.5f}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    const float spec[4][3] = {{1, 1, 1}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int i = 0; i < 4; ++i) {
+        Material m;
+        for (int c = 0; c < 3; ++c) { m.diffuse_color[c] = colors[i][c]; m.specular[c] = spec[i][c]; m.emission_color[c] = colors[i][c] * 0.0f; }
+        m.roughness = i == 0 ? 0.8f : 0.0f;
+        s->mats.push_back(m);
+    }
+    const float ps = 10.0f;
+    const ptb_float4 v0 = f4(-ps, 0, -ps, 1), v1 = f4(-ps, 0, ps, 1), v2 = f4(ps, 0, -ps, 1), v3 = f4(ps, 0, ps, 1), gn = f4(0, 1, 0, 0);
+    push(v0, v1, v2, gn, gn, gn, 0);
+    push(v2, v1, v3, gn, gn, gn, 0);
+    const float centers[3][3] = {{-3, 1, 0}, {0, 1, 0}, {3, 1, 0}};
+    const int stacks = 16, slices = 32;
+    const float radius = 1.0f;
+    for (int sp = 0; sp < 3; ++sp) {
+        std::vector<ptb_float4> verts, norms;
+        for (int i = 0; i <= stacks; ++i) {
+            const float phi = (float)(3.14159265358979323846 * i / stacks);
+            const float y = radius * cosf(phi), r = radius * sinf(phi);
+            for (int j = 0; j <= slices; ++j) {
+                const float theta = (float)(2.0f * 3.14159265358979323846 * j / slices);
+                const float x = r * cosf(theta), z = r * sinf(theta);
+                verts.push_back(f4(centers[sp][0] + x, centers[sp][1] + y, centers[sp][2] + z, 1.0f));
+                const float inv = 1.0f / sqrtf(x * x + y * y + z * z);
+                norms.push_back(f4(x * inv, y * inv, z * inv, 0.0f));
+            }
+        }
+        for (int i = 0; i < stacks; ++i)
+            for (int j = 0; j < slices; ++j) {
+                const int first = i * (slices + 1) + j, second = first + slices + 1;
+                push(verts[first], verts[second], verts[first + 1], norms[first], norms[second], norms[first + 1], 1u + (uint32_t)sp);
+                push(verts[first + 1], verts[second], verts[second + 1], norms[first + 1], norms[second], norms[second + 1], 1u + (uint32_t)sp);
+            }
+    }
+    s->revision++;
+    *out = s;
+    return PTB_OK;
+}
+
 int ptb_scene_set_materials(ptb_scene* scene, const ptb_HitGroupData* mats, int n) {
     if (!scene || !mats || n <= 0) return fail(PTB_ERR_INVALID, "ptb_scene_set_materials: bad arguments");
     for (uint32_t id : scene->mat_ids) if (id >= (uint32_t)n) return fail(PTB_ERR_INVALID, "ptb_scene_set_materials: a triangle references a material beyond the table");

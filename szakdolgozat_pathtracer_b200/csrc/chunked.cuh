@@ -210,8 +210,8 @@ __global__ void __launch_bounds__(PTB_CHUNK_THREADS) k_chunk_miss(SceneView s, F
 
 // One block = one chunk, from the first camera ray to the last sample of its pixels.
 // totals[3] is not touched here (launch count is added by k_fold_counters' sibling on the host path).
-template <bool COUNT, int QUANTUM>
-__global__ void __launch_bounds__(PTB_CHUNK_THREADS) k_chunk_fused(SceneView s, FrameView f, PathView p, unsigned char* status,
+template <bool COUNT, int QUANTUM, int MINB>
+__global__ void __launch_bounds__(PTB_CHUNK_THREADS, MINB) k_chunk_fused(SceneView s, FrameView f, PathView p, unsigned char* status,
                                                                   unsigned long long* totals, unsigned long long* trav_stats,
                                                                   unsigned int* max_iters_seen) {
     __shared__ ChunkShared sh;

@@ -335,11 +335,8 @@ int ptb_launch(ptb_context* ctx, const ptb_Params* P, const ptb_render_cfg* cfg_
     q.counters = ctx->counters; q.trav_stats = ctx->trav_stats;
     const SceneView s = scene_view(d);
 
-    static const int env_tq = getenv("PTB_TRACE_QUANTUM") ? atoi(getenv("PTB_TRACE_QUANTUM")) : 0;
-    static const int env_tb = getenv("PTB_TRACE_BLOCKS_PER_SM") ? atoi(getenv("PTB_TRACE_BLOCKS_PER_SM")) : 0;
-    static const int env_pipe = getenv("PTB_PIPELINE") ? atoi(getenv("PTB_PIPELINE")) : -1;
-    const int tq = env_tq;
-    int pipeline = cfg.pipeline > 0 ? cfg.pipeline : (env_pipe >= 0 ? env_pipe : PTB_PIPELINE_DEFAULT);
+    static const int env_pipe = getenv("PTB_PIPELINE") ? atoi(getenv("PTB_PIPELINE")) : -1;  // experiments only
+    int pipeline = cfg.pipeline > 0 ? cfg.pipeline : (env_pipe > 0 ? env_pipe : PTB_PIPELINE_DEFAULT);
     if (pipeline < PTB_PIPELINE_QUEUES || pipeline > PTB_PIPELINE_CHUNK_FUSED) return fail(PTB_ERR_INVALID, "ptb_launch: unknown pipeline");
 
     CU(cudaMemsetAsync(ctx->counters, 0, (size_t)(iters + 2) * 4 * sizeof(uint32_t), st));
@@ -362,15 +359,12 @@ int ptb_launch(ptb_context* ctx, const ptb_Params* P, const ptb_render_cfg* cfg_
         const uint32_t need = (slots + 127u) / 128u;
         const uint32_t cap = (uint32_t)ctx->num_sms * 32u;
         const uint32_t grid = need < cap ? need : cap;
-        const uint32_t tcap = (uint32_t)ctx->num_sms * (uint32_t)(env_tb > 0 ? env_tb : 10);  // k_trace is persistent
+        const uint32_t tcap = (uint32_t)ctx->num_sms * 10u;  // k_trace is persistent
         const uint32_t tgrid = need < tcap ? need : tcap;
         launches = 1;
         for (uint32_t it = 0; it < iters; ++it) {
-            if (cfg.count_traversal) k_trace<true, 16><<<tgrid, 128, 0, st>>>(s, f, p, q, (int)it);
-            else if (tq == 4) k_trace<false, 4><<<tgrid, 128, 0, st>>>(s, f, p, q, (int)it);
-            else if (tq == 8) k_trace<false, 8><<<tgrid, 128, 0, st>>>(s, f, p, q, (int)it);
-            else if (tq == 32) k_trace<false, 32><<<tgrid, 128, 0, st>>>(s, f, p, q, (int)it);
-            else k_trace<false, 16><<<tgrid, 128, 0, st>>>(s, f, p, q, (int)it);
+            if (cfg.count_traversal) k_trace<true, PTB_TRACE_QUANTUM><<<tgrid, 128, 0, st>>>(s, f, p, q, (int)it);
+            else k_trace<false, PTB_TRACE_QUANTUM><<<tgrid, 128, 0, st>>>(s, f, p, q, (int)it);
             if (prof) CU(cudaEventRecord(ctx->events[2 + (size_t)it * 3 + 0], st));
             k_shade<<<grid, 128, 0, st>>>(s, f, p, q, (int)it);
             if (prof) CU(cudaEventRecord(ctx->events[2 + (size_t)it * 3 + 1], st));
@@ -388,9 +382,8 @@ int ptb_launch(ptb_context* ctx, const ptb_Params* P, const ptb_render_cfg* cfg_
         launches = 1;
         if (pipeline == PTB_PIPELINE_CHUNK_STAGES) {
             for (uint32_t it = 0; it < iters; ++it) {
-                if (cfg.count_traversal) k_chunk_trace<true, 16><<<chunks, PTB_CHUNK_THREADS, 0, st>>>(s, f, p, ctx->status, ctx->launch_totals, ctx->trav_stats, (int)it);
-                else if (tq == 8) k_chunk_trace<false, 8><<<chunks, PTB_CHUNK_THREADS, 0, st>>>(s, f, p, ctx->status, ctx->launch_totals, ctx->trav_stats, (int)it);
-                else k_chunk_trace<false, 16><<<chunks, PTB_CHUNK_THREADS, 0, st>>>(s, f, p, ctx->status, ctx->launch_totals, ctx->trav_stats, (int)it);
+                if (cfg.count_traversal) k_chunk_trace<true, PTB_TRACE_QUANTUM><<<chunks, PTB_CHUNK_THREADS, 0, st>>>(s, f, p, ctx->status, ctx->launch_totals, ctx->trav_stats, (int)it);
+                else k_chunk_trace<false, PTB_TRACE_QUANTUM><<<chunks, PTB_CHUNK_THREADS, 0, st>>>(s, f, p, ctx->status, ctx->launch_totals, ctx->trav_stats, (int)it);
                 if (prof) CU(cudaEventRecord(ctx->events[2 + (size_t)it * 3 + 0], st));
                 k_chunk_shade<<<chunks, PTB_CHUNK_THREADS, 0, st>>>(s, f, p, ctx->status);
                 if (prof) CU(cudaEventRecord(ctx->events[2 + (size_t)it * 3 + 1], st));
@@ -400,9 +393,12 @@ int ptb_launch(ptb_context* ctx, const ptb_Params* P, const ptb_render_cfg* cfg_
             }
         } else {
             unsigned int* max_iters = (unsigned int*)(ctx->launch_totals + 3);
-            if (cfg.count_traversal) k_chunk_fused<true, 16><<<chunks, PTB_CHUNK_THREADS, 0, st>>>(s, f, p, ctx->status, ctx->launch_totals, ctx->trav_stats, max_iters);
-            else if (tq == 8) k_chunk_fused<false, 8><<<chunks, PTB_CHUNK_THREADS, 0, st>>>(s, f, p, ctx->status, ctx->launch_totals, ctx->trav_stats, max_iters);
-            else k_chunk_fused<false, 16><<<chunks, PTB_CHUNK_THREADS, 0, st>>>(s, f, p, ctx->status, ctx->launch_totals, ctx->trav_stats, max_iters);
+            // 64 registers / 8 blocks per SM once there are enough chunks to keep that many blocks busy (the fused kernel
+            // is occupancy-limited: +12 % at 8 batched subframes), the unconstrained 94-register build for small frames
+            const bool wide = chunks >= (uint32_t)ctx->num_sms * 8u * 4u;
+            if (cfg.count_traversal) k_chunk_fused<true, PTB_TRACE_QUANTUM, 5><<<chunks, PTB_CHUNK_THREADS, 0, st>>>(s, f, p, ctx->status, ctx->launch_totals, ctx->trav_stats, max_iters);
+            else if (wide) k_chunk_fused<false, PTB_TRACE_QUANTUM, 8><<<chunks, PTB_CHUNK_THREADS, 0, st>>>(s, f, p, ctx->status, ctx->launch_totals, ctx->trav_stats, max_iters);
+            else k_chunk_fused<false, PTB_TRACE_QUANTUM, 5><<<chunks, PTB_CHUNK_THREADS, 0, st>>>(s, f, p, ctx->status, ctx->launch_totals, ctx->trav_stats, max_iters);
             launches += 1;
             prof_iters = 0;
             if (prof) {  // a single kernel: everything between raygen and resolve is reported as "trace"

@@ -255,3 +255,17 @@ def test_batched_subframes_bit_identical_to_consecutive_launches(ptb, ctx, asset
     assert seg == sum(s.segments for s in seq_st)
     assert np.array_equal(a.view(np.uint32), seq_a.view(np.uint32))
     assert np.array_equal(f, seq_f)
+
+
+def test_demo_scene_parity(ptb, ctx, oh, assets):
+    """The reference's procedural scene (degenerate pole triangles, roughness-0 spheres clamped to 0.015): bit-exact."""
+    sc = ptb.Scene.demo()
+    sc.set_env_pixels(assets.make_env(7, 256, 128).astype(np.float32).repeat(1, axis=2)[..., [0, 1, 2, 2]])
+    handle, st = ctx.accel_build(sc)
+    osc = oh.OracleScene.from_ptb(sc, guard=False)
+    kw = dict(spp_per_launch=4, max_depth=10)
+    ga, gf, gh, gst = _render_gpu(ptb, ctx, handle, 240, 160, kw)
+    ca, cf, ch, cseg = _render_cpu(oh, ptb, osc, 240, 160, kw)
+    assert np.array_equal(gh, ch) and gst[0].segments == cseg
+    assert np.array_equal(ga.view(np.uint32), ca.view(np.uint32))
+    assert len(np.unique(gh)) > 100

@@ -204,3 +204,20 @@ def test_raw_scene_and_material_table(ptb):
     sc2 = ptb.Scene.from_triangles(tri, np.array([2], np.uint32))
     with pytest.raises(ptb.PtbError):
         sc2.set_materials([dict()])                    # material id beyond the table
+
+
+def test_demo_scene(ptb):
+    """createSceneGeometry(loadFromFile=false), optixSphere.cpp:650-751: 2 + 3*16*32*2 triangles, 4 fixed materials."""
+    sc = ptb.Scene.demo()
+    assert sc.num_triangles == 2 + 3 * 16 * 32 * 2 and sc.num_materials == 4
+    t = sc.triangles()
+    ids = sc.material_ids()
+    assert list(ids[:2]) == [0, 0] and set(ids[2:2 + 1024]) == {1} and set(ids[-1024:]) == {3}
+    v = t[:, 0:12].reshape(-1, 4)
+    assert np.all(v[:, 3] == 1.0)  # the demo scene stores w = 1 (files store 0)
+    centers = np.array([[-3, 1, 0], [0, 1, 0], [3, 1, 0]], np.float32)
+    for k in range(3):
+        vv = t[2 + k * 1024: 2 + (k + 1) * 1024, 0:12].reshape(-1, 4)[:, :3]
+        assert np.allclose(np.linalg.norm(vv - centers[k], axis=1), 1.0, atol=1e-5)
+    m = sc.material(1)
+    assert list(m.diffuse_color) == [1.0, 0.0, 0.0] and m.roughness == 0.0 and sc.material(0).roughness == np.float32(0.8)
