@@ -269,3 +269,74 @@ def test_demo_scene_parity(ptb, ctx, oh, assets):
     assert np.array_equal(gh, ch) and gst[0].segments == cseg
     assert np.array_equal(ga.view(np.uint32), ca.view(np.uint32))
     assert len(np.unique(gh)) > 100
+
+
+def _tri_scene(ptb, assets, tris):
+    sc = ptb.Scene.from_triangles(np.asarray(tris, np.float32).reshape(-1, 32), None)
+    env = assets.make_env(3, 64, 32)
+    sc.set_env_pixels(np.concatenate([env, np.ones_like(env[..., :1])], -1))
+    return sc
+
+
+def _one_tri(y=0.0, s=3.0):
+    t = np.zeros(32, np.float32)
+    t[0:12] = [-s, y, -s, 0, -s, y, s, 0, s, y, -s, 0]
+    t[12:24] = [0, 1, 0, 0] * 3
+    return t
+
+
+@pytest.mark.parametrize("n_tris", [0, 1, 2, 3])
+def test_degenerate_scenes(ptb, ctx, oh, assets, n_tris):
+    """Empty, 1-, 2- and 3-triangle scenes (the builder's n < 2 path has no Karras tree), odd frame sizes."""
+    tris = [_one_tri(0.1 * k, 3.0 - 0.5 * k) for k in range(n_tris)]
+    sc = _tri_scene(ptb, assets, tris if tris else np.zeros((0, 32), np.float32))
+    handle, st = ctx.accel_build(sc)
+    assert st.num_triangles == n_tris
+    osc = oh.OracleScene.from_ptb(sc, guard=False)
+    for (W, H) in ((1, 1), (37, 23)):
+        kw = dict(spp_per_launch=2, max_depth=3)
+        ga, gf, gh, gst = _render_gpu(ptb, ctx, handle, W, H, kw)
+        ca, cf, ch, cseg = _render_cpu(oh, ptb, osc, W, H, kw)
+        assert np.array_equal(gh, ch) and gst[0].segments == cseg
+        assert np.array_equal(ga.view(np.uint32), ca.view(np.uint32))
+    if n_tris == 0:
+        assert np.all(gh == -1)
+
+
+def test_depth_zero_and_single_sample(ptb, ctx, oh, assets):
+    """max_depth = 0: the first hit already sets done (optixSphere.cu:738); spp = 1."""
+    sc = load_config(ptb, assets, "c1", small=True)
+    handle, _ = ctx.accel_build(sc)
+    osc = oh.OracleScene.from_ptb(sc, guard=False)
+    for kw in (dict(spp_per_launch=1, max_depth=0), dict(spp_per_launch=1, max_depth=1)):
+        ga, gf, gh, gst = _render_gpu(ptb, ctx, handle, 64, 48, kw, dof=False)
+        ca, cf, ch, cseg = _render_cpu(oh, ptb, osc, 64, 48, kw, dof=False)
+        assert gst[0].segments == cseg and np.array_equal(gh, ch)
+        assert np.array_equal(ga.view(np.uint32), ca.view(np.uint32))
+
+
+def test_launch_argument_errors(ptb, ctx, assets):
+    sc = load_config(ptb, assets, "c1", small=True)
+    handle, _ = ctx.accel_build(sc)
+    d = ctx.alloc(64 * 64 * 16)
+    try:
+        p = ptb.make_params(64, 64)
+        p.accum_buffer, p.frame_buffer, p.handle = d, None, handle
+        with pytest.raises(ptb.PtbError):  # frame buffer missing while write_frame = 1
+            ctx.launch(p, ptb.default_render_cfg())
+        p.handle = 987654
+        with pytest.raises(ptb.PtbError):  # unknown acceleration structure
+            ctx.launch(p, ptb.default_render_cfg(write_frame=0))
+        p.handle = handle
+        with pytest.raises(ptb.PtbError) as e:  # cannot reproduce the reference estimator
+            ctx.launch(p, ptb.default_render_cfg(write_frame=0, env_importance_sampling=1))
+        assert e.value.code == ptb.PTB_ERR_UNSUPPORTED
+        with pytest.raises(ptb.PtbError):
+            ctx.launch(p, ptb.default_render_cfg(write_frame=0, spp_per_launch=0))
+        ctx.launch(p, ptb.default_render_cfg(write_frame=0, spp_per_launch=1, max_depth=2))  # and a valid one still works
+        assert ctx.launch_stats().segments > 0
+    finally:
+        ctx.free(d)
+    bare = ptb.Scene.from_triangles(_one_tri().reshape(1, 32), None)
+    with pytest.raises(ptb.PtbError):  # no environment map
+        ctx.accel_build(bare)
