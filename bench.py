@@ -34,8 +34,28 @@ for p in (ROOT, ROOT / "tests", ROOT / "tools"):
 
 import numpy as np
 
-W, H, SPP_PER_LAUNCH, LAUNCHES_PER_STEP, DEPTH = 1920, 1080, 8, 8, 8
-WORKLOAD = "C2: monkey.obj+monkey_albedo.png, env2 2048x1024 (synthetic, seed 2), 1920x1080, 64 spp (8 subframes x 8), depth 8, reference camera, DoF on"
+# BASELINE.json configs.  The headline metric is quoted on C2; the others are selectable
+# with --config (one step = ONE batched launch of `subframes` subframes of `spp` samples per pixel).
+CONFIGS = {
+    "c2": dict(scene="c2", res=(1920, 1080), spp=8, subframes=8, depth=8, camera="default",
+               text="C2: monkey.obj+monkey_albedo.png, env2 2048x1024 (synthetic, seed 2), 1920x1080, 64 spp (8 subframes x 8), depth 8, reference camera, DoF on"),
+    "c2_close": dict(scene="c2", res=(1920, 1080), spp=8, subframes=8, depth=8, camera="monkey_close",
+                     text="C2 scene with the close camera of SURVEY.md section 8d (eye (0,1.2,3.2) -> (0,0.7,0)), 1920x1080, 64 spp, depth 8"),
+    "c3": dict(scene="c3", res=(3840, 2160), spp=8, subframes=32, depth=8, camera="default",
+               text="C3: suitcase.obj full PBR (real metallic/normal/roughness, synthetic albedo), env3 4096x2048, 3840x2160, 256 spp (32 subframes x 8), depth 8"),
+    "c4": dict(scene="c4", res=(1920, 1080), spp=8, subframes=16, depth=8, camera="default",
+               text="C4: fish+tower+5 synthetic 0.33-1.3 M triangle stand-ins (4.6 M triangles), env4, 1920x1080, 128 spp (16 subframes x 8), depth 8"),
+    "c5": dict(scene="c5", res=(3840, 2160), spp=64, subframes=64, depth=8, camera="default",
+               text="C5: synthetic model.obj (0.33 M triangles, uvs) + albedo, env5 4096x2048, 3840x2160, 4096 spp (64 subframes x 64), depth 8"),
+}
+W, H, SPP_PER_LAUNCH, LAUNCHES_PER_STEP, DEPTH, SCENE, CAMERA, WORKLOAD = 1920, 1080, 8, 8, 8, "c2", "default", CONFIGS["c2"]["text"]
+
+
+def select_config(name):
+    global W, H, SPP_PER_LAUNCH, LAUNCHES_PER_STEP, DEPTH, SCENE, CAMERA, WORKLOAD
+    c = CONFIGS[name]
+    (W, H), SPP_PER_LAUNCH, LAUNCHES_PER_STEP, DEPTH = c["res"], c["spp"], c["subframes"], c["depth"]
+    SCENE, CAMERA, WORKLOAD = c["scene"], c["camera"], c["text"]
 
 
 def measured_peaks():
@@ -94,7 +114,7 @@ def cpu_reference_sample(oh, ptb, osc, rows, threads=0):
     from scenes import CAMERAS
     kind = "reference" if oh.have_ref() else "port"
     which = "ref" if kind == "reference" else "oracle"
-    p = ptb.make_params(W, H, subframe_index=0, dof=True, **CAMERAS["default"])
+    p = ptb.make_params(W, H, subframe_index=0, dof=True, **CAMERAS[CAMERA])
     y0 = max(0, min(H - rows, H // 2 - rows // 2 - 40))  # a band around the mesh; rows == H is the whole frame
     if kind == "reference":
         cfg = oh.default_config("ref", threads=threads)
@@ -106,7 +126,7 @@ def cpu_reference_sample(oh, ptb, osc, rows, threads=0):
     _, _, _, st, rc = oh.render(which, osc, oh.params_from_ptb(p), cfg, accum=accum, window=(0, y0, W, y0 + rows), want_hits=False)
     if rc not in (0, 3):
         raise RuntimeError(f"CPU reference render failed rc={rc}")
-    sample = f"one launch over rows {y0}..{y0 + rows - 1} of the C2 1920x1080 frame ({W * rows} px), {lits}, {st.segments} segments, {st.seconds:.2f} s"
+    sample = f"one launch over rows {y0}..{y0 + rows - 1} of the {SCENE} {W}x{H} frame ({W * rows} px), {lits}, {st.segments} segments, {st.seconds:.2f} s"
     return dict(value=st.segments / st.seconds / 1e6, unit="Msegments/s", cores=int(st.threads), kind=kind, sample=sample), st
 
 
@@ -118,9 +138,9 @@ def run_reference_arm(args):
     import orchelp as oh
     import szakdolgozat_pathtracer_b200 as ptb
     from scenes import load_config
-    sc = load_config(ptb, make_assets, "c2")
+    sc = load_config(ptb, make_assets, SCENE)
     osc = oh.OracleScene.from_ptb(sc, guard=True)
-    rows = args.ref_rows
+    rows = min(args.ref_rows, H)
     for _ in range(args.warmup):
         cpu_reference_sample(oh, ptb, osc, max(4, rows // 8))
     seg, sec, last = 0, 0.0, None
@@ -150,9 +170,14 @@ def main():
     ap.add_argument("--cpu-rows", type=int, default=1080, help="rows of the frame for the cpu_baseline sample of our arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pipeline", type=int, default=3, help="1 global queues, 2 chunked stage kernels, 3 chunked fused (default)")
+    ap.add_argument("--config", default="c2", choices=list(CONFIGS))
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="N > 1: fused peer-memory exchange (default) or NCCL reduce")
     args = ap.parse_args()
+    select_config(args.config)
     if args.impl == "reference":
         return run_reference_arm(args)
+    if args.cpu_rows > H:
+        args.cpu_rows = H
 
     import torch
     import torch.distributed as dist
@@ -175,10 +200,10 @@ def main():
 
     ctx = ptb.Context(local_rank)
     if rank == 0:
-        make_assets.ensure("c2")
+        make_assets.ensure(SCENE)
     if world > 1:
         dist.barrier()
-    sc = load_config(ptb, make_assets, "c2")
+    sc = load_config(ptb, make_assets, SCENE)
     handle, bst = ctx.accel_build(sc)
 
     n = W * H
@@ -190,19 +215,52 @@ def main():
     cfg = ptb.default_render_cfg(spp_per_launch=SPP_PER_LAUNCH, max_depth=DEPTH, subframes_per_launch=LAUNCHES_PER_STEP,
                                  pipeline=args.pipeline, accumulate_mode=1 if multi else 0, write_frame=0 if multi else 1)
 
+    # N > 1 exchange.  "p2p": every rank reduces + tonemaps its slice of the frame straight out of the peers' accumulators
+    # (CUDA IPC mappings over NVLink) and stores it into rank 0's buffers: ONE kernel per rank (ptb_resolve_peers), NCCL only
+    # for two stream-ordered barriers.  "nccl": ncclReduce of the float4 accumulator, then ptb_resolve on rank 0.
+    acc_ptr, frame_ptr = accum.data_ptr(), frame.data_ptr()
+    exchange, exchange_note, tiny = None, "none (single GPU)", None
+    if multi:
+        exchange_note = "nccl reduce + ptb_resolve on rank 0"
+        if args.exchange == "p2p":
+            try:
+                raw_accum, raw_out = ctx.alloc(n * 16), ctx.alloc(n * 16)   # plain cudaMalloc: exportable through CUDA IPC
+                raw_frame = ctx.alloc(n * 4)
+                exchange = parallel.PeerExchange(ctx, rank, world, raw_accum, raw_out, raw_frame)
+                acc_ptr, frame_ptr = raw_accum, raw_frame
+                tiny = torch.zeros(1, device=dev)
+                exchange_note = "fused peer-memory reduce-scatter -> tonemap -> gather (ptb_resolve_peers over CUDA IPC / NVLink), 2 NCCL barriers"
+            except Exception as e:  # capability probe at set-up time, outside every timed region
+                print(f"[rank {rank}] peer-memory exchange unavailable ({e}); using the NCCL reduce", file=sys.stderr)
+                exchange = None
+        flag = torch.tensor([1 if exchange is not None else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0 and exchange is not None:
+            exchange.close(); exchange = None
+            acc_ptr, frame_ptr = accum.data_ptr(), frame.data_ptr()
+            exchange_note = "nccl reduce + ptb_resolve on rank 0 (a peer could not map the IPC handles)"
+
+    def zero_accum():
+        ctx.memset(acc_ptr, 0, n * 16, stream=stream)
+
+    def stream_barrier():
+        dist.all_reduce(tiny)
+
     def one_step(step_index, cfg_used):
         # a fresh 64-spp frame: the accumulator restarts (the reference resets subframe_index on camera change, cpp:267-278)
         if multi:
-            accum.zero_()
+            zero_accum()
         # rank r renders the contiguous block of subframes [r*8, r*8+8) of the 64*N-spp frame
         first = parallel.subframe_block_for_rank(rank, world, LAUNCHES_PER_STEP * world)[0]
-        p = ptb.make_params(W, H, subframe_index=first, dof=True, **CAMERAS["default"])
-        p.accum_buffer, p.frame_buffer, p.handle = accum.data_ptr(), frame.data_ptr(), handle
+        p = ptb.make_params(W, H, subframe_index=first, dof=True, **CAMERAS[CAMERA])
+        p.accum_buffer, p.frame_buffer, p.handle = acc_ptr, frame_ptr, handle
         ctx.launch(p, cfg_used, stream=stream)
-        if multi:
+        if multi and exchange is not None:
+            exchange.resolve(n, LAUNCHES_PER_STEP * world, cfg_used, stream, stream_barrier)
+        elif multi:
             parallel.reduce_accumulator(accum, dst=0)
             if rank == 0:
-                ctx.resolve(accum.data_ptr(), accum.data_ptr(), frame.data_ptr(), n, parallel.resolve_scale(LAUNCHES_PER_STEP * world), cfg_used, stream=stream)
+                ctx.resolve(acc_ptr, acc_ptr, frame_ptr, n, parallel.resolve_scale(LAUNCHES_PER_STEP * world), cfg_used, stream=stream)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -244,10 +302,10 @@ def main():
         acc = {k: 0.0 for k in ("raygen", "trace", "shade", "miss", "resolve", "total")}
         reps = max(1, min(args.steps, 3))
         for _ in range(reps):
-            accum.zero_()
+            zero_accum()
             first = parallel.subframe_block_for_rank(rank, world, LAUNCHES_PER_STEP * world)[0]
-            pp = ptb.make_params(W, H, subframe_index=first, dof=True, **CAMERAS["default"])
-            pp.accum_buffer, pp.frame_buffer, pp.handle = accum.data_ptr(), frame.data_ptr(), handle
+            pp = ptb.make_params(W, H, subframe_index=first, dof=True, **CAMERAS[CAMERA])
+            pp.accum_buffer, pp.frame_buffer, pp.handle = acc_ptr, frame_ptr, handle
             ctx.launch(pp, cfgp, stream=stream)
             for kk, v in ctx.stage_ms().items():
                 acc[kk] += v / reps
@@ -257,7 +315,7 @@ def main():
     stage_split = profiled(2) if args.pipeline == 3 else stage
     # traversal work per segment, from one instrumented launch of subframe 0
     cfg_cnt = ptb.default_render_cfg(spp_per_launch=SPP_PER_LAUNCH, max_depth=DEPTH, write_frame=0, count_traversal=1, pipeline=args.pipeline)
-    p = ptb.make_params(W, H, subframe_index=0, dof=True, **CAMERAS["default"])
+    p = ptb.make_params(W, H, subframe_index=0, dof=True, **CAMERAS[CAMERA])
     scratch = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
     p.accum_buffer, p.frame_buffer, p.handle = scratch.data_ptr(), frame.data_ptr(), handle
     ctx.launch(p, cfg_cnt, stream=stream)
@@ -272,6 +330,8 @@ def main():
     trace_bytes_per_seg = 4 + 32 + 16 + 1 + 64.0 * nodes_per_seg + 48.0 * tris_per_seg
     shade_bytes_per_seg = hit_frac * (80 + 64 + 120) + (1.0 - hit_frac) * (48 + 64 + 32 + 64)
     peak, peak_src = measured_peaks()
+    l2_peak = ctx.microbench_read(32 << 20, 40)    # 32 MiB working set: L2 -> SM read bandwidth
+    hbm_read = ctx.microbench_read(2 << 30, 4)     # 2 GiB working set: HBM read bandwidth of the same kernel
     if args.pipeline == 3:
         kernel, kernel_ms, launches_k = "k_chunk_fused", stage["trace"], 1
         bytes_per_seg = trace_bytes_per_seg + shade_bytes_per_seg
@@ -290,6 +350,7 @@ def main():
     roofline = {
         "kernel": kernel, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "traffic": traffic, "peak_source": peak_src,
+        "l2_peak_gbs": l2_peak, "frac_of_l2_peak": achieved / l2_peak if l2_peak > 0 else None, "hbm_read_gbs_own_microbench": hbm_read,
         "algorithmic_bytes_per_segment": bytes_per_seg, "algorithmic_bytes_per_launch": bytes_per_seg * seg_per_step / launches_k,
         "avg_launch_ms": kernel_ms / launches_k, "launches_per_step": launches_k,
         "nodes_per_segment": nodes_per_seg, "tris_per_segment": tris_per_seg, "hit_fraction": hit_frac,
@@ -307,11 +368,12 @@ def main():
     L = ptb.lib()
 
     def e2e_step():
-        L.ptb_copy_to_device(ctx._h, C.c_void_p(accum.data_ptr()), C.c_void_p(h_accum.data_ptr()), C.c_size_t(n * 16), C.c_void_p(stream))
+        L.ptb_copy_to_device(ctx._h, C.c_void_p(acc_ptr), C.c_void_p(h_accum.data_ptr()), C.c_size_t(n * 16), C.c_void_p(stream))
         one_step(0, cfg)
         if rank == 0:
-            L.ptb_copy_to_host(ctx._h, C.c_void_p(h_accum.data_ptr()), C.c_void_p(accum.data_ptr()), C.c_size_t(n * 16), C.c_void_p(stream))
-            L.ptb_copy_to_host(ctx._h, C.c_void_p(h_frame.data_ptr()), C.c_void_p(frame.data_ptr()), C.c_size_t(n * 4), C.c_void_p(stream))
+            res_ptr = exchange.out_accum if exchange is not None else acc_ptr
+            L.ptb_copy_to_host(ctx._h, C.c_void_p(h_accum.data_ptr()), C.c_void_p(res_ptr), C.c_size_t(n * 16), C.c_void_p(stream))
+            L.ptb_copy_to_host(ctx._h, C.c_void_p(h_frame.data_ptr()), C.c_void_p(frame_ptr), C.c_size_t(n * 4), C.c_void_p(stream))
 
     e2e_step()
     sync_all()
@@ -342,13 +404,16 @@ def main():
                        "l2": "no flush: the path pool of one step is 8 x 1920 x 1080 slots x 97 B = 1.6 GB (> 126 MB L2) and is rewritten every iteration",
                        "pipeline": {1: "global queues", 2: "block-local wavefront, one kernel per stage and iteration", 3: "block-local wavefront, fused persistent kernel"}[args.pipeline],
                        "subframes_per_launch": LAUNCHES_PER_STEP,
-                       "multi_gpu": "scene replicated, subframes split by rank, NCCL reduce of the float4 accumulator" if multi else "single GPU, reference accumulate mode",
+                       "multi_gpu": ("scene replicated, subframes split by rank; exchange: " + exchange_note) if multi else "single GPU, reference accumulate mode",
                        "bvh": {"triangles": bst.num_triangles, "nodes": bst.num_nodes, "max_depth": bst.max_depth, "sah": bst.sah_cost, "build_ms": bst.build_ms}},
-            "spp_per_s_1080p": SPP_PER_LAUNCH * LAUNCHES_PER_STEP * world * args.steps / (ms_max * 1e-3),
+            "spp_per_s_1080p": SPP_PER_LAUNCH * LAUNCHES_PER_STEP * world * args.steps / (ms_max * 1e-3) * (W * H / (1920.0 * 1080.0)),
             "segments_per_step": seg_total / args.steps,
             "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line))
+    if exchange is not None:
+        torch.cuda.synchronize()
+        exchange.close()
     if multi:
         dist.barrier()
         dist.destroy_process_group()

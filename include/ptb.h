@@ -245,6 +245,18 @@ int ptb_launch_get_stage_ms(ptb_context* ctx, float out[6]);
  * Used after a multi-GPU reduce of sum-mode accumulators. */
 int ptb_resolve(ptb_context* ctx, const ptb_float4* accum, ptb_float4* accum_out, ptb_uchar4* frame, uint32_t n_pixels,
                 float scale, const ptb_render_cfg* cfg, void* stream);
+/* Multi-GPU accumulate/tonemap fused with its exchange over NVLink peer memory (reduce-scatter ->
+ * tonemap -> gather, as ONE kernel per rank, no NCCL on the data path).  accums[k] is rank k's sum-mode accumulator
+ * (own memory or a peer mapping from ptb_ipc_open); the kernel sums them in rank order for pixels
+ * [first_pixel, first_pixel + n_pixels), scales, and stores the float4 result to accum_out and the tonemapped pixel to
+ * frame -- both may be peer pointers (e.g. rank 0's buffers), which is the gather.  The caller orders it after every
+ * rank's rendering (a stream-ordered barrier) and must barrier again before the root reads the frame. */
+int ptb_resolve_peers(ptb_context* ctx, const ptb_float4* const* accums, int n_ranks, ptb_float4* accum_out, ptb_uchar4* frame,
+                      uint32_t first_pixel, uint32_t n_pixels, float scale, const ptb_render_cfg* cfg, void* stream);
+/* CUDA IPC plumbing for the above (one process per GPU): export a cudaMalloc'ed buffer, open a peer's, close it */
+int ptb_ipc_export(ptb_context* ctx, const void* device_ptr, unsigned char handle[64]);
+int ptb_ipc_open(ptb_context* ctx, const unsigned char handle[64], void** device_ptr);
+int ptb_ipc_close(ptb_context* ctx, void* device_ptr);
 /* batch closest-hit query on the built BVH (device arrays of float3 / outputs) */
 int ptb_trace_rays(ptb_context* ctx, unsigned long long handle, const float* d_origins, const float* d_dirs, uint32_t n,
                    float tmin, float tmax, int32_t* d_prim, float* d_t, float* d_b1, float* d_b2, void* stream);
@@ -283,6 +295,12 @@ void ptb_free(void* p);
  * vx vy vz nx ny nz tx ty (float32, raw: unscaled, normals not normalised) + has_normal, has_texcoord (int32).
  * *records is released with ptb_free(). */
 int ptb_obj_read(const char* path, void** records, uint64_t* n_face_vertices);
+
+/* ---- roofline denominators measured on the device itself (the L2 peak is not in
+ *      MEASURED_PEAKS.json).  Streams `bytes` of device memory through every SM with 16-byte loads, `iters` times,
+ *      and returns the read bandwidth in GB/s: bytes <= 32 MiB stays L2-resident (L2 -> SM peak), bytes >> 126 MiB
+ *      measures HBM reads. */
+int ptb_microbench_read(ptb_context* ctx, size_t bytes, int iters, double* gb_per_s);
 
 /* ---- device self-test hooks used by the parity tests --------------------------- */
 /* op: 0 rng (in: seed as uint bits -> out: next seed bits, u), 1 sincos (x -> s, c),

@@ -117,10 +117,10 @@ EXPORTS = [
     "ptb_scene_copy_triangles", "ptb_scene_copy_material_ids", "ptb_scene_get_material", "ptb_scene_copy_texture",
     "ptb_scene_env_size", "ptb_scene_copy_env", "ptb_default_build_cfg", "ptb_accel_build", "ptb_accel_read",
     "ptb_camera_uvw", "ptb_params_default_camera", "ptb_default_render_cfg", "ptb_launch", "ptb_launch_get_stats", "ptb_launch_get_stage_ms", "ptb_context_get_totals",
-    "ptb_resolve", "ptb_trace_rays", "ptb_output_create", "ptb_output_resize", "ptb_output_map", "ptb_output_unmap",
+    "ptb_resolve", "ptb_resolve_peers", "ptb_ipc_export", "ptb_ipc_open", "ptb_ipc_close", "ptb_trace_rays", "ptb_output_create", "ptb_output_resize", "ptb_output_map", "ptb_output_unmap",
     "ptb_output_host_ptr", "ptb_output_width", "ptb_output_height", "ptb_output_destroy", "ptb_device_alloc",
     "ptb_device_free", "ptb_device_memset", "ptb_copy_to_device", "ptb_copy_to_host", "ptb_image_load_rgba8",
-    "ptb_image_load_float4", "ptb_save_image", "ptb_free", "ptb_obj_read", "ptb_test_device_math",
+    "ptb_image_load_float4", "ptb_save_image", "ptb_free", "ptb_obj_read", "ptb_microbench_read", "ptb_test_device_math",
 ]
 
 _lib = None
@@ -367,6 +367,26 @@ class Context:
         _check(lib().ptb_resolve(self._h, C.c_void_p(accum_ptr), C.c_void_p(accum_out_ptr), C.c_void_p(frame_ptr), C.c_uint32(n_pixels),
                                  C.c_float(scale), C.byref(cfg) if cfg is not None else None, C.c_void_p(stream)))
 
+    def resolve_peers(self, accum_ptrs, accum_out_ptr, frame_ptr, first_pixel, n_pixels, scale, cfg: RenderCfg | None = None, stream=0):
+        """Fused reduce -> tonemap -> gather over local/peer accumulators (one kernel, no NCCL on the data path)."""
+        arr = (C.c_void_p * len(accum_ptrs))(*accum_ptrs)
+        _check(lib().ptb_resolve_peers(self._h, arr, len(accum_ptrs), C.c_void_p(accum_out_ptr), C.c_void_p(frame_ptr), C.c_uint32(first_pixel),
+                                       C.c_uint32(n_pixels), C.c_float(scale), C.byref(cfg) if cfg is not None else None, C.c_void_p(stream)))
+
+    def ipc_export(self, ptr) -> bytes:
+        h = (C.c_ubyte * 64)()
+        _check(lib().ptb_ipc_export(self._h, C.c_void_p(ptr), h))
+        return bytes(h)
+
+    def ipc_open(self, handle: bytes) -> int:
+        h = (C.c_ubyte * 64)(*handle)
+        p = C.c_void_p()
+        _check(lib().ptb_ipc_open(self._h, h, C.byref(p)))
+        return p.value
+
+    def ipc_close(self, ptr):
+        _check(lib().ptb_ipc_close(self._h, C.c_void_p(ptr)))
+
     def synchronize(self, stream=0):
         _check(lib().ptb_context_synchronize(self._h, C.c_void_p(stream)))
 
@@ -410,6 +430,12 @@ class Context:
             for b in bufs:
                 self.free(b)
         return prim, t, b1, b2
+
+    def microbench_read(self, nbytes, iters=20) -> float:
+        """Read bandwidth in GB/s over a buffer of nbytes (<= 32 MiB: L2-resident; >> 126 MiB: HBM)."""
+        out = C.c_double()
+        _check(lib().ptb_microbench_read(self._h, C.c_size_t(nbytes), iters, C.byref(out)))
+        return out.value
 
     def test_device_math(self, op, inp: np.ndarray, out_stride) -> np.ndarray:
         a = np.ascontiguousarray(inp, np.float32)

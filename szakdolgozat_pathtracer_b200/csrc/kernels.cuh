@@ -528,6 +528,23 @@ __global__ void __launch_bounds__(256) k_resolve_scaled(const float4* __restrict
     if (frame) frame[i] = display_color(c, exposure_scale, inv_gamma, contrast);
 }
 
+// Fused reduce-scatter -> tonemap -> gather over peer memory: every rank runs this over ITS slice of the frame, reading
+// that slice from all ranks' accumulators (local HBM or NVLink peer loads) and storing the result where the root wants it.
+#define PTB_MAX_RANKS 16
+struct PeerAccums { const float4* a[PTB_MAX_RANKS]; int n; };
+__global__ void __launch_bounds__(256) k_resolve_peers(PeerAccums peers, float4* __restrict__ accum_out, uchar4* __restrict__ frame,
+                                                       uint32_t first, uint32_t n, float scale, float exposure_scale,
+                                                       float inv_gamma, float contrast) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t px = first + i;
+    float3 sum = mk3(0.0f);
+    for (int k = 0; k < peers.n; ++k) sum = sum + mk3(peers.a[k][px]);  // fixed rank order: deterministic
+    const float3 c = sum * scale;
+    if (accum_out) accum_out[px] = make_float4(c.x, c.y, c.z, 1.0f);
+    if (frame) frame[px] = display_color(c, exposure_scale, inv_gamma, contrast);
+}
+
 // ---- batch ray query + device self tests ----------------------------------------------------------
 __global__ void k_trace_rays(SceneView s, const float* __restrict__ origins, const float* __restrict__ dirs, uint32_t n,
                              float tmin, float tmax, int* __restrict__ prim, float* __restrict__ t, float* __restrict__ b1,
@@ -542,6 +559,19 @@ __global__ void k_trace_rays(SceneView s, const float* __restrict__ origins, con
     if (t) t[i] = h.t;
     if (b1) b1[i] = h.b1;
     if (b2) b2[i] = h.b2;
+}
+
+// read-bandwidth microbenchmark: every thread sums 16-byte loads over a grid-stride sweep, `iters` sweeps
+__global__ void __launch_bounds__(256) k_microbench_read(const float4* __restrict__ buf, size_t n_vec, int iters, float* __restrict__ sink) {
+    float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (int it = 0; it < iters; ++it) {
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
+            const float4 v = __ldcg(buf + i);  // cache at L2 only: this measures L2 -> SM (or HBM -> SM), not L1
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+    }
+    if (acc.x + acc.y + acc.z + acc.w == 123456.789f) sink[0] = acc.x;  // keeps the loads alive
 }
 
 __global__ void k_test_math(int op, const float* __restrict__ in, int in_stride, float* __restrict__ out, int out_stride, uint32_t n) {

@@ -484,6 +484,45 @@ int ptb_resolve(ptb_context* ctx, const ptb_float4* accum, ptb_float4* accum_out
     return PTB_OK;
 }
 
+int ptb_resolve_peers(ptb_context* ctx, const ptb_float4* const* accums, int n_ranks, ptb_float4* accum_out, ptb_uchar4* frame,
+                      uint32_t first_pixel, uint32_t n_pixels, float scale, const ptb_render_cfg* cfg_in, void* stream_) {
+    if (!ctx || !accums || n_ranks < 1 || n_ranks > PTB_MAX_RANKS) return fail(PTB_ERR_INVALID, "ptb_resolve_peers: bad arguments");
+    ptb_render_cfg cfg;
+    if (cfg_in) cfg = *cfg_in; else ptb_default_render_cfg(&cfg);
+    PeerAccums pa;
+    pa.n = n_ranks;
+    for (int k = 0; k < n_ranks; ++k) { if (!accums[k]) return fail(PTB_ERR_INVALID, "ptb_resolve_peers: null accumulator"); pa.a[k] = (const float4*)accums[k]; }
+    CU(cudaSetDevice(ctx->device));
+    if (n_pixels) k_resolve_peers<<<(n_pixels + 255u) / 256u, 256, 0, (cudaStream_t)stream_>>>(pa, (float4*)accum_out, (uchar4*)frame, first_pixel, n_pixels,
+                                                                                                scale, exp2f(cfg.exposure), 1.0f / cfg.gamma, cfg.contrast);
+    CU(cudaGetLastError());
+    return PTB_OK;
+}
+
+int ptb_ipc_export(ptb_context* ctx, const void* device_ptr, unsigned char handle[64]) {
+    if (!ctx || !device_ptr || !handle) return fail(PTB_ERR_INVALID, "ptb_ipc_export: bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CU(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, const_cast<void*>(device_ptr)));
+    memcpy(handle, &h, 64);
+    return PTB_OK;
+}
+int ptb_ipc_open(ptb_context* ctx, const unsigned char handle[64], void** device_ptr) {
+    if (!ctx || !handle || !device_ptr) return fail(PTB_ERR_INVALID, "ptb_ipc_open: bad arguments");
+    CU(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CU(cudaIpcOpenMemHandle(device_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return PTB_OK;
+}
+int ptb_ipc_close(ptb_context* ctx, void* device_ptr) {
+    if (!ctx || !device_ptr) return fail(PTB_ERR_INVALID, "ptb_ipc_close: bad arguments");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaIpcCloseMemHandle(device_ptr));
+    return PTB_OK;
+}
+
 int ptb_trace_rays(ptb_context* ctx, unsigned long long handle, const float* d_origins, const float* d_dirs, uint32_t n, float tmin,
                    float tmax, int32_t* d_prim, float* d_t, float* d_b1, float* d_b2, void* stream_) {
     if (!ctx || !d_origins || !d_dirs) return fail(PTB_ERR_INVALID, "ptb_trace_rays: bad arguments");
@@ -569,6 +608,30 @@ int ptb_copy_to_host(ptb_context* ctx, void* dst, const void* src, size_t bytes,
     CU(cudaSetDevice(ctx->device));
     CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CU(cudaStreamSynchronize((cudaStream_t)stream));
+    return PTB_OK;
+}
+
+int ptb_microbench_read(ptb_context* ctx, size_t bytes, int iters, double* gb_per_s) {
+    if (!ctx || !gb_per_s || bytes < 4096 || iters < 1) return fail(PTB_ERR_INVALID, "ptb_microbench_read: bad arguments");
+    CU(cudaSetDevice(ctx->device));
+    float4* buf = nullptr; float* sink = nullptr;
+    const size_t n_vec = bytes / 16;
+    CU(cudaMalloc((void**)&buf, n_vec * 16));
+    if (cudaMalloc((void**)&sink, 16) != cudaSuccess) { cudaFree(buf); return fail(PTB_ERR_CUDA, "cudaMalloc failed"); }
+    cudaMemset(buf, 0, n_vec * 16);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int grid = ctx->num_sms * 8;
+    k_microbench_read<<<grid, 256>>>(buf, n_vec, 2, sink);  // warm-up: brings the buffer into L2
+    cudaEventRecord(e0);
+    k_microbench_read<<<grid, 256>>>(buf, n_vec, iters, sink);
+    cudaEventRecord(e1);
+    cudaError_t e = cudaEventSynchronize(e1);
+    float ms = 0.0f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(buf); cudaFree(sink);
+    if (e != cudaSuccess || ms <= 0.0f) return fail(PTB_ERR_CUDA, std::string("ptb_microbench_read: ") + cudaGetErrorString(e));
+    *gb_per_s = (double)n_vec * 16.0 * (double)iters / ((double)ms * 1e-3) / 1e9;
     return PTB_OK;
 }
 

@@ -39,3 +39,53 @@ def reduce_accumulator(accum, dst: int = 0):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.reduce(accum, dst=dst, op=dist.ReduceOp.SUM)
     return accum
+
+
+def pixel_slice_for_rank(rank: int, world: int, n_pixels: int) -> tuple[int, int]:
+    """(first, count) of the frame slice rank reduces and tonemaps in the fused peer-memory exchange (ptb_resolve_peers)."""
+    if world < 1 or not (0 <= rank < world) or n_pixels < 0:
+        raise ValueError("bad rank/world/n_pixels")
+    k = -(-n_pixels // world)
+    lo, hi = min(rank * k, n_pixels), min((rank + 1) * k, n_pixels)
+    return lo, hi - lo
+
+
+class PeerExchange:
+    """One process per GPU: every rank exports its sum-mode accumulator (and the root its result buffers) through CUDA
+    IPC; resolve() then runs ptb_resolve_peers on this rank's slice.  NCCL is used only for two stream-ordered barriers."""
+
+    def __init__(self, ctx, rank, world, accum_ptr, out_accum_ptr, out_frame_ptr):
+        import torch.distributed as dist
+        self.ctx, self.rank, self.world = ctx, rank, world
+        mine = dict(accum=ctx.ipc_export(accum_ptr))
+        if rank == 0:
+            mine.update(out_accum=ctx.ipc_export(out_accum_ptr), out_frame=ctx.ipc_export(out_frame_ptr))
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        self._opened = []
+        self.accums = []
+        for r in range(world):
+            if r == rank:
+                self.accums.append(accum_ptr)
+            else:
+                p = ctx.ipc_open(gathered[r]["accum"]); self._opened.append(p); self.accums.append(p)
+        if rank == 0:
+            self.out_accum, self.out_frame = out_accum_ptr, out_frame_ptr
+        else:
+            self.out_accum = ctx.ipc_open(gathered[0]["out_accum"]); self.out_frame = ctx.ipc_open(gathered[0]["out_frame"])
+            self._opened += [self.out_accum, self.out_frame]
+
+    def resolve(self, n_pixels, n_subframes, cfg, stream, barrier):
+        """barrier(): a stream-ordered cross-rank barrier (e.g. a 1-element NCCL all_reduce on `stream`)."""
+        barrier()  # every rank has finished rendering into its accumulator
+        first, count = pixel_slice_for_rank(self.rank, self.world, n_pixels)
+        self.ctx.resolve_peers(self.accums, self.out_accum, self.out_frame, first, count, resolve_scale(n_subframes), cfg, stream)
+        barrier()  # every slice has landed in the root's buffers
+
+    def close(self):
+        for p in self._opened:
+            try:
+                self.ctx.ipc_close(p)
+            except Exception:
+                pass
+        self._opened = []

@@ -340,3 +340,32 @@ def test_launch_argument_errors(ptb, ctx, assets):
     bare = ptb.Scene.from_triangles(_one_tri().reshape(1, 32), None)
     with pytest.raises(ptb.PtbError):  # no environment map
         ctx.accel_build(bare)
+
+
+def test_resolve_peers_single_device(ptb, ctx):
+    """ptb_resolve_peers with three 'ranks' living on one device: fixed-order sum, scale, tonemap, slice handling."""
+    from szakdolgozat_pathtracer_b200 import parallel
+    rng = np.random.default_rng(5)
+    n = 1000
+    accs = [(rng.random((n, 4), dtype=np.float32) * 3).astype(np.float32) for _ in range(3)]
+    ptrs = [ctx.alloc(n * 16) for _ in range(3)]
+    d_out, d_frame = ctx.alloc(n * 16), ctx.alloc(n * 4)
+    try:
+        for pp, a in zip(ptrs, accs):
+            ctx.to_device(pp, a)
+        ctx.memset(d_out, 0, n * 16); ctx.memset(d_frame, 0, n * 4)
+        for r in range(3):  # three slices, as three ranks would do it
+            first, cnt = parallel.pixel_slice_for_rank(r, 3, n)
+            ctx.resolve_peers(ptrs, d_out, d_frame, first, cnt, 1.0 / 3.0)
+        ctx.synchronize()
+        out = ctx.to_host(d_out, (n, 4), np.float32)
+        frame = ctx.to_host(d_frame, (n, 4), np.uint8)
+        ctx.resolve(d_out, 0, d_frame, n, 1.0)  # tonemap of the same values through the single-GPU entry point
+        ctx.synchronize()
+        frame2 = ctx.to_host(d_frame, (n, 4), np.uint8)
+    finally:
+        for pp in ptrs + [d_out, d_frame]:
+            ctx.free(pp)
+    want = ((accs[0][:, :3] + accs[1][:, :3]) + accs[2][:, :3]) * np.float32(1.0 / 3.0)
+    assert np.array_equal(out[:, :3], want) and np.all(out[:, 3] == 1.0)
+    assert np.array_equal(frame, frame2) and frame[:, 3].min() == 255

@@ -59,6 +59,12 @@ def test_subframe_schedule():
     assert parallel.subframes_for_rank(1, 2, 5) == [1, 3]
     assert parallel.subframes_for_rank(3, 4, 2) == []  # ragged: more ranks than subframes
     assert parallel.resolve_scale(8) == 0.125
+    for world in (1, 2, 3, 8):
+        blocks = [parallel.subframe_block_for_rank(r, world, 17, first=4) for r in range(world)]
+        assert sum(blocks, []) == list(range(4, 21))
+        slices = [parallel.pixel_slice_for_rank(r, world, 1920 * 1080 + 5) for r in range(world)]
+        assert slices[0][0] == 0 and sum(c for _, c in slices) == 1920 * 1080 + 5
+        assert all(slices[i][0] + slices[i][1] == slices[i + 1][0] for i in range(world - 1))
     import pytest
     with pytest.raises(ValueError):
         parallel.subframes_for_rank(2, 2, 4)
