@@ -121,7 +121,12 @@ typedef struct ptb_render_cfg {
     int32_t accumulate_mode;  /* 0: running average by subframe_index (optixSphere.cu:403-409);
                                  1: accum += launch mean (sample-split multi-GPU; resolve with ptb_resolve) */
     int32_t write_frame;      /* 1: tonemap into Params.frame_buffer (optixSphere.cu:411-435); 0: skip */
-    int32_t env_importance_sampling; /* 0 = reference estimator (BSDF sampling only).  Reserved. */
+    int32_t env_importance_sampling; /* 0 = the reference estimator (BSDF sampling only; the parity-checked path).
+                                 1 = OPTIONAL MODE BEYOND THE REFERENCE: linear estimator with next-event estimation of the
+                                     environment through a prebuilt luminance*sin(theta) CDF, shadow rays and MIS;
+                                 2 = the same linear estimator with BSDF sampling only (A/B baseline for mode 1).
+                                 Modes 1/2 cannot reproduce the reference's expectation (its sample value is divided by
+                                 max(attenuation), optixSphere.cu:382-387) and are validated on their own. */
     int32_t count_traversal;  /* 1: also count BVH nodes visited / triangles tested (slower) */
     int32_t profile_stages;   /* 1: bracket every stage kernel with CUDA events (ptb_launch_get_stage_ms) */
     int32_t subframes_per_launch; /* default 1.  n > 1: this one call renders subframes subframe_index .. +n-1 as ONE
@@ -305,6 +310,8 @@ int ptb_microbench_read(ptb_context* ctx, size_t bytes, int iters, double* gb_pe
 /* ---- device self-test hooks used by the parity tests --------------------------- */
 /* op: 0 rng (in: seed as uint bits -> out: next seed bits, u), 1 sincos (x -> s, c),
  *     2 atan2 (y, x -> r), 3 asin (x -> r).  in/out are HOST arrays. */
+/* n samples of the scene's environment CDF: xi = n x 2 uniforms (HOST) -> out = n x 4 (direction xyz, solid-angle pdf) */
+int ptb_test_env_sample(ptb_context* ctx, unsigned long long handle, const float* xi, uint32_t n, float* out);
 int ptb_test_device_math(ptb_context* ctx, int op, const float* in, int in_stride, float* out, int out_stride, uint32_t n);
 
 #ifdef __cplusplus

@@ -120,7 +120,7 @@ EXPORTS = [
     "ptb_resolve", "ptb_resolve_peers", "ptb_ipc_export", "ptb_ipc_open", "ptb_ipc_close", "ptb_trace_rays", "ptb_output_create", "ptb_output_resize", "ptb_output_map", "ptb_output_unmap",
     "ptb_output_host_ptr", "ptb_output_width", "ptb_output_height", "ptb_output_destroy", "ptb_device_alloc",
     "ptb_device_free", "ptb_device_memset", "ptb_copy_to_device", "ptb_copy_to_host", "ptb_image_load_rgba8",
-    "ptb_image_load_float4", "ptb_save_image", "ptb_free", "ptb_obj_read", "ptb_microbench_read", "ptb_test_device_math",
+    "ptb_image_load_float4", "ptb_save_image", "ptb_free", "ptb_obj_read", "ptb_microbench_read", "ptb_test_env_sample", "ptb_test_device_math",
 ]
 
 _lib = None
@@ -436,6 +436,13 @@ class Context:
         out = C.c_double()
         _check(lib().ptb_microbench_read(self._h, C.c_size_t(nbytes), iters, C.byref(out)))
         return out.value
+
+    def test_env_sample(self, handle, xi: np.ndarray) -> np.ndarray:
+        """Samples of the scene's environment CDF: xi [n, 2] uniforms -> [n, 4] (direction, solid-angle pdf)."""
+        x = np.ascontiguousarray(xi, np.float32).reshape(-1, 2)
+        out = np.zeros((x.shape[0], 4), np.float32)
+        _check(lib().ptb_test_env_sample(self._h, C.c_ulonglong(handle), _fptr(x), C.c_uint32(x.shape[0]), _fptr(out)))
+        return out
 
     def test_device_math(self, op, inp: np.ndarray, out_stride) -> np.ndarray:
         a = np.ascontiguousarray(inp, np.float32)

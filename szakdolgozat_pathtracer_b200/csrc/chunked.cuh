@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(256) k_chunk_raygen(FrameView f, PathView p, u
     p.ray_o[i] = make_float4(o.x, o.y, o.z, 0.0f);
     p.ray_d[i] = make_float4(d.x, d.y, d.z, 0.0f);
     p.atten_seed[i] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(seed));
-    p.misc[i] = make_uint4(seed, (uint32_t)f.max_depth, 0u, 0u);
+    p.misc[i] = make_uint4(seed, (uint32_t)f.max_depth, 0u, __float_as_uint(-1.0f));  // .w: no BSDF pdf yet (linear.cuh)
     p.pixsum[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     status[i] = ST_TRACE;
 }

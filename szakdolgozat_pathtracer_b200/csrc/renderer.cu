@@ -25,7 +25,7 @@
 
 #include "bvh_build.h"
 #include "host.h"
-#include "chunked.cuh"
+#include "linear.cuh"
 
 namespace ptb {
 
@@ -37,6 +37,7 @@ struct DeviceScene {
     DevMaterial* mats = nullptr; int n_mats = 0;
     std::vector<void*> textures;
     float4* env = nullptr; int env_w = 0, env_h = 0;
+    float *cdf_marginal = nullptr, *cdf_conditional = nullptr, *cdf_row_weight = nullptr; float cdf_total = 0.0f;
     DeviceBvh bvh;
     unsigned long long handle = 0;
     ptb_context* owner = nullptr;
@@ -44,6 +45,8 @@ struct DeviceScene {
 
 void free_device_scene_buffers(DeviceScene* d) {
     cudaFree(d->verts); cudaFree(d->normals); cudaFree(d->uvs); cudaFree(d->mat_ids); cudaFree(d->mats); cudaFree(d->env);
+    cudaFree(d->cdf_marginal); cudaFree(d->cdf_conditional); cudaFree(d->cdf_row_weight);
+    d->cdf_marginal = d->cdf_conditional = d->cdf_row_weight = nullptr;
     for (void* t : d->textures) cudaFree(t);
     d->textures.clear();
     d->verts = d->normals = nullptr; d->uvs = nullptr; d->mat_ids = nullptr; d->mats = nullptr; d->env = nullptr;
@@ -67,6 +70,8 @@ struct ptb_context {
     unsigned long long* totals = nullptr;  // segments, hits, misses, launches since the last reset
     unsigned long long* launch_totals = nullptr;  // the same for the launch in flight ([3]: iterations of the fused pipeline)
     unsigned char* status = nullptr;       // one byte per slot (chunked pipelines)
+    // linear estimator (env_importance_sampling != 0): pending shadow rays, allocated on first use
+    float4 *shadow_o = nullptr, *shadow_d = nullptr, *shadow_c = nullptr; unsigned char* shadow_flag = nullptr; uint32_t shadow_slots = 0;
     int last_pipeline = 0;
     // last launch, for ptb_launch_get_stats
     cudaStream_t last_stream = nullptr;
@@ -113,6 +118,8 @@ cudaError_t upload(T** dst, const void* src, size_t bytes, cudaStream_t st) {
 void free_pool(ptb_context* c) {
     cudaFree(c->ray_o); cudaFree(c->ray_d); cudaFree(c->hit); cudaFree(c->atten_seed); cudaFree(c->pixsum); cudaFree(c->misc);
     cudaFree(c->q_trace[0]); cudaFree(c->q_trace[1]); cudaFree(c->q_hit); cudaFree(c->q_miss); cudaFree(c->status);
+    cudaFree(c->shadow_o); cudaFree(c->shadow_d); cudaFree(c->shadow_c); cudaFree(c->shadow_flag);
+    c->shadow_o = c->shadow_d = c->shadow_c = nullptr; c->shadow_flag = nullptr; c->shadow_slots = 0;
     c->status = nullptr;
     c->ray_o = c->ray_d = c->hit = c->atten_seed = c->pixsum = nullptr; c->misc = nullptr;
     c->q_trace[0] = c->q_trace[1] = c->q_hit = c->q_miss = nullptr;
@@ -256,6 +263,25 @@ int ptb_accel_build(ptb_context* ctx, ptb_scene* scene, const ptb_build_cfg* cfg
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // host staging vectors go out of scope below
     if (e != cudaSuccess) { free_device_scene_buffers(d); delete d; return fail(PTB_ERR_CUDA, std::string("scene upload: ") + cudaGetErrorString(e)); }
 
+    // environment CDF for the optional light-sampling mode (env_cdf.cuh): luminance * sin(theta), with a floor of
+    // 1 % of the mean luminance so that no direction with non-zero radiance has zero density
+    {
+        const int ew = d->env_w, eh = d->env_h;
+        double mean = 0.0;
+        for (size_t i = 0; i < scene->env.size(); i += 4) mean += 0.2126 * scene->env[i] + 0.7152 * scene->env[i + 1] + 0.0722 * scene->env[i + 2];
+        mean /= (double)ew * eh;
+        cudaError_t ce = cudaMalloc((void**)&d->cdf_marginal, (size_t)(eh + 1) * sizeof(float));
+        if (ce == cudaSuccess) ce = cudaMalloc((void**)&d->cdf_conditional, (size_t)eh * (ew + 1) * sizeof(float));
+        if (ce == cudaSuccess) ce = cudaMalloc((void**)&d->cdf_row_weight, (size_t)(eh + 1) * sizeof(float));
+        if (ce == cudaSuccess) {
+            k_env_row_cdf<<<eh, 256, 0, st>>>(d->env, ew, eh, (float)(0.01 * mean) + 1e-12f, d->cdf_conditional, d->cdf_row_weight);
+            k_env_marginal<<<1, 256, 0, st>>>(ew, eh, d->cdf_conditional, d->cdf_row_weight, d->cdf_marginal, d->cdf_row_weight + eh);
+            ce = cudaMemcpyAsync(&d->cdf_total, d->cdf_row_weight + eh, sizeof(float), cudaMemcpyDeviceToHost, st);
+            if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+        }
+        if (ce != cudaSuccess) { free_device_scene_buffers(d); delete d; return fail(PTB_ERR_CUDA, std::string("environment CDF: ") + cudaGetErrorString(ce)); }
+    }
+
     ptb_build_stats stats;
     std::string err;
     bool built = build_bvh(d->verts, n, cfg, st, d->bvh, stats, err);
@@ -303,7 +329,7 @@ int ptb_launch(ptb_context* ctx, const ptb_Params* P, const ptb_render_cfg* cfg_
     if (!P->accum_buffer) return fail(PTB_ERR_INVALID, "ptb_launch: Params.accum_buffer is null");
     if (cfg.write_frame && !P->frame_buffer) return fail(PTB_ERR_INVALID, "ptb_launch: Params.frame_buffer is null (set write_frame = 0 to skip tonemapping)");
     if (cfg.spp_per_launch < 1 || cfg.max_depth < 0 || cfg.max_depth > 1000) return fail(PTB_ERR_INVALID, "ptb_launch: bad spp_per_launch / max_depth");
-    if (cfg.env_importance_sampling) return fail(PTB_ERR_UNSUPPORTED, "env importance sampling cannot reproduce the reference estimator and is not implemented");
+    if (cfg.env_importance_sampling < 0 || cfg.env_importance_sampling > 2) return fail(PTB_ERR_INVALID, "ptb_launch: env_importance_sampling must be 0, 1 or 2");
     DeviceScene* d = find_scene(ctx, P->handle);
     if (!d) return fail(PTB_ERR_INVALID, "ptb_launch: Params.handle does not name a built acceleration structure");
     cudaStream_t st = (cudaStream_t)stream_;
@@ -352,7 +378,37 @@ int ptb_launch(ptb_context* ctx, const ptb_Params* P, const ptb_render_cfg* cfg_
     ctx->prof_iters = 0;
     uint32_t launches = 0;
     uint32_t prof_iters = iters;
-    if (pipeline == PTB_PIPELINE_QUEUES) {
+    if (cfg.env_importance_sampling) {
+        // optional mode beyond the reference (linear.cuh): trace -> shade(+NEE) -> shadow -> miss, one kernel per stage
+        if (slots > ctx->shadow_slots) {
+            cudaFree(ctx->shadow_o); cudaFree(ctx->shadow_d); cudaFree(ctx->shadow_c); cudaFree(ctx->shadow_flag);
+            ctx->shadow_o = ctx->shadow_d = ctx->shadow_c = nullptr; ctx->shadow_flag = nullptr; ctx->shadow_slots = 0;
+            CU(cudaMalloc((void**)&ctx->shadow_o, (size_t)slots * 16)); CU(cudaMalloc((void**)&ctx->shadow_d, (size_t)slots * 16));
+            CU(cudaMalloc((void**)&ctx->shadow_c, (size_t)slots * 16)); CU(cudaMalloc((void**)&ctx->shadow_flag, (size_t)slots + 64));
+            ctx->shadow_slots = slots;
+        }
+        CU(cudaMemsetAsync(ctx->shadow_flag, 0, (size_t)slots + 64, st));
+        LinearView lv;
+        lv.cdf.marginal = d->cdf_marginal; lv.cdf.conditional = d->cdf_conditional; lv.cdf.row_weight = d->cdf_row_weight;
+        lv.cdf.total = d->cdf_total; lv.cdf.w = d->env_w; lv.cdf.h = d->env_h;
+        lv.shadow_o = ctx->shadow_o; lv.shadow_d = ctx->shadow_d; lv.shadow_c = ctx->shadow_c; lv.shadow_flag = ctx->shadow_flag;
+        lv.nee = cfg.env_importance_sampling == 1 ? 1 : 0;
+        pipeline = PTB_PIPELINE_CHUNK_STAGES;
+        const uint32_t chunks = (slots + PTB_CHUNK - 1u) / PTB_CHUNK;
+        k_chunk_raygen<<<pix_blocks, 256, 0, st>>>(f, p, ctx->status);
+        if (prof) CU(cudaEventRecord(ctx->events[1], st));
+        launches = 1;
+        for (uint32_t it = 0; it < iters; ++it) {
+            k_chunk_trace<false, PTB_TRACE_QUANTUM><<<chunks, PTB_CHUNK_THREADS, 0, st>>>(s, f, p, ctx->status, ctx->launch_totals, ctx->trav_stats, (int)it);
+            if (prof) CU(cudaEventRecord(ctx->events[2 + (size_t)it * 3 + 0], st));
+            k_chunk_shade_linear<<<chunks, PTB_CHUNK_THREADS, 0, st>>>(s, f, p, lv, ctx->status);
+            if (lv.nee) { k_chunk_shadow<<<chunks, PTB_CHUNK_THREADS, 0, st>>>(s, f, p, lv); launches += 1; }
+            if (prof) CU(cudaEventRecord(ctx->events[2 + (size_t)it * 3 + 1], st));
+            k_chunk_miss_linear<<<chunks, PTB_CHUNK_THREADS, 0, st>>>(s, f, p, lv, ctx->status);
+            if (prof) CU(cudaEventRecord(ctx->events[2 + (size_t)it * 3 + 2], st));
+            launches += 3;
+        }
+    } else if (pipeline == PTB_PIPELINE_QUEUES) {
         // global queues, one kernel per stage and iteration (kernels.cuh)
         k_raygen_init<<<pix_blocks, 256, 0, st>>>(f, p, q);
         if (prof) CU(cudaEventRecord(ctx->events[1], st));
@@ -632,6 +688,26 @@ int ptb_microbench_read(ptb_context* ctx, size_t bytes, int iters, double* gb_pe
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(buf); cudaFree(sink);
     if (e != cudaSuccess || ms <= 0.0f) return fail(PTB_ERR_CUDA, std::string("ptb_microbench_read: ") + cudaGetErrorString(e));
     *gb_per_s = (double)n_vec * 16.0 * (double)iters / ((double)ms * 1e-3) / 1e9;
+    return PTB_OK;
+}
+
+int ptb_test_env_sample(ptb_context* ctx, unsigned long long handle, const float* xi, uint32_t n, float* out) {
+    if (!ctx || !xi || !out) return fail(PTB_ERR_INVALID, "ptb_test_env_sample: bad arguments");
+    DeviceScene* d = find_scene(ctx, handle);
+    if (!d) return fail(PTB_ERR_INVALID, "ptb_test_env_sample: unknown handle");
+    CU(cudaSetDevice(ctx->device));
+    float *d_xi = nullptr, *d_out = nullptr;
+    CU(cudaMalloc((void**)&d_xi, (size_t)n * 8 + 16));
+    if (cudaMalloc((void**)&d_out, (size_t)n * 16 + 16) != cudaSuccess) { cudaFree(d_xi); return fail(PTB_ERR_CUDA, "cudaMalloc failed"); }
+    cudaMemcpy(d_xi, xi, (size_t)n * 8, cudaMemcpyHostToDevice);
+    EnvCdf cdf;
+    cdf.marginal = d->cdf_marginal; cdf.conditional = d->cdf_conditional; cdf.row_weight = d->cdf_row_weight; cdf.total = d->cdf_total;
+    cdf.w = d->env_w; cdf.h = d->env_h;
+    if (n) k_env_sample_test<<<(n + 255u) / 256u, 256>>>(cdf, d_xi, n, d_out);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(out, d_out, (size_t)n * 16, cudaMemcpyDeviceToHost);
+    cudaFree(d_xi); cudaFree(d_out);
+    if (e != cudaSuccess) return fail(PTB_ERR_CUDA, std::string("ptb_test_env_sample: ") + cudaGetErrorString(e));
     return PTB_OK;
 }
 

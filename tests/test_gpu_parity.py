@@ -328,9 +328,8 @@ def test_launch_argument_errors(ptb, ctx, assets):
         with pytest.raises(ptb.PtbError):  # unknown acceleration structure
             ctx.launch(p, ptb.default_render_cfg(write_frame=0))
         p.handle = handle
-        with pytest.raises(ptb.PtbError) as e:  # cannot reproduce the reference estimator
-            ctx.launch(p, ptb.default_render_cfg(write_frame=0, env_importance_sampling=1))
-        assert e.value.code == ptb.PTB_ERR_UNSUPPORTED
+        with pytest.raises(ptb.PtbError):  # 0 = reference estimator, 1/2 = the optional linear modes
+            ctx.launch(p, ptb.default_render_cfg(write_frame=0, env_importance_sampling=7))
         with pytest.raises(ptb.PtbError):
             ctx.launch(p, ptb.default_render_cfg(write_frame=0, spp_per_launch=0))
         ctx.launch(p, ptb.default_render_cfg(write_frame=0, spp_per_launch=1, max_depth=2))  # and a valid one still works
