@@ -5,7 +5,7 @@
 // over a pool that is larger than L2 (1.6 GB at 8 subframes): both kernels sat at ~45 % of HBM peak, stalled on
 // long-scoreboard, with an L2 hit rate below 30 % even for the 2 MB of geometry.
 //
-// Layout: one status byte per slot (ST_TRACE / ST_HIT / ST_MISS / ST_DONE).  A block owns PTB_CHUNK
+// Layout: one status byte per slot (ST_TRACE / ST_HIT / ST_MISS / ST_DONE).  A block owns PTB_CHUNK (2048)
 // consecutive slots.  Every stage first compacts the slots of its chunk that are in the wanted state into a list
 // in shared memory (8 status bytes per thread, warp ballot-free popcount + block scan; the list is ascending, so
 // the state accesses that follow are coalesced and fully use their sectors), then runs the stage body over that
@@ -25,8 +25,10 @@
 
 namespace ptb {
 
-#define PTB_CHUNK 1024           // slots per block
-#define PTB_CHUNK_THREADS 128    // 8 slots per thread in the compaction step
+#ifndef PTB_CHUNK_THREADS
+#define PTB_CHUNK_THREADS 256    // 8 slots per thread in the compaction step (measured on C2: 256 > 512 > 128)
+#endif
+#define PTB_CHUNK (PTB_CHUNK_THREADS * 8)  // slots per block
 
 enum SlotStatus : unsigned char { ST_DONE = 0, ST_TRACE = 1, ST_HIT = 2, ST_MISS = 3 };
 
@@ -211,7 +213,7 @@ __global__ void __launch_bounds__(PTB_CHUNK_THREADS) k_chunk_miss(SceneView s, F
 // One block = one chunk, from the first camera ray to the last sample of its pixels.
 // totals[3] is not touched here (launch count is added by k_fold_counters' sibling on the host path).
 template <bool COUNT, int QUANTUM, int MINB>
-__global__ void __launch_bounds__(PTB_CHUNK_THREADS, MINB) k_chunk_fused(SceneView s, FrameView f, PathView p, unsigned char* status,
+__global__ void __launch_bounds__(PTB_CHUNK_THREADS, (MINB * 128) / PTB_CHUNK_THREADS) k_chunk_fused(SceneView s, FrameView f, PathView p, unsigned char* status,
                                                                   unsigned long long* totals, unsigned long long* trav_stats,
                                                                   unsigned int* max_iters_seen) {
     __shared__ ChunkShared sh;

@@ -60,8 +60,12 @@ PTB_DEV float pcg_hash_f(uint32_t input) {
     return (float)((word >> 22u) ^ word);
 }
 PTB_DEV float myrnd(uint32_t& seed) {
-    seed = (uint32_t)pcg_hash_f(seed);
-    return (float)seed / 4294967296.0f;  // (float)UINT_MAX == 2^32
+    // seed = pcg_hash(seed) converts the float back to uint (saturating); (float)seed is then the SAME float again
+    // (2^32 saturates to 0xFFFFFFFF, which rounds back to 2^32), and dividing by (float)UINT_MAX == 2^32 is an exact
+    // scaling: one int->float conversion per draw instead of two, bit-identical to optixSphere.cu:32-35.
+    const float hf = pcg_hash_f(seed);
+    seed = (uint32_t)hf;
+    return hf * 2.3283064365386962890625e-10f;
 }
 
 // ---- detmath (same algorithms as oracle/oracle_math.h) -------------------------

@@ -451,7 +451,7 @@ int ptb_launch(ptb_context* ctx, const ptb_Params* P, const ptb_render_cfg* cfg_
             unsigned int* max_iters = (unsigned int*)(ctx->launch_totals + 3);
             // 64 registers / 8 blocks per SM once there are enough chunks to keep that many blocks busy (the fused kernel
             // is occupancy-limited: +12 % at 8 batched subframes), the unconstrained 94-register build for small frames
-            const bool wide = chunks >= (uint32_t)ctx->num_sms * 8u * 4u;
+            const bool wide = chunks >= (uint32_t)ctx->num_sms * (1024u / PTB_CHUNK_THREADS) * 4u;
             if (cfg.count_traversal) k_chunk_fused<true, PTB_TRACE_QUANTUM, 5><<<chunks, PTB_CHUNK_THREADS, 0, st>>>(s, f, p, ctx->status, ctx->launch_totals, ctx->trav_stats, max_iters);
             else if (wide) k_chunk_fused<false, PTB_TRACE_QUANTUM, 8><<<chunks, PTB_CHUNK_THREADS, 0, st>>>(s, f, p, ctx->status, ctx->launch_totals, ctx->trav_stats, max_iters);
             else k_chunk_fused<false, PTB_TRACE_QUANTUM, 5><<<chunks, PTB_CHUNK_THREADS, 0, st>>>(s, f, p, ctx->status, ctx->launch_totals, ctx->trav_stats, max_iters);
