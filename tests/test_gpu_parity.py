@@ -389,3 +389,20 @@ def test_c3_full_pbr_parity_crop(ptb, ctx, oh, assets):
     assert bad.sum() == 0, f"{bad.sum()} of {W * H} accum pixels differ"
     assert (gh < 2204).mean() > 0.2  # the textured mesh covers a good part of the frame
     assert np.abs(gf.astype(np.int32) - cf.astype(np.int32)).max() <= 1
+
+
+def test_c2_full_frame_primary_hits(ptb, ctx, oh, assets):
+    """BASELINE config 2 at its full size: all 2 073 600 primary-hit triangle IDs (DoF on) and the 1-sample image, bit-exact."""
+    if PIPELINE != 3:
+        pytest.skip("full-frame check on the default pipeline")
+    sc = load_config(ptb, assets, "c2")
+    handle, _ = ctx.accel_build(sc)
+    osc = oh.OracleScene.from_ptb(sc, guard=False)
+    kw = dict(spp_per_launch=1, max_depth=2)
+    ga, gf, gh, gst = _render_gpu(ptb, ctx, handle, 1920, 1080, kw)
+    ca, cf, ch, cseg = _render_cpu(oh, ptb, osc, 1920, 1080, kw)
+    mism = int((gh != ch).sum())
+    assert mism == 0, f"{mism} of 2073600 primary hits differ (edge ties would show up here)"
+    assert gst[0].segments == cseg
+    assert np.array_equal(ga.view(np.uint32), ca.view(np.uint32))
+    assert 0.02 < (gh < 15744).mean() < 0.2 and (gh == -1).mean() > 0.1
