@@ -171,6 +171,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pipeline", type=int, default=3, help="1 global queues, 2 chunked stage kernels, 3 chunked fused (default)")
     ap.add_argument("--config", default="c2", choices=list(CONFIGS))
+    ap.add_argument("--split", default="samples", choices=["samples", "tiles"],
+                    help="N > 1: split the frame's subframes across ranks (weak scaling, default) or its rows (tile partitioning, strong scaling)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="N > 1: fused peer-memory exchange (default) or NCCL reduce")
     args = ap.parse_args()
     select_config(args.config)
@@ -212,8 +214,13 @@ def main():
     frame = torch.zeros((H, W, 4), dtype=torch.uint8, device=dev)
     multi = world > 1
     # the whole 64-spp frame of this rank is ONE wavefront: 8 subframes x 1920 x 1080 path slots
+    tiles = multi and args.split == "tiles"
+    band = (0, 0)
+    il = dict(row_interleave_count=world, row_interleave_index=rank, row_interleave_height=16) if tiles else {}
+    total_subframes = LAUNCHES_PER_STEP * (1 if (tiles or not multi) else world)   # subframes in the frame all ranks produce together
     cfg = ptb.default_render_cfg(spp_per_launch=SPP_PER_LAUNCH, max_depth=DEPTH, subframes_per_launch=LAUNCHES_PER_STEP,
-                                 pipeline=args.pipeline, accumulate_mode=1 if multi else 0, write_frame=0 if multi else 1)
+                                 pipeline=args.pipeline, accumulate_mode=1 if multi else 0, write_frame=0 if multi else 1,
+                                 row_begin=band[0], row_end=band[1], **il)
 
     # N > 1 exchange.  "p2p": every rank reduces + tonemaps its slice of the frame straight out of the peers' accumulators
     # (CUDA IPC mappings over NVLink) and stores it into rank 0's buffers: ONE kernel per rank (ptb_resolve_peers), NCCL only
@@ -250,17 +257,19 @@ def main():
         # a fresh 64-spp frame: the accumulator restarts (the reference resets subframe_index on camera change, cpp:267-278)
         if multi:
             zero_accum()
-        # rank r renders the contiguous block of subframes [r*8, r*8+8) of the 64*N-spp frame
-        first = parallel.subframe_block_for_rank(rank, world, LAUNCHES_PER_STEP * world)[0]
+        # samples: rank r renders the contiguous block of subframes [r*8, r*8+8) of the 64*N-spp frame;
+        # tiles:   every rank renders subframes [0, 8) of ITS row band (the rest of its accumulator stays zero, so the
+        #          same sum-exchange doubles as the gather)
+        first = 0 if tiles else parallel.subframe_block_for_rank(rank, world, LAUNCHES_PER_STEP * world)[0]
         p = ptb.make_params(W, H, subframe_index=first, dof=True, **CAMERAS[CAMERA])
         p.accum_buffer, p.frame_buffer, p.handle = acc_ptr, frame_ptr, handle
         ctx.launch(p, cfg_used, stream=stream)
         if multi and exchange is not None:
-            exchange.resolve(n, LAUNCHES_PER_STEP * world, cfg_used, stream, stream_barrier)
+            exchange.resolve(n, total_subframes, cfg_used, stream, stream_barrier)
         elif multi:
             parallel.reduce_accumulator(accum, dst=0)
             if rank == 0:
-                ctx.resolve(acc_ptr, acc_ptr, frame_ptr, n, parallel.resolve_scale(LAUNCHES_PER_STEP * world), cfg_used, stream=stream)
+                ctx.resolve(acc_ptr, acc_ptr, frame_ptr, n, parallel.resolve_scale(total_subframes), cfg_used, stream=stream)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -298,12 +307,13 @@ def main():
     # (1) the timed pipeline with profile_stages: for the fused pipeline "trace" is the one persistent kernel
     def profiled(pipeline):
         cfgp = ptb.default_render_cfg(spp_per_launch=SPP_PER_LAUNCH, max_depth=DEPTH, subframes_per_launch=LAUNCHES_PER_STEP,
-                                      pipeline=pipeline, accumulate_mode=cfg.accumulate_mode, write_frame=cfg.write_frame, profile_stages=1)
+                                      pipeline=pipeline, accumulate_mode=cfg.accumulate_mode, write_frame=cfg.write_frame, profile_stages=1,
+                                      row_begin=band[0], row_end=band[1], **il)
         acc = {k: 0.0 for k in ("raygen", "trace", "shade", "miss", "resolve", "total")}
         reps = max(1, min(args.steps, 3))
         for _ in range(reps):
             zero_accum()
-            first = parallel.subframe_block_for_rank(rank, world, LAUNCHES_PER_STEP * world)[0]
+            first = 0 if tiles else parallel.subframe_block_for_rank(rank, world, LAUNCHES_PER_STEP * world)[0]
             pp = ptb.make_params(W, H, subframe_index=first, dof=True, **CAMERAS[CAMERA])
             pp.accum_buffer, pp.frame_buffer, pp.handle = acc_ptr, frame_ptr, handle
             ctx.launch(pp, cfgp, stream=stream)
@@ -398,15 +408,15 @@ def main():
     if rank == 0:
         line = {
             "metric": "Msegments/s", "value": value, "unit": "Msegments/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong" if tiles else "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "spp_per_step_per_gpu": SPP_PER_LAUNCH * LAUNCHES_PER_STEP,
+            "config": {"workload": WORKLOAD, "spp_per_step_per_gpu": SPP_PER_LAUNCH * LAUNCHES_PER_STEP, "split": ("tiles (16-row strips dealt round-robin)" if tiles else "samples") if multi else "none",
                        "l2": "no flush: the path pool of one step is 8 x 1920 x 1080 slots x 97 B = 1.6 GB (> 126 MB L2) and is rewritten every iteration",
                        "pipeline": {1: "global queues", 2: "block-local wavefront, one kernel per stage and iteration", 3: "block-local wavefront, fused persistent kernel"}[args.pipeline],
                        "subframes_per_launch": LAUNCHES_PER_STEP,
                        "multi_gpu": ("scene replicated, subframes split by rank; exchange: " + exchange_note) if multi else "single GPU, reference accumulate mode",
                        "bvh": {"triangles": bst.num_triangles, "nodes": bst.num_nodes, "max_depth": bst.max_depth, "sah": bst.sah_cost, "build_ms": bst.build_ms}},
-            "spp_per_s_1080p": SPP_PER_LAUNCH * LAUNCHES_PER_STEP * world * args.steps / (ms_max * 1e-3) * (W * H / (1920.0 * 1080.0)),
+            "spp_per_s_1080p": SPP_PER_LAUNCH * total_subframes * args.steps / (ms_max * 1e-3) * (W * H / (1920.0 * 1080.0)),
             "segments_per_step": seg_total / args.steps,
             "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
         }

@@ -137,6 +137,12 @@ typedef struct ptb_render_cfg {
                                  2: block-local wavefront over chunks of the path pool, one kernel per stage and
                                     iteration; 3: the same stages fused into one persistent kernel per launch.
                                  All three produce bit-identical results. */
+    int32_t row_begin, row_end; /* 0, 0 = the whole frame.  Otherwise only image rows [row_begin, row_end) are rendered (and only
+                                 those rows of accum/frame/aux are touched): tile partitioning for multi-GPU single-pass frames.
+                                 Every pixel is still seeded by its full-frame coordinates, so bands tile bit-identically. */
+    int32_t row_interleave_count, row_interleave_index, row_interleave_height; /* count > 1: the frame is cut into strips of
+                                 `height` rows and this launch renders strips index, index + count, ... (load-balanced tile
+                                 partitioning: sky strips are cheap, strips over the mesh are not).  Chunked pipelines only. */
     int32_t* aux_primary_hit; /* optional DEVICE int32[W*H]: primitive hit by the first segment of sample 0, -1 = miss */
 } ptb_render_cfg;
 

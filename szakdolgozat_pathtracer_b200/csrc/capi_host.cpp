@@ -54,7 +54,7 @@ void ptb_default_render_cfg(ptb_render_cfg* cfg) {
     cfg->spp_per_launch = 10; cfg->max_depth = 20; cfg->tmin = 0.01f; cfg->tmax = 1e16f;
     cfg->dof_blur = 0.01f; cfg->focus_dist = 1.0f; cfg->nmap_strength = 0.4f;
     cfg->exposure = -0.5f; cfg->gamma = 2.2f; cfg->contrast = 1.25f;
-    cfg->accumulate_mode = 0; cfg->write_frame = 1; cfg->env_importance_sampling = 0; cfg->count_traversal = 0; cfg->profile_stages = 0; cfg->subframes_per_launch = 1; cfg->pipeline = 0;
+    cfg->accumulate_mode = 0; cfg->write_frame = 1; cfg->env_importance_sampling = 0; cfg->count_traversal = 0; cfg->profile_stages = 0; cfg->subframes_per_launch = 1; cfg->pipeline = 0; cfg->row_begin = 0; cfg->row_end = 0; cfg->row_interleave_count = 0; cfg->row_interleave_index = 0; cfg->row_interleave_height = 0;
     cfg->aux_primary_hit = nullptr;
 }
 

@@ -109,7 +109,7 @@ PTB_DEV void chunk_stage_trace(ChunkShared& sh, const SceneView& s, const FrameV
             const bool is_hit = t.best.prim >= 0;
             status[slot] = is_hit ? ST_HIT : ST_MISS;
             hits += is_hit ? 1u : 0u;
-            if (first_iteration && f.aux_primary && slot < f.n_pixels) f.aux_primary[slot] = t.best.prim;
+            if (first_iteration && f.aux_primary && slot < f.n_pixels) f.aux_primary[(size_t)image_row(f, slot / f.W) * f.W + slot % f.W] = t.best.prim;
         }
     }
     for (int off = 16; off > 0; off >>= 1) hits += __shfl_xor_sync(0xffffffffu, hits, off);
@@ -170,7 +170,9 @@ __global__ void __launch_bounds__(256) k_chunk_raygen(FrameView f, PathView p, u
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.n_slots) return;
     const uint32_t pix = i % f.n_pixels, sub = i / f.n_pixels;
-    const uint32_t ix = pix % f.W, iy = pix / f.W;
+    const uint32_t ix = pix % f.W, iy = image_row(f, pix / f.W);
+    p.pixsum[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (iy >= f.H) { status[i] = ST_DONE; return; }  // padding rows of the last interleaved strip
     uint32_t seed = iy * f.W + ix + ((uint32_t)f.subframe + sub) * f.W * f.H;  // cu:316
     float3 o, d;
     start_sample(f, ix, iy, seed, o, d);
@@ -178,7 +180,6 @@ __global__ void __launch_bounds__(256) k_chunk_raygen(FrameView f, PathView p, u
     p.ray_d[i] = make_float4(d.x, d.y, d.z, 0.0f);
     p.atten_seed[i] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(seed));
     p.misc[i] = make_uint4(seed, (uint32_t)f.max_depth, 0u, __float_as_uint(-1.0f));  // .w: no BSDF pdf yet (linear.cuh)
-    p.pixsum[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     status[i] = ST_TRACE;
 }
 

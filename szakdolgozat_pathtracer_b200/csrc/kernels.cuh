@@ -37,7 +37,9 @@ struct SceneView {
 
 struct FrameView {
     uint32_t W, H;
-    uint32_t n_pixels;   // W * H
+    uint32_t row0;       // first image row rendered by this launch (row band; 0 for the whole frame)
+    uint32_t il_n, il_r, il_h;  // il_n > 1: interleaved strips of il_h rows, this launch renders strips il_r, il_r + il_n, ...
+    uint32_t n_pixels;   // W * rows of the band
     int n_subframes;     // subframes rendered by this launch as ONE wavefront (slot = sub * n_pixels + pixel)
     int subframe, dof;   // subframe = index of the first one
     float3 eye, U, V, Wv;
@@ -70,6 +72,12 @@ struct QueueView {
 
 #define PTB_PI_F 3.14159265358979323846f
 
+// image row of the launch-local row lr (identity / row band / interleaved strips); may be >= H for the padded last strip
+PTB_DEV uint32_t image_row(const FrameView& f, uint32_t lr) {
+    if (f.il_n > 1u) return ((lr / f.il_h) * f.il_n + f.il_r) * f.il_h + lr % f.il_h;
+    return f.row0 + lr;
+}
+
 // ---- camera ray of one sample (cu:326-347) ------------------------------------------
 PTB_DEV void start_sample(const FrameView& f, uint32_t ix, uint32_t iy, uint32_t& seed, float3& origin, float3& direction) {
     const float jx = myrnd(seed);
@@ -99,7 +107,7 @@ __global__ void __launch_bounds__(256) k_raygen_init(FrameView f, PathView p, Qu
     if (i == 0) q.counters[0] = p.n_slots;
     if (i >= p.n_slots) return;
     const uint32_t pix = i % f.n_pixels, sub = i / f.n_pixels;
-    const uint32_t ix = pix % f.W, iy = pix / f.W;
+    const uint32_t ix = pix % f.W, iy = image_row(f, pix / f.W);
     uint32_t seed = iy * f.W + ix + ((uint32_t)f.subframe + sub) * f.W * f.H;  // cu:316
     float3 o, d;
     start_sample(f, ix, iy, seed, o, d);
@@ -139,7 +147,7 @@ __global__ void __launch_bounds__(128) k_trace(SceneView s, FrameView f, PathVie
             const bool is_hit = t.best.prim >= 0;
             if (pending) {
                 p.hit[slot] = make_float4(t.best.t, t.best.b1, t.best.b2, __int_as_float(t.best.prim));
-                if (iter == 0 && f.aux_primary && slot < f.n_pixels) f.aux_primary[slot] = t.best.prim;
+                if (iter == 0 && f.aux_primary && slot < f.n_pixels) f.aux_primary[(size_t)image_row(f, slot / f.W) * f.W + slot % f.W] = t.best.prim;
             }
             queue_push(q.hit, &q.counters[iter * 4 + 1], pending && is_hit, slot);
             queue_push(q.miss, &q.counters[iter * 4 + 2], pending && !is_hit, slot);
@@ -391,7 +399,7 @@ PTB_DEV bool after_segment(const FrameView& f, const PathView& p, uint32_t slot,
     if (sample >= (uint32_t)f.spp) return false;
     float3 o, d;
     const uint32_t pix = slot % f.n_pixels;
-    start_sample(f, pix % f.W, pix / f.W, seed_rg, o, d);
+    start_sample(f, pix % f.W, image_row(f, pix / f.W), seed_rg, o, d);
     p.ray_o[slot] = make_float4(o.x, o.y, o.z, 0.0f);
     p.ray_d[slot] = make_float4(d.x, d.y, d.z, 0.0f);
     p.atten_seed[slot] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(seed_rg));
@@ -480,20 +488,23 @@ __global__ void __launch_bounds__(256) k_resolve(FrameView f, PathView p) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= f.n_pixels) return;
     // the subframes of this launch are folded in order, exactly as consecutive launches would do it
+    const uint32_t iy = image_row(f, i / f.W);
+    if (iy >= f.H) return;  // padding rows of the last interleaved strip
+    const size_t px = (size_t)iy * f.W + i % f.W;  // position in the caller's full-frame buffers
     float3 accum_color = mk3(0.0f);
     for (int sub = 0; sub < f.n_subframes; ++sub) {
         const float4 sum = p.pixsum[(size_t)sub * f.n_pixels + i];
         accum_color = mk3(sum) / (float)f.spp;  // cu:401
         const int subframe = f.subframe + sub;
         if (f.accumulate_mode == 1) {
-            accum_color = mk3(f.accum[i]) + accum_color;
+            accum_color = mk3(f.accum[px]) + accum_color;
         } else if (subframe > 0) {
             const float a = 1.0f / (float)(subframe + 1);
-            accum_color = lerp(mk3(f.accum[i]), accum_color, a);  // cu:403-408
+            accum_color = lerp(mk3(f.accum[px]), accum_color, a);  // cu:403-408
         }
-        f.accum[i] = make_float4(accum_color.x, accum_color.y, accum_color.z, 1.0f);
+        f.accum[px] = make_float4(accum_color.x, accum_color.y, accum_color.z, 1.0f);
     }
-    if (f.write_frame && f.frame) f.frame[i] = display_color(accum_color, f.exposure_scale, f.inv_gamma, f.contrast);
+    if (f.write_frame && f.frame) f.frame[px] = display_color(accum_color, f.exposure_scale, f.inv_gamma, f.contrast);
 }
 
 // Folds the per-iteration queue sizes of one launch into the context's running totals

@@ -96,7 +96,7 @@ PTB_DEV bool linear_next_sample(const FrameView& f, const PathView& p, uint32_t 
     if (sample >= (uint32_t)f.spp) return false;
     const uint32_t pix = slot % f.n_pixels;
     float3 o, d;
-    start_sample(f, pix % f.W, pix / f.W, seed_rg, o, d);
+    start_sample(f, pix % f.W, image_row(f, pix / f.W), seed_rg, o, d);
     p.ray_o[slot] = make_float4(o.x, o.y, o.z, 0.0f);
     p.ray_d[slot] = make_float4(d.x, d.y, d.z, 0.0f);
     p.atten_seed[slot] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(seed_rg));

@@ -336,7 +336,24 @@ int ptb_launch(ptb_context* ctx, const ptb_Params* P, const ptb_render_cfg* cfg_
     CU(cudaSetDevice(ctx->device));
 
     const int n_sub = cfg.subframes_per_launch < 1 ? 1 : cfg.subframes_per_launch;
-    const uint32_t n_pixels = P->image_width * P->image_height;
+    uint32_t row0 = 0, rows = P->image_height;
+    if (cfg.row_begin != 0 || cfg.row_end != 0) {
+        if (cfg.row_begin < 0 || cfg.row_end <= cfg.row_begin || (uint32_t)cfg.row_end > P->image_height)
+            return fail(PTB_ERR_INVALID, "ptb_launch: bad row band");
+        row0 = (uint32_t)cfg.row_begin; rows = (uint32_t)(cfg.row_end - cfg.row_begin);
+    }
+    uint32_t il_n = 0, il_r = 0, il_h = 0;
+    if (cfg.row_interleave_count > 1) {
+        if (cfg.row_begin != 0 || cfg.row_end != 0 || cfg.row_interleave_index < 0 || cfg.row_interleave_index >= cfg.row_interleave_count ||
+            cfg.row_interleave_height < 1)
+            return fail(PTB_ERR_INVALID, "ptb_launch: bad row interleave");
+        il_n = (uint32_t)cfg.row_interleave_count; il_r = (uint32_t)cfg.row_interleave_index; il_h = (uint32_t)cfg.row_interleave_height;
+        const uint32_t strips = (P->image_height + il_h - 1u) / il_h;                 // strips in the frame
+        const uint32_t mine = strips > il_r ? (strips - il_r + il_n - 1u) / il_n : 0u;  // strips il_r, il_r + il_n, ...
+        rows = mine * il_h;                                                             // the last one may be padded
+        if (rows == 0) return PTB_OK;  // more ranks than strips: nothing to render
+    }
+    const uint32_t n_pixels = P->image_width * rows;
     if ((uint64_t)n_pixels * (uint64_t)n_sub > 0x7fffffffull) return fail(PTB_ERR_INVALID, "ptb_launch: subframes_per_launch * pixels too large");
     const uint32_t slots = n_pixels * (uint32_t)n_sub;
     const uint32_t iters = (uint32_t)cfg.spp_per_launch * (uint32_t)(cfg.max_depth + 1);
@@ -344,7 +361,7 @@ int ptb_launch(ptb_context* ctx, const ptb_Params* P, const ptb_render_cfg* cfg_
     if (rc != PTB_OK) return rc;
 
     FrameView f;
-    f.W = P->image_width; f.H = P->image_height; f.n_pixels = n_pixels; f.n_subframes = n_sub; f.subframe = P->subframe_index; f.dof = P->dof ? 1 : 0;
+    f.W = P->image_width; f.H = P->image_height; f.row0 = row0; f.il_n = il_n; f.il_r = il_r; f.il_h = il_h; f.n_pixels = n_pixels; f.n_subframes = n_sub; f.subframe = P->subframe_index; f.dof = P->dof ? 1 : 0;
     f.eye = make_float3(P->eye.x, P->eye.y, P->eye.z); f.U = make_float3(P->U.x, P->U.y, P->U.z);
     f.V = make_float3(P->V.x, P->V.y, P->V.z); f.Wv = make_float3(P->W.x, P->W.y, P->W.z);
     f.spp = cfg.spp_per_launch; f.max_depth = cfg.max_depth; f.tmin = cfg.tmin; f.tmax = cfg.tmax;
@@ -364,6 +381,7 @@ int ptb_launch(ptb_context* ctx, const ptb_Params* P, const ptb_render_cfg* cfg_
     static const int env_pipe = getenv("PTB_PIPELINE") ? atoi(getenv("PTB_PIPELINE")) : -1;  // experiments only
     int pipeline = cfg.pipeline > 0 ? cfg.pipeline : (env_pipe > 0 ? env_pipe : PTB_PIPELINE_DEFAULT);
     if (pipeline < PTB_PIPELINE_QUEUES || pipeline > PTB_PIPELINE_CHUNK_FUSED) return fail(PTB_ERR_INVALID, "ptb_launch: unknown pipeline");
+    if (il_n > 1 && pipeline == PTB_PIPELINE_QUEUES) return fail(PTB_ERR_UNSUPPORTED, "ptb_launch: row interleave needs a chunked pipeline (2 or 3)");
 
     CU(cudaMemsetAsync(ctx->counters, 0, (size_t)(iters + 2) * 4 * sizeof(uint32_t), st));
     CU(cudaMemsetAsync(ctx->trav_stats, 0, 2 * sizeof(unsigned long long), st));

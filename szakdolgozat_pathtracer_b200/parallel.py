@@ -89,3 +89,13 @@ class PeerExchange:
             except Exception:
                 pass
         self._opened = []
+
+
+def row_band_for_rank(rank: int, world: int, height: int) -> tuple[int, int]:
+    """[row_begin, row_end) of the band rank renders under TILE partitioning (ptb_render_cfg.row_begin/row_end): the
+    alternative to the sample split for single-pass frames.  Every pixel is computed whole on one GPU with its
+    full-frame seed, so the tiled frame is bit-identical to the single-GPU one; there is no reduction, only a gather."""
+    if world < 1 or not (0 <= rank < world) or height < 0:
+        raise ValueError("bad rank/world/height")
+    k = -(-height // world)
+    return min(rank * k, height), min((rank + 1) * k, height)

@@ -406,3 +406,67 @@ def test_c2_full_frame_primary_hits(ptb, ctx, oh, assets):
     assert gst[0].segments == cseg
     assert np.array_equal(ga.view(np.uint32), ca.view(np.uint32))
     assert 0.02 < (gh < 15744).mean() < 0.2 and (gh == -1).mean() > 0.1
+
+
+def test_row_bands_tile_bit_identically(ptb, ctx, assets):
+    """Tile partitioning: three row bands rendered by separate launches == the whole frame (accum, frame, hit IDs)."""
+    from szakdolgozat_pathtracer_b200 import parallel
+    sc = load_config(ptb, assets, "c1", small=True)
+    handle, _ = ctx.accel_build(sc)
+    W, H = 150, 100
+    kw = dict(spp_per_launch=3, max_depth=5)
+    full_a, full_f, full_h, full_st = _render_gpu(ptb, ctx, handle, W, H, kw, subframes=2)
+    n = W * H
+    d_accum, d_frame, d_hits = ctx.alloc(n * 16), ctx.alloc(n * 4), ctx.alloc(n * 4)
+    try:
+        ctx.memset(d_accum, 0, n * 16); ctx.memset(d_frame, 0, n * 4); ctx.memset(d_hits, 0xFF, n * 4)
+        seg = 0
+        for r in (2, 0, 1):  # any order
+            r0, r1 = parallel.row_band_for_rank(r, 3, H)
+            for sf in range(2):
+                p = ptb.make_params(W, H, subframe_index=sf, dof=True)
+                p.accum_buffer, p.frame_buffer, p.handle = d_accum, d_frame, handle
+                ctx.launch(p, ptb.default_render_cfg(row_begin=r0, row_end=r1, pipeline=PIPELINE, aux_primary_hit=d_hits if sf == 0 else None, **kw))
+                seg += ctx.launch_stats().segments
+        a = ctx.to_host(d_accum, (H, W, 4), np.float32); f = ctx.to_host(d_frame, (H, W, 4), np.uint8); h = ctx.to_host(d_hits, (H, W), np.int32)
+        p = ptb.make_params(W, H)
+        p.accum_buffer, p.frame_buffer, p.handle = d_accum, d_frame, handle
+        with pytest.raises(ptb.PtbError):
+            ctx.launch(p, ptb.default_render_cfg(row_begin=10, row_end=H + 1, **kw))
+    finally:
+        for b in (d_accum, d_frame, d_hits):
+            ctx.free(b)
+    assert seg == sum(s.segments for s in full_st)
+    assert np.array_equal(a.view(np.uint32), full_a.view(np.uint32)) and np.array_equal(f, full_f) and np.array_equal(h, full_h)
+
+
+def test_interleaved_strips_tile_bit_identically(ptb, ctx, assets):
+    """Load-balanced tile partitioning: strips of 7 rows dealt round-robin to 3 'ranks' (ragged: 100 rows = 14 strips + 2
+    rows, so one rank's last strip is padded) == the whole frame, bit for bit."""
+    if PIPELINE == 1:
+        pytest.skip("row interleave is a feature of the chunked pipelines")
+    sc = load_config(ptb, assets, "c1", small=True)
+    handle, _ = ctx.accel_build(sc)
+    W, H = 90, 100
+    kw = dict(spp_per_launch=2, max_depth=5, pipeline=PIPELINE)
+    full_a, full_f, full_h, full_st = _render_gpu(ptb, ctx, handle, W, H, dict(spp_per_launch=2, max_depth=5))
+    n = W * H
+    d_accum, d_frame, d_hits = ctx.alloc(n * 16), ctx.alloc(n * 4), ctx.alloc(n * 4)
+    try:
+        ctx.memset(d_accum, 0, n * 16); ctx.memset(d_frame, 0, n * 4); ctx.memset(d_hits, 0xFF, n * 4)
+        seg = 0
+        for r in range(3):
+            p = ptb.make_params(W, H, subframe_index=0, dof=True)
+            p.accum_buffer, p.frame_buffer, p.handle = d_accum, d_frame, handle
+            ctx.launch(p, ptb.default_render_cfg(row_interleave_count=3, row_interleave_index=r, row_interleave_height=7, aux_primary_hit=d_hits, **kw))
+            seg += ctx.launch_stats().segments
+        a = ctx.to_host(d_accum, (H, W, 4), np.float32); f = ctx.to_host(d_frame, (H, W, 4), np.uint8); h = ctx.to_host(d_hits, (H, W), np.int32)
+        # more ranks than strips: a no-op, not an error
+        p = ptb.make_params(W, H)
+        p.accum_buffer, p.frame_buffer, p.handle = d_accum, d_frame, handle
+        ctx.launch(p, ptb.default_render_cfg(row_interleave_count=64, row_interleave_index=63, row_interleave_height=50, **kw))
+    finally:
+        for b in (d_accum, d_frame, d_hits):
+            ctx.free(b)
+    assert seg == full_st[0].segments
+    assert np.array_equal(a.view(np.uint32), full_a.view(np.uint32)) and np.array_equal(f, full_f) and np.array_equal(h, full_h)

@@ -62,6 +62,8 @@ def test_subframe_schedule():
     for world in (1, 2, 3, 8):
         blocks = [parallel.subframe_block_for_rank(r, world, 17, first=4) for r in range(world)]
         assert sum(blocks, []) == list(range(4, 21))
+        bands = [parallel.row_band_for_rank(r, world, 1081) for r in range(world)]
+        assert bands[0][0] == 0 and bands[-1][1] == 1081 and all(bands[i][1] == bands[i + 1][0] for i in range(world - 1))
         slices = [parallel.pixel_slice_for_rank(r, world, 1920 * 1080 + 5) for r in range(world)]
         assert slices[0][0] == 0 and sum(c for _, c in slices) == 1920 * 1080 + 5
         assert all(slices[i][0] + slices[i][1] == slices[i + 1][0] for i in range(world - 1))
