@@ -112,6 +112,9 @@ def cpu_reference_sample(oh, ptb, osc, rows, threads=0):
     """Times the reference's CPU implementation on a band of the C2 frame.
     oracle/_ref (the reference's optixSphere.cu compiled for the host) when present, else the oracle port."""
     from scenes import CAMERAS
+    if threads <= 0:
+        # all host cores this process may use; explicit because torchrun exports OMP_NUM_THREADS=1 to its workers
+        threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     kind = "reference" if oh.have_ref() else "port"
     which = "ref" if kind == "reference" else "oracle"
     p = ptb.make_params(W, H, subframe_index=0, dof=True, **CAMERAS[CAMERA])
