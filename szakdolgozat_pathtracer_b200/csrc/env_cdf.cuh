@@ -54,9 +54,9 @@ __global__ void __launch_bounds__(256) k_env_row_cdf(const float4* __restrict__ 
     if (threadIdx.x == 0) row_weight[row] = carry;
 }
 
-// normalise every row, build the marginal CDF (single block; h <= a few thousand)
-__global__ void __launch_bounds__(256) k_env_marginal(int w, int h, float* __restrict__ conditional, const float* __restrict__ row_weight,
-                                                      float* __restrict__ marginal, float* __restrict__ total_out) {
+// marginal CDF over the rows (single block; h is a few thousand at most)
+__global__ void __launch_bounds__(256) k_env_marginal(int h, const float* __restrict__ row_weight, float* __restrict__ marginal,
+                                                      float* __restrict__ total_out) {
     __shared__ float total;
     if (threadIdx.x == 0) {
         float acc = 0.0f;
@@ -68,11 +68,14 @@ __global__ void __launch_bounds__(256) k_env_marginal(int w, int h, float* __res
     __syncthreads();
     const float inv_total = total > 0.0f ? 1.0f / total : 0.0f;
     for (int r = threadIdx.x; r <= h; r += blockDim.x) marginal[r] = r == h ? 1.0f : marginal[r] * inv_total;
-    for (size_t k = threadIdx.x; k < (size_t)h * (w + 1); k += blockDim.x) {
-        const int r = (int)(k / (size_t)(w + 1)), i = (int)(k % (size_t)(w + 1));
-        const float rw = row_weight[r];
-        conditional[k] = i == w ? 1.0f : (rw > 0.0f ? conditional[k] / rw : (float)i / (float)w);
-    }
+}
+
+// normalise the conditional CDF of every row to [0,1] (one block per row)
+__global__ void __launch_bounds__(256) k_env_normalize_rows(int w, float* __restrict__ conditional, const float* __restrict__ row_weight) {
+    const int r = blockIdx.x;
+    const float rw = row_weight[r];
+    float* row = conditional + (size_t)r * (w + 1);
+    for (int i = threadIdx.x; i <= w; i += blockDim.x) row[i] = i == w ? 1.0f : (rw > 0.0f ? row[i] / rw : (float)i / (float)w);
 }
 
 // largest index k in [0, n-1] with cdf[k] <= x  (cdf has n + 1 entries, cdf[0] = 0, cdf[n] = 1)

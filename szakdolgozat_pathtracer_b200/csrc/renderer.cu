@@ -275,7 +275,8 @@ int ptb_accel_build(ptb_context* ctx, ptb_scene* scene, const ptb_build_cfg* cfg
         if (ce == cudaSuccess) ce = cudaMalloc((void**)&d->cdf_row_weight, (size_t)(eh + 1) * sizeof(float));
         if (ce == cudaSuccess) {
             k_env_row_cdf<<<eh, 256, 0, st>>>(d->env, ew, eh, (float)(0.01 * mean) + 1e-12f, d->cdf_conditional, d->cdf_row_weight);
-            k_env_marginal<<<1, 256, 0, st>>>(ew, eh, d->cdf_conditional, d->cdf_row_weight, d->cdf_marginal, d->cdf_row_weight + eh);
+            k_env_marginal<<<1, 256, 0, st>>>(eh, d->cdf_row_weight, d->cdf_marginal, d->cdf_row_weight + eh);
+            k_env_normalize_rows<<<eh, 256, 0, st>>>(ew, d->cdf_conditional, d->cdf_row_weight);
             ce = cudaMemcpyAsync(&d->cdf_total, d->cdf_row_weight + eh, sizeof(float), cudaMemcpyDeviceToHost, st);
             if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
         }
