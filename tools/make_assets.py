@@ -249,6 +249,19 @@ def ensure(config: str, small: bool = False) -> dict:
         out["files"] = [str(d / "model.obj")]
     if stamp.exists():
         return out
+    # concurrent callers (two gloo ranks, pytest-xdist workers) must not read half-written files:
+    # one generates under an exclusive lock, the others wait and then find the stamp
+    import fcntl
+    GEN.mkdir(parents=True, exist_ok=True)
+    with open(GEN / ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not stamp.exists():
+            _generate(config, d, c, es, ew, eh, small)
+            stamp.write_text("ok\n")
+    return out
+
+
+def _generate(config, d, c, es, ew, eh, small):
     d.mkdir(parents=True, exist_ok=True)
     write_exr(d / f"env{es}.exr", make_env(es, ew, eh), compression="zip")
     tex_n = 128 if small else None
@@ -276,8 +289,6 @@ def ensure(config: str, small: bool = False) -> dict:
     elif config == "c5":
         write_blob_obj(d / "model.obj", 3 if small else 7, 51, radius=1.2, center=(0, 1.2, 0), with_uv=True)
         write_png(d / "model_albedo.png", make_albedo(52, tex_n or 2048))
-    stamp.write_text("ok\n")
-    return out
 
 
 if __name__ == "__main__":
