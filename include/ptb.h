@@ -39,6 +39,7 @@ extern "C" {
 #define PTB_PIPELINE_QUEUES 1
 #define PTB_PIPELINE_CHUNK_STAGES 2
 #define PTB_PIPELINE_CHUNK_FUSED 3
+#define PTB_PIPELINE_POOL_FUSED 4
 #define PTB_PIPELINE_DEFAULT PTB_PIPELINE_CHUNK_FUSED
 
 /* ---- data layouts shared with the reference (optixSphere.h) ---------------
@@ -160,6 +161,7 @@ typedef struct ptb_build_cfg {
     int32_t sah_refine;    /* 1: binned-SAH refinement of the LBVH (default); 0: plain LBVH */
     int32_t sah_bins;      /* default 16 */
     int32_t treelet_size;  /* primitives per refinement treelet, default 512 */
+    int32_t morton_bits;   /* 30 (default: 10 bits per axis) or 63 (21 bits per axis) */
 } ptb_build_cfg;
 
 typedef struct ptb_build_stats {

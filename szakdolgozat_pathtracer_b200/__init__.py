@@ -18,7 +18,7 @@ import numpy as np
 
 _PKG = Path(__file__).resolve().parent
 _ROOT = _PKG.parent
-LIB_PATH = _PKG / "libptb.so"
+LIB_PATH = Path(os.environ["PTB_LIB"]) if os.environ.get("PTB_LIB") else _PKG / "libptb.so"  # PTB_LIB: A/B builds of the same library (experiments)
 
 PTB_OK, PTB_ERR_INVALID, PTB_ERR_IO, PTB_ERR_CUDA, PTB_ERR_UNSUPPORTED, PTB_ERR_NO_DEVICE = range(6)
 
@@ -89,7 +89,8 @@ class LaunchStats(C.Structure):
 
 
 class BuildCfg(C.Structure):
-    _fields_ = [("max_leaf_size", C.c_int32), ("sah_refine", C.c_int32), ("sah_bins", C.c_int32), ("treelet_size", C.c_int32)]
+    _fields_ = [("max_leaf_size", C.c_int32), ("sah_refine", C.c_int32), ("sah_bins", C.c_int32), ("treelet_size", C.c_int32),
+                ("morton_bits", C.c_int32)]
 
 
 class BuildStats(C.Structure):

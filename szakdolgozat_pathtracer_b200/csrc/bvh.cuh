@@ -25,7 +25,7 @@
 
 namespace ptb {
 
-#define PTB_BVH_STACK 64
+#define PTB_BVH_STACK 128
 
 struct HitRec { float t, b1, b2; int prim; };
 

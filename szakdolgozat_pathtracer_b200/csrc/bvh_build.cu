@@ -6,8 +6,8 @@
 // no index buffer); the algorithm is ours:
 //   1. k_tri_bounds      per-triangle AABB + centroid, scene bounds by warp
 //                        shuffle reduction + one atomic per warp
-//   2. k_morton          30-bit Morton code of the centroid
-//   3. radix sort        own 4 x 8-bit LSD passes (histogram / scan / stable
+//   2. k_morton          63-bit (or 30-bit) Morton code of the centroid
+//   3. radix sort        own 8 (4) x 8-bit LSD passes (histogram / scan / stable
 //                        scatter with __match_any_sync ranking)
 //   4. k_hierarchy       Karras 2012 radix tree, one thread per internal node
 //   5. k_refit           bottom-up AABBs with one atomic arrival flag per node
@@ -23,6 +23,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -83,20 +84,54 @@ __device__ __forceinline__ uint32_t expand_bits10(uint32_t v) {
     return v;
 }
 
+__device__ __forceinline__ uint64_t expand_bits21(uint64_t v) {
+    v &= 0x1fffffull;
+    v = (v | (v << 32)) & 0x001f00000000ffffull;
+    v = (v | (v << 16)) & 0x001f0000ff0000ffull;
+    v = (v | (v << 8)) & 0x100f00f00f00f00full;
+    v = (v | (v << 4)) & 0x10c30c30c30c30c3ull;
+    v = (v | (v << 2)) & 0x1249249249249249ull;
+    return v;
+}
+
+// Morton code of the centroid inside the CENTROID bounds, each axis normalised by its own extent.  bits = 10: the classic
+// 30-bit code (default); bits = 21: a 63-bit code for scenes whose meshes need more than 1024 cells per axis (ties between
+// identical keys fall back to an index split, Karras 2012 section 4).  On the BASELINE scenes both give the same trees.
 __global__ void k_morton(const float4* __restrict__ tri_lo, const float4* __restrict__ tri_hi, uint32_t n,
-                         const float* __restrict__ scene_bounds, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+                         const float* __restrict__ scene_bounds, int bits, int cubic, float huge_frac, uint64_t* __restrict__ keys,
+                         uint32_t* __restrict__ vals) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float4 lo = tri_lo[i], hi = tri_hi[i];
     const float c[3] = {0.5f * (lo.x + hi.x), 0.5f * (lo.y + hi.y), 0.5f * (lo.z + hi.z)};
+    const float cells = (float)(1u << bits);
+    // cubic = 1: one cell size for all three axes (the largest centroid extent).  Measured on C2/C4/C5 (profiles/r1_bvh_probe.md):
+    // per-axis normalisation gives the better trees for the reference's slab-shaped scenes (floor 400 x 400, meshes ~2 high),
+    // so it is the default; the cubic grid is kept for experiments (PTB_MORTON_CUBIC=1).
+    const float ext_max = fmaxf(scene_bounds[9] - scene_bounds[6], fmaxf(scene_bounds[10] - scene_bounds[7], scene_bounds[11] - scene_bounds[8]));
     uint32_t q[3];
     for (int k = 0; k < 3; ++k) {
-        const float clo = scene_bounds[6 + k], ext = scene_bounds[9 + k] - clo;
+        const float clo = scene_bounds[6 + k];
+        const float ext = cubic ? ext_max : scene_bounds[9 + k] - clo;
         float u = ext > 0.0f ? (c[k] - clo) / ext : 0.0f;
-        u = fminf(fmaxf(u * 1024.0f, 0.0f), 1023.0f);
+        u = fminf(fmaxf(u * cells, 0.0f), cells - 1.0f);
         q[k] = (uint32_t)u;
     }
-    keys[i] = (expand_bits10(q[0]) << 2) | (expand_bits10(q[1]) << 1) | expand_bits10(q[2]);
+    uint64_t key;
+    if (bits <= 10) key = (uint64_t)((expand_bits10(q[0]) << 2) | (expand_bits10(q[1]) << 1) | expand_bits10(q[2]));
+    else key = (expand_bits21(q[0]) << 2) | (expand_bits21(q[1]) << 1) | expand_bits21(q[2]);
+    // Huge primitives go to the root.  A triangle whose box is a sizeable fraction of the whole scene (the reference's
+    // 400 x 400 floor quad, optixSphere.cpp:598-646) would otherwise sit deep inside the Morton order and inflate the
+    // boxes of all its ancestors, so that every ray walks down to it.  Bit 63 separates the two groups: it is the first
+    // split of the radix tree, the huge ones become one small subtree next to the root (usually a single leaf) and the
+    // rest of the scene gets a tree with tight boxes.  (C2: 7.9 -> see profiles/ nodes per segment.)
+    if (huge_frac > 0.0f) {
+        const float sx = scene_bounds[3] - scene_bounds[0], sy = scene_bounds[4] - scene_bounds[1], sz = scene_bounds[5] - scene_bounds[2];
+        const float tx = hi.x - lo.x, ty = hi.y - lo.y, tz = hi.z - lo.z;
+        const float scene_area = sx * sy + sy * sz + sz * sx, tri_area = tx * ty + ty * tz + tz * tx;
+        if (!(tri_area >= huge_frac * scene_area)) key |= 1ull << 63;
+    }
+    keys[i] = key;
     vals[i] = i;
 }
 
@@ -105,14 +140,14 @@ __global__ void k_morton(const float4* __restrict__ tri_lo, const float4* __rest
 // chunk uses __match_any_sync, so the scatter is stable.
 #define SORT_TILE 2048u
 
-__global__ void k_sort_hist(const uint32_t* __restrict__ keys, uint32_t n, int shift, uint32_t* __restrict__ hist,
+__global__ void k_sort_hist(const uint64_t* __restrict__ keys, uint32_t n, int shift, uint32_t* __restrict__ hist,
                             uint32_t n_tiles) {
     __shared__ uint32_t h[256];
     const uint32_t tile = blockIdx.x, lane = threadIdx.x;
     for (uint32_t b = lane; b < 256; b += 32) h[b] = 0;
     __syncwarp();
     const uint32_t begin = tile * SORT_TILE, end = min(begin + SORT_TILE, n);
-    for (uint32_t i = begin + lane; i < end; i += 32) atomicAdd(&h[(keys[i] >> shift) & 255u], 1u);
+    for (uint32_t i = begin + lane; i < end; i += 32) atomicAdd(&h[(uint32_t)(keys[i] >> shift) & 255u], 1u);
     __syncwarp();
     for (uint32_t b = lane; b < 256; b += 32) hist[(size_t)b * n_tiles + tile] = h[b];  // bin-major
 }
@@ -146,9 +181,9 @@ __global__ void k_sort_scan(uint32_t* __restrict__ hist, uint32_t total) {
     }
 }
 
-__global__ void k_sort_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t n,
+__global__ void k_sort_scatter(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t n,
                                int shift, const uint32_t* __restrict__ hist, uint32_t n_tiles,
-                               uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
+                               uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
     __shared__ uint32_t offs[256];
     const uint32_t tile = blockIdx.x, lane = threadIdx.x;
     for (uint32_t b = lane; b < 256; b += 32) offs[b] = hist[(size_t)b * n_tiles + tile];
@@ -157,8 +192,9 @@ __global__ void k_sort_scatter(const uint32_t* __restrict__ keys_in, const uint3
     for (uint32_t base = begin; base < end; base += 32) {
         const uint32_t i = base + lane;
         const bool active = i < end;
-        const uint32_t key = active ? keys_in[i] : 0u, val = active ? vals_in[i] : 0u;
-        const uint32_t digit = active ? ((key >> shift) & 255u) : 256u;  // 256 = inactive group
+        const uint64_t key = active ? keys_in[i] : 0ull;
+        const uint32_t val = active ? vals_in[i] : 0u;
+        const uint32_t digit = active ? ((uint32_t)(key >> shift) & 255u) : 256u;  // 256 = inactive group
         const unsigned peers = __match_any_sync(0xffffffffu, digit);
         const uint32_t rank = (uint32_t)__popc(peers & ((1u << lane) - 1u));
         uint32_t dst = 0;
@@ -171,15 +207,15 @@ __global__ void k_sort_scatter(const uint32_t* __restrict__ keys_in, const uint3
 }
 
 // ---- Karras 2012 ----------------------------------------------------------------------
-__device__ __forceinline__ int delta(const uint32_t* __restrict__ keys, int n, int i, int j) {
+__device__ __forceinline__ int delta(const uint64_t* __restrict__ keys, int n, int i, int j) {
     if (j < 0 || j >= n) return -1;
-    const uint32_t a = keys[i], b = keys[j];
-    if (a == b) return 32 + __clz((uint32_t)i ^ (uint32_t)j);
-    return __clz(a ^ b);
+    const uint64_t a = keys[i], b = keys[j];
+    if (a == b) return 64 + __clz((uint32_t)i ^ (uint32_t)j);
+    return __clzll((long long)(a ^ b));
 }
 
 // child encoding in the build tree: >= 0 internal node index, < 0 leaf ~index
-__global__ void k_hierarchy(const uint32_t* __restrict__ keys, int n, int2* __restrict__ children,
+__global__ void k_hierarchy(const uint64_t* __restrict__ keys, int n, int2* __restrict__ children,
                             int2* __restrict__ ranges, int* __restrict__ node_parent, int* __restrict__ leaf_parent) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
@@ -368,7 +404,7 @@ bool build_bvh(const float4* d_verts, uint32_t n, const ptb_build_cfg& cfg, cuda
 
     Scratch sc;
     float4 *tri_lo, *tri_hi, *leaf_lo, *leaf_hi, *node_lo, *node_hi;
-    float* scene_bounds; uint32_t *keys[2], *vals[2], *hist; int2 *children, *ranges; int *node_parent, *leaf_parent;
+    float* scene_bounds; uint64_t* keys[2]; uint32_t *vals[2], *hist; int2 *children, *ranges; int *node_parent, *leaf_parent;
     unsigned int *flags, *counters; float* sah; unsigned char* collapse; int* treelets;
     const uint32_t n_tiles = (n + SORT_TILE - 1) / SORT_TILE;
     if (!sc.alloc(&tri_lo, n, err) || !sc.alloc(&tri_hi, n, err) || !sc.alloc(&leaf_lo, n, err) || !sc.alloc(&leaf_hi, n, err) ||
@@ -387,10 +423,18 @@ bool build_bvh(const float4* d_verts, uint32_t n, const ptb_build_cfg& cfg, cuda
 
     const uint32_t B = 256, G = (n + B - 1) / B;
     k_tri_bounds<<<G, B, 0, stream>>>(d_verts, n, tri_lo, tri_hi, scene_bounds);
-    k_morton<<<G, B, 0, stream>>>(tri_lo, tri_hi, n, scene_bounds, keys[0], vals[0]);
+    const int morton_bits = cfg.morton_bits == 63 ? 21 : 10;
+    static const int env_cubic = getenv("PTB_MORTON_CUBIC") ? atoi(getenv("PTB_MORTON_CUBIC")) : 0;  // experiments only
+    static const float env_huge = getenv("PTB_HUGE_FRAC") ? (float)atof(getenv("PTB_HUGE_FRAC")) : -1.0f;  // experiments only
+    const float huge_frac = env_huge >= 0.0f ? env_huge : 0.0625f;
+    const bool huge_bit = huge_frac > 0.0f;
+    k_morton<<<G, B, 0, stream>>>(tri_lo, tri_hi, n, scene_bounds, morton_bits, env_cubic, huge_frac, keys[0], vals[0]);
     int cur = 0;
-    for (int pass = 0; pass < 4; ++pass) {
-        const int shift = pass * 8;
+    // 8-bit LSD passes over the bits in use: 30-bit codes need 4, 63-bit codes 8; the huge-primitive flag (bit 63) adds
+    // one pass over the top byte to the 30-bit case
+    const int n_pass = morton_bits == 10 ? (huge_bit ? 5 : 4) : 8;
+    for (int pass = 0; pass < n_pass; ++pass) {
+        const int shift = (morton_bits == 10 && pass == 4) ? 56 : pass * 8;
         k_sort_hist<<<n_tiles, 32, 0, stream>>>(keys[cur], n, shift, hist, n_tiles);
         k_sort_scan<<<1, 1024, 0, stream>>>(hist, 256u * n_tiles);
         k_sort_scatter<<<n_tiles, 32, 0, stream>>>(keys[cur], vals[cur], n, shift, hist, n_tiles, keys[cur ^ 1], vals[cur ^ 1]);

@@ -7,7 +7,7 @@
 
 #include "../../include/ptb.h"
 
-#define PTB_BVH_MAX_DEPTH 64  // traversal stack entries (bvh.cuh: PTB_BVH_STACK)
+#define PTB_BVH_MAX_DEPTH 128 // traversal stack entries (bvh.cuh: PTB_BVH_STACK)
 
 namespace ptb {
 

@@ -20,7 +20,11 @@ namespace ptb {
 #define PTB_SAH_BINS 16
 #define PTB_REFINE_WARPS 2
 
-struct TreeletTask { unsigned short begin, end; int slot; };
+struct TreeletTask { unsigned short begin, end; int slot; int depth; };
+
+// SAH splits can be very uneven (1 : n-1); below this treelet-local depth the rebuild switches to median splits, so a
+// treelet adds at most PTB_TREELET_SAH_DEPTH + log2(PTB_TREELET_MAX) levels and the tree always fits the traversal stack.
+#define PTB_TREELET_SAH_DEPTH 24
 
 struct TreeletShared {
     float lo[3][PTB_TREELET_MAX], hi[3][PTB_TREELET_MAX];
@@ -82,12 +86,12 @@ k_refine_treelets(const int* __restrict__ list, const unsigned int* __restrict__
         for (int s = a + 1 + (int)lane; s <= a + k - 2; s += 32) { collapse[s] = 1; ranges[s] = make_int2(0, -1); }
         int next_free = a + 1;
         int sp = 0;
-        if (lane == 0) { sh.stack[0].begin = 0; sh.stack[0].end = (unsigned short)k; sh.stack[0].slot = root; }
+        if (lane == 0) { sh.stack[0].begin = 0; sh.stack[0].end = (unsigned short)k; sh.stack[0].slot = root; sh.stack[0].depth = 0; }
         sp = 1;
         __syncwarp();
         while (sp > 0) {
             --sp;
-            const int begin = sh.stack[sp].begin, end = sh.stack[sp].end, slot = sh.stack[sp].slot;
+            const int begin = sh.stack[sp].begin, end = sh.stack[sp].end, slot = sh.stack[sp].slot, depth = sh.stack[sp].depth;
             const int n = end - begin;
             __syncwarp();
             // node box and centroid box
@@ -163,6 +167,7 @@ k_refine_treelets(const int* __restrict__ list, const unsigned int* __restrict__
                 const unsigned int onl = __shfl_xor_sync(0xffffffffu, best_nl, off);
                 if (ocand >= 0 && (best_cand < 0 || oc < best_cost || (oc == best_cost && ocand < best_cand))) { best_cost = oc; best_cand = ocand; best_nl = onl; }
             }
+            if (depth >= PTB_TREELET_SAH_DEPTH) best_cand = -1;  // median splits from here on (bounded depth)
             const float leaf_cost = node_area * (float)n;
             const float split_cost = best_cand >= 0 ? node_area + best_cost : 3.4e38f;
             if (n <= max_leaf && slot != 0 && (best_cand < 0 || leaf_cost <= split_cost)) {
@@ -217,6 +222,7 @@ k_refine_treelets(const int* __restrict__ list, const unsigned int* __restrict__
                     if (lane == 0) {
                         node_parent[cslot] = slot;
                         sh.stack[sp].begin = (unsigned short)cb[c]; sh.stack[sp].end = (unsigned short)ce[c]; sh.stack[sp].slot = cslot;
+                        sh.stack[sp].depth = depth + 1;
                     }
                     sp++;
                 }

@@ -28,30 +28,52 @@ namespace ptb {
 #ifndef PTB_CHUNK_THREADS
 #define PTB_CHUNK_THREADS 256    // 8 slots per thread in the compaction step (measured on C2: 256 > 512 > 128)
 #endif
-#define PTB_CHUNK (PTB_CHUNK_THREADS * 8)  // slots per block
+#ifndef PTB_CHUNK_SPT
+#define PTB_CHUNK_SPT 8          // slots per thread: 8 or 16 (status bytes are read as 64-bit words)
+#endif
+#define PTB_CHUNK (PTB_CHUNK_THREADS * PTB_CHUNK_SPT)  // slots per block
 
-enum SlotStatus : unsigned char { ST_DONE = 0, ST_TRACE = 1, ST_HIT = 2, ST_MISS = 3 };
+// ST_BUSY: the slot's ray is parked half-traversed in a lane of the fused kernel (see chunk_stage_trace_suspend)
+enum SlotStatus : unsigned char { ST_DONE = 0, ST_TRACE = 1, ST_HIT = 2, ST_MISS = 3, ST_BUSY = 4 };
 
 struct ChunkShared {
     unsigned short list[PTB_CHUNK];  // slot offsets inside the chunk, ascending
     unsigned int warp_sums[PTB_CHUNK_THREADS / 32];
+    unsigned int warp_sums_b[PTB_CHUNK_THREADS / 32];
     unsigned int n;                  // list length
     unsigned int next;               // dynamic fetch cursor of the trace stage
     unsigned int count[4];           // per-block totals: segments, hits, misses, -
 };
 
 // Compacts the offsets of the chunk's slots whose status == want into sh.list (ascending).  Block-uniform result.
+// bit k of the result is set when status byte k of this thread's PTB_CHUNK_SPT slots equals want (slots beyond n_slots
+// read as ST_DONE; `want` is never ST_DONE)
+PTB_DEV unsigned int chunk_status_words(const unsigned char* __restrict__ status, uint32_t first, uint32_t n_slots, unsigned long long* words) {
+#pragma unroll
+    for (int w = 0; w < PTB_CHUNK_SPT / 8; ++w) {
+        const uint32_t f0 = first + 8u * w;
+        unsigned long long bytes = 0ull;
+        if (f0 + 8u <= n_slots) bytes = *reinterpret_cast<const unsigned long long*>(status + f0);
+        else if (f0 < n_slots) for (uint32_t k = 0; f0 + k < n_slots; ++k) bytes |= (unsigned long long)status[f0 + k] << (8u * k);
+        words[w] = bytes;
+    }
+    return 0u;
+}
+PTB_DEV unsigned int chunk_match(const unsigned long long* words, unsigned char want) {
+    unsigned int m = 0;
+#pragma unroll
+    for (int w = 0; w < PTB_CHUNK_SPT / 8; ++w)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) m |= (((unsigned int)(words[w] >> (8 * k)) & 0xffu) == (unsigned int)want ? 1u : 0u) << (8 * w + k);
+    return m;
+}
+
 PTB_DEV unsigned int chunk_build_list(ChunkShared& sh, const unsigned char* __restrict__ status, uint32_t base,
                                       uint32_t n_slots, unsigned char want) {
     const unsigned int tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint32_t first = base + tid * 8u;
-    unsigned long long bytes = 0ull;
-    if (first + 8u <= n_slots) bytes = *reinterpret_cast<const unsigned long long*>(status + first);
-    else for (uint32_t k = 0; k < 8u; ++k) if (first + k < n_slots) bytes |= (unsigned long long)status[first + k] << (8u * k);
-    unsigned int match = 0;  // bit k set when byte k == want
-#pragma unroll
-    for (int k = 0; k < 8; ++k) match |= (((bytes >> (8 * k)) & 0xffull) == (unsigned long long)want ? 1u : 0u) << k;
-    if (first + 8u > n_slots) for (uint32_t k = 0; k < 8u; ++k) if (first + k >= n_slots) match &= ~(1u << k);
+    unsigned long long words[PTB_CHUNK_SPT / 8];
+    chunk_status_words(status, base + tid * (unsigned int)PTB_CHUNK_SPT, n_slots, words);
+    unsigned int match = chunk_match(words, want);
     const unsigned int mine = (unsigned int)__popc(match);
     unsigned int incl = mine;
 #pragma unroll
@@ -63,10 +85,112 @@ PTB_DEV unsigned int chunk_build_list(ChunkShared& sh, const unsigned char* __re
     for (unsigned int w = 0; w < PTB_CHUNK_THREADS / 32; ++w) { const unsigned int v = sh.warp_sums[w]; if (w < warp) warp_off += v; total += v; }
     unsigned int pos = warp_off + incl - mine;
     unsigned int m = match;
-    while (m) { const int k = __ffs(m) - 1; m &= m - 1u; sh.list[pos++] = (unsigned short)(tid * 8u + (unsigned int)k); }
+    while (m) { const int k = __ffs(m) - 1; m &= m - 1u; sh.list[pos++] = (unsigned short)(tid * (unsigned int)PTB_CHUNK_SPT + (unsigned int)k); }
     if (tid == 0) { sh.n = total; sh.next = 0; }
     __syncthreads();
     return total;
+}
+
+// One pass over the chunk's status bytes builds TWO lists: slots in state want_a ascending from the front of sh.list,
+// slots in state want_b ascending at its back (sh.list[PTB_CHUNK - nb ..)).  Block-uniform result.
+PTB_DEV void chunk_build_two(ChunkShared& sh, const unsigned char* __restrict__ status, uint32_t base, uint32_t n_slots,
+                             unsigned char want_a, unsigned char want_b, unsigned int* na, unsigned int* nb) {
+    const unsigned int tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    unsigned long long words[PTB_CHUNK_SPT / 8];
+    chunk_status_words(status, base + tid * (unsigned int)PTB_CHUNK_SPT, n_slots, words);
+    unsigned int ma = chunk_match(words, want_a), mb = chunk_match(words, want_b);
+    // one packed inclusive warp scan for both counts (each <= 512 per warp: 16 bits are plenty)
+    const unsigned int mine = (unsigned int)__popc(ma) | ((unsigned int)__popc(mb) << 16);
+    unsigned int incl = mine;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) { const unsigned int y = __shfl_up_sync(0xffffffffu, incl, off); if ((int)lane >= off) incl += y; }
+    if (lane == 31u) { sh.warp_sums[warp] = incl & 0xffffu; sh.warp_sums_b[warp] = incl >> 16; }
+    __syncthreads();
+    unsigned int off_a = 0, tot_a = 0, off_b = 0, tot_b = 0;
+#pragma unroll
+    for (unsigned int w = 0; w < PTB_CHUNK_THREADS / 32; ++w) {
+        const unsigned int va = sh.warp_sums[w], vb = sh.warp_sums_b[w];
+        if (w < warp) { off_a += va; off_b += vb; }
+        tot_a += va; tot_b += vb;
+    }
+    unsigned int pa = off_a + (incl & 0xffffu) - (mine & 0xffffu);
+    unsigned int pb = (unsigned int)PTB_CHUNK - tot_b + off_b + (incl >> 16) - (mine >> 16);
+    while (ma) { const int k = __ffs(ma) - 1; ma &= ma - 1u; sh.list[pa++] = (unsigned short)(tid * (unsigned int)PTB_CHUNK_SPT + (unsigned int)k); }
+    while (mb) { const int k = __ffs(mb) - 1; mb &= mb - 1u; sh.list[pb++] = (unsigned short)(tid * (unsigned int)PTB_CHUNK_SPT + (unsigned int)k); }
+    if (tid == 0) { sh.n = tot_a; sh.next = 0; }
+    __syncthreads();
+    *na = tot_a; *nb = tot_b;
+}
+
+// A ray parked between two trace stages of the fused kernel: everything else is recomputed from the slot's ray on resume.
+struct ParkedRay { HitRec best; int node, sp; uint32_t slot; bool active, primary; };
+
+// Trace stage of the fused kernel.  Like chunk_stage_trace, but a warp does not wait for its longest rays: once the
+// chunk's list is exhausted and fewer than PARK_BELOW of its lanes are still traversing, the unfinished rays are parked
+// (status ST_BUSY, traversal position kept in `parked` and in the lane's stack) and resumed at the next trace stage.
+// Which iteration finishes a ray has no influence on its result, so the output stays bit-identical.
+// allow_park is false in the tail of a chunk (short lists), where waiting is cheaper than extra iterations.
+template <bool COUNT, int QUANTUM, int PARK_BELOW>
+PTB_DEV void chunk_stage_trace_park(ChunkShared& sh, const SceneView& s, const FrameView& f, const PathView& p,
+                                    unsigned char* __restrict__ status, uint32_t base, unsigned int n, bool first_iteration,
+                                    bool allow_park, ParkedRay& parked, int* stack, TravCounters& tc) {
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    Trav t;
+    t.node = PTB_TRAV_SENTINEL; t.sp = 0; t.best.prim = -1; t.best.t = 0.0f; t.best.b1 = 0.0f; t.best.b2 = 0.0f;
+    uint32_t slot = 0;
+    bool have = false, primary = false, exhausted = n == 0u;
+    unsigned int hits = 0;
+    if (parked.active) {
+        slot = parked.slot;
+        const float4 o4 = p.ray_o[slot], d4 = p.ray_d[slot];
+        trav_begin(t, stack, mk3(o4), mk3(d4), f.tmin, f.tmax);  // stack[0] is the sentinel already; the rest is kept
+        t.best = parked.best; t.node = parked.node; t.sp = parked.sp;
+        primary = parked.primary;
+        have = true;
+        parked.active = false;
+    }
+    for (;;) {
+        __syncwarp();
+        if (!exhausted) {
+            const unsigned need = __ballot_sync(0xffffffffu, !have);
+            if (need) {
+                const int leader = __ffs(need) - 1;
+                const unsigned int cnt = (unsigned int)__popc(need);
+                unsigned int b0 = 0;
+                if ((int)lane == leader) b0 = atomicAdd(&sh.next, cnt);
+                b0 = __shfl_sync(0xffffffffu, b0, leader);
+                const unsigned int idx = b0 + (unsigned int)__popc(need & lt_mask);
+                if (!have && idx < n) {
+                    slot = base + sh.list[idx];
+                    const float4 o4 = p.ray_o[slot], d4 = p.ray_d[slot];
+                    trav_begin(t, stack, mk3(o4), mk3(d4), f.tmin, f.tmax);
+                    have = true; primary = first_iteration;
+                }
+                if (b0 + cnt >= n) exhausted = true;  // warp-uniform
+            }
+        }
+        const unsigned busy = __ballot_sync(0xffffffffu, have);
+        if (!busy) break;
+        if (exhausted && allow_park && __popc(busy) < PARK_BELOW) {
+            if (have) {
+                parked.best = t.best; parked.node = t.node; parked.sp = t.sp; parked.slot = slot; parked.primary = primary;
+                parked.active = true;
+                status[slot] = ST_BUSY;
+            }
+            break;
+        }
+        if (have && trav_run<COUNT>(t, stack, s.nodes, s.tris, QUANTUM, &tc)) {
+            have = false;
+            p.hit[slot] = make_float4(t.best.t, t.best.b1, t.best.b2, __int_as_float(t.best.prim));
+            const bool is_hit = t.best.prim >= 0;
+            status[slot] = is_hit ? ST_HIT : ST_MISS;
+            hits += is_hit ? 1u : 0u;
+            if (primary && f.aux_primary && slot < f.n_pixels) f.aux_primary[(size_t)image_row(f, slot / f.W) * f.W + slot % f.W] = t.best.prim;
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) hits += __shfl_xor_sync(0xffffffffu, hits, off);
+    if (lane == 0u && hits) atomicAdd(&sh.count[1], hits);
 }
 
 // ---- stage bodies over one chunk ---------------------------------------------------------------------------
@@ -117,9 +241,9 @@ PTB_DEV void chunk_stage_trace(ChunkShared& sh, const SceneView& s, const FrameV
 }
 
 PTB_DEV void chunk_stage_shade(ChunkShared& sh, const SceneView& s, const FrameView& f, const PathView& p,
-                               unsigned char* __restrict__ status, uint32_t base, unsigned int n) {
+                               unsigned char* __restrict__ status, uint32_t base, unsigned int n, unsigned int list_off = 0) {
     for (unsigned int i = threadIdx.x; i < n; i += PTB_CHUNK_THREADS) {
-        const uint32_t slot = base + sh.list[i];
+        const uint32_t slot = base + sh.list[list_off + i];
         const float4 o4 = p.ray_o[slot], d4 = p.ray_d[slot], h4 = p.hit[slot], as = p.atten_seed[slot];
         const uint4 mi = p.misc[slot];
         Bounce b;
@@ -131,9 +255,9 @@ PTB_DEV void chunk_stage_shade(ChunkShared& sh, const SceneView& s, const FrameV
 }
 
 PTB_DEV void chunk_stage_miss(ChunkShared& sh, const SceneView& s, const FrameView& f, const PathView& p,
-                              unsigned char* __restrict__ status, uint32_t base, unsigned int n) {
+                              unsigned char* __restrict__ status, uint32_t base, unsigned int n, unsigned int list_off = 0) {
     for (unsigned int i = threadIdx.x; i < n; i += PTB_CHUNK_THREADS) {
-        const uint32_t slot = base + sh.list[i];
+        const uint32_t slot = base + sh.list[list_off + i];
         const float4 d4 = p.ray_d[slot], as = p.atten_seed[slot];
         const uint4 mi = p.misc[slot];
         const float3 ray_dir = normalize(mk3(d4));
@@ -145,6 +269,37 @@ PTB_DEV void chunk_stage_miss(ChunkShared& sh, const SceneView& s, const FrameVi
         b.radiance = mk3(0.0f) + b.atten * mk3(hdr);
         b.origin = mk3(0.0f); b.direction = mk3(0.0f);
         b.done = 1;
+        status[slot] = after_segment(f, p, slot, b, mi.x, (int)mi.y, mi.z) ? ST_TRACE : ST_DONE;
+    }
+}
+
+// Shade and miss as ONE pass over both lists of chunk_build_two (hits at the front, misses at the back): the raygen-side
+// end of segment (after_segment: Russian roulette, accumulation, path regeneration) exists once in the instruction
+// stream, there is one stage barrier less per iteration, and the per-stage rounding loss (a list of n items keeps
+// ceil(n / threads) rounds busy) is paid once instead of twice.  Only the warp that straddles the hit/miss boundary
+// executes both bodies.
+PTB_DEV void chunk_stage_shade_miss(ChunkShared& sh, const SceneView& s, const FrameView& f, const PathView& p,
+                                    unsigned char* __restrict__ status, uint32_t base, unsigned int n_hit, unsigned int n_miss) {
+    const unsigned int total = n_hit + n_miss;
+    for (unsigned int i = threadIdx.x; i < total; i += PTB_CHUNK_THREADS) {
+        const bool is_hit = i < n_hit;
+        const uint32_t slot = base + sh.list[is_hit ? i : (unsigned int)PTB_CHUNK - total + i];
+        const float4 d4 = p.ray_d[slot], as = p.atten_seed[slot];
+        const uint4 mi = p.misc[slot];
+        Bounce b;
+        b.atten = mk3(as); b.seed = __float_as_uint(as.w);
+        if (is_hit) {
+            const float4 o4 = p.ray_o[slot], h4 = p.hit[slot];
+            closest_hit(s, f, __float_as_int(h4.w), h4.y, h4.z, h4.x, mk3(o4), mk3(d4), (int)mi.y, b);
+        } else {
+            const float3 ray_dir = normalize(mk3(d4));
+            const float u = 0.5f + det_atan2f(ray_dir.z, ray_dir.x) / (2.0f * PTB_PI_F);
+            const float v = 0.5f - det_asinf(ray_dir.y) / PTB_PI_F;
+            const float4 hdr = sample_env(s.env, s.env_w, s.env_h, u, v);
+            b.radiance = mk3(0.0f) + b.atten * mk3(hdr);
+            b.origin = mk3(0.0f); b.direction = mk3(0.0f);
+            b.done = 1;
+        }
         status[slot] = after_segment(f, p, slot, b, mi.x, (int)mi.y, mi.z) ? ST_TRACE : ST_DONE;
     }
 }
@@ -211,9 +366,10 @@ __global__ void __launch_bounds__(PTB_CHUNK_THREADS) k_chunk_miss(SceneView s, F
     if (n) chunk_stage_miss(sh, s, f, p, status, base, n);
 }
 
-// One block = one chunk, from the first camera ray to the last sample of its pixels.
+// One block = one chunk, from the first camera ray to the last sample of its pixels.  Two list passes per wavefront
+// iteration (one code copy, alternating phases): {TRACE, BUSY} before the trace stage, {HIT, MISS} before shade + miss.
 // totals[3] is not touched here (launch count is added by k_fold_counters' sibling on the host path).
-template <bool COUNT, int QUANTUM, int MINB>
+template <bool COUNT, int QUANTUM, int MINB, int PARK_BELOW, bool MERGE>
 __global__ void __launch_bounds__(PTB_CHUNK_THREADS, (MINB * 128) / PTB_CHUNK_THREADS) k_chunk_fused(SceneView s, FrameView f, PathView p, unsigned char* status,
                                                                   unsigned long long* totals, unsigned long long* trav_stats,
                                                                   unsigned int* max_iters_seen) {
@@ -221,19 +377,26 @@ __global__ void __launch_bounds__(PTB_CHUNK_THREADS, (MINB * 128) / PTB_CHUNK_TH
     const uint32_t base = blockIdx.x * PTB_CHUNK;
     if (threadIdx.x < 4) sh.count[threadIdx.x] = 0;
     TravCounters tc; tc.nodes = 0; tc.tris = 0;
+    int stack[PTB_BVH_STACK];
+    ParkedRay parked; parked.active = false; parked.primary = false; parked.slot = 0; parked.node = 0; parked.sp = 0;
+    parked.best.t = 0.0f; parked.best.b1 = 0.0f; parked.best.b2 = 0.0f; parked.best.prim = -1;
     unsigned int iter = 0;
-    for (;; ++iter) {
-        const unsigned int nt = chunk_build_list(sh, status, base, p.n_slots, ST_TRACE);
-        if (nt == 0) break;
-        if (threadIdx.x == 0) sh.count[0] += nt;
-        chunk_stage_trace<COUNT, QUANTUM>(sh, s, f, p, status, base, nt, iter == 0, tc);
+    for (unsigned int phase = 0;; phase ^= 1u) {
+        unsigned int na, nb;
+        chunk_build_two(sh, status, base, p.n_slots, phase ? ST_HIT : ST_TRACE, phase ? ST_MISS : ST_BUSY, &na, &nb);
+        if (phase == 0u) {
+            if (na == 0u && nb == 0u) break;  // nothing to trace, nothing parked: every pixel of the chunk is done
+            if (threadIdx.x == 0) sh.count[0] += na;
+            chunk_stage_trace_park<COUNT, QUANTUM, PARK_BELOW>(sh, s, f, p, status, base, na, iter == 0, na >= 2u * PTB_CHUNK_THREADS, parked, stack, tc);
+            ++iter;
+        } else {
+            if (MERGE) chunk_stage_shade_miss(sh, s, f, p, status, base, na, nb);
+            else {
+                if (na) chunk_stage_shade(sh, s, f, p, status, base, na);
+                if (nb) chunk_stage_miss(sh, s, f, p, status, base, nb, (unsigned int)PTB_CHUNK - nb);
+            }
+        }
         __syncthreads();  // status / hit records of this chunk are block-visible from here on
-        const unsigned int nh = chunk_build_list(sh, status, base, p.n_slots, ST_HIT);
-        if (nh) chunk_stage_shade(sh, s, f, p, status, base, nh);
-        __syncthreads();
-        const unsigned int nm = chunk_build_list(sh, status, base, p.n_slots, ST_MISS);
-        if (nm) chunk_stage_miss(sh, s, f, p, status, base, nm);
-        __syncthreads();
     }
     chunk_flush_counts(sh, totals, trav_stats, tc, COUNT);
     if (threadIdx.x == 0) atomicMax(max_iters_seen, iter);

@@ -186,17 +186,26 @@ __global__ void __launch_bounds__(128) k_trace(SceneView s, FrameView f, PathVie
 // ---- textures ---------------------------------------------------------------------------
 // Texel by the reference's linear index y*w + x (cu:518-521, 587-590); a negative
 // index (x0 or y0 == -1, an out-of-bounds read in the reference) wraps by +w*h.
+// b / 255.0f for an 8-bit b (optixSphere.cpp:370-373), correctly rounded without the IEEE-division sequence: one
+// Newton step on q = b * RN(1/255) with the exact residual.  Bit-identical to the division for all 256 inputs
+// (checked exhaustively on the host by tests/test_abi.py and on the device by test_device_math_bit_exact).
+PTB_DEV float unit_from_u8(unsigned int b) {
+    const float fb = (float)b, rc = 1.0f / 255.0f;
+    const float q = fb * rc;
+    return fmaf(fmaf(-q, 255.0f, fb), rc, q);
+}
 PTB_DEV float4 fetch_texel(const void* data, int fmt, int w, int h, int x, int y) {
     int idx = y * w + x;
     if (idx < 0) idx += w * h;
     if (fmt == 1) {
         const uchar4 c = __ldg((const uchar4*)data + idx);
-        return make_float4(c.x / 255.0f, c.y / 255.0f, c.z / 255.0f, c.w / 255.0f);  // optixSphere.cpp:370-373
+        return make_float4(unit_from_u8(c.x), unit_from_u8(c.y), unit_from_u8(c.z), unit_from_u8(c.w));
     }
     return __ldg((const float4*)data + idx);
 }
+// x0 in [-1, w-1] and y0 in [-1, h-1] at both call sites (see there), so (x0 + 1) % w is a compare, not a division.
 PTB_DEV float4 bilinear(const void* data, int fmt, int w, int h, int x0, int y0, float s, float t) {
-    const int x1 = (x0 + 1) % w, y1 = (y0 + 1) % h;
+    const int x1 = x0 + 1 == w ? 0 : x0 + 1, y1 = y0 + 1 == h ? 0 : y0 + 1;
     const float4 c00 = fetch_texel(data, fmt, w, h, x0, y0), c10 = fetch_texel(data, fmt, w, h, x1, y0);
     const float4 c01 = fetch_texel(data, fmt, w, h, x0, y1), c11 = fetch_texel(data, fmt, w, h, x1, y1);
     const float4 c0 = lerp(c00, c10, s), c1 = lerp(c01, c11, s);
@@ -206,14 +215,17 @@ PTB_DEV float4 bilinear(const void* data, int fmt, int w, int h, int x0, int y0,
 PTB_DEV float4 sample_texture(const DevTexture& tx, float u, float v) {
     u = u - floorf(u);
     v = v - floorf(v);
+    // u, v in [0, 1] here (1.0 when a tiny negative rounds up; NaN converts to texel 0): x0 in [-1, w-1]
     const float x = u * tx.w - 0.5f, y = v * tx.h - 0.5f;
     const int x0 = (int)floorf(x), y0 = (int)floorf(y);
     return bilinear(tx.data, tx.fmt, tx.w, tx.h, x0, y0, x - floorf(x), y - floorf(y));
 }
 // sampleHDRI (cu:503-529)
 PTB_DEV float4 sample_env(const float4* env, int w, int h, float u, float v) {
+    // u, v are in [0, 1] (atan2 / asin of a normalised direction; a NaN converts to 0), so floorf(x) is in [-1, w-1]
+    // and the reference's `% w` (C remainder: -1 stays -1) is the identity on that range: no integer division here.
     const float x = u * w - 0.5f, y = v * h - 0.5f;
-    const int x0 = (int)floorf(x) % w, y0 = (int)floorf(y) % h;
+    const int x0 = (int)floorf(x), y0 = (int)floorf(y);
     return bilinear(env, 2, w, h, x0, y0, x - floorf(x), y - floorf(y));
 }
 // setMaterialProperty (cu:598-613)
@@ -305,8 +317,22 @@ PTB_DEV void closest_hit(const SceneView& s, const FrameView& f, int prim_idx, f
     const float3 hit_pos = ray_orig + t_hit * ray_dir;
     uint32_t seed = io.seed;
 
-    const float3 diffuse_albedo = material_property(m.tex[0], mk3(m.diffuse[0], m.diffuse[1], m.diffuse[2]), uvx, uvy);
-    float3 normal_map = material_property(m.tex[2], mk3(0.0f, 1.0f, 0.0f), uvx, uvy);
+    // setMaterialProperty x 4 (cu:682-714).  ONE copy of the bilinear fetch in the instruction stream, run up to four
+    // times: the lookups have no side effects, so their order is free, and the fused kernels are instruction-fetch
+    // bound (profiles/: stall_no_instruction), which makes code size worth more than the unrolled schedule.
+    float3 diffuse_albedo = mk3(m.diffuse[0], m.diffuse[1], m.diffuse[2]);
+    float3 normal_map = mk3(0.0f, 1.0f, 0.0f);
+    float roughness = m.roughness;
+    float metallicity = m.metallic ? 1.0f : 0.0f;
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) {
+        if (m.tex[k].fmt == 0) continue;
+        const float4 c = sample_texture(m.tex[k], uvx, uvy);
+        if (k == 0) diffuse_albedo = mk3(c);
+        else if (k == 1) roughness = c.x;
+        else if (k == 2) normal_map = mk3(c);
+        else metallicity = c.x;
+    }
     if (m.tex[2].fmt != 0) {
         normal_map = normalize(2.0f * normal_map - mk3(1.0f));
         normal_map = mk3(normal_map.x, normal_map.z, normal_map.y);
@@ -319,8 +345,6 @@ PTB_DEV void closest_hit(const SceneView& s, const FrameView& f, int prim_idx, f
     const float3 specular_albedo = diffuse_albedo;
     const float3 emission_color = mk3(m.emission[0], m.emission[1], m.emission[2]);
 
-    float roughness = material_property(m.tex[1], mk3(m.roughness), uvx, uvy).x;
-    const float metallicity = material_property(m.tex[3], m.metallic ? mk3(1.0f) : mk3(0.0f), uvx, uvy).x;
     const float ior = 1.5f;
 
     if (length(emission_color) > 0.0001f) {
@@ -594,6 +618,7 @@ __global__ void k_test_math(int op, const float* __restrict__ in, int in_stride,
     else if (op == 1) { float sn, cs; det_sincosf(a[0], &sn, &cs); r[0] = sn; r[1] = cs; }
     else if (op == 2) r[0] = det_atan2f(a[0], a[1]);
     else if (op == 3) r[0] = det_asinf(a[0]);
+    else if (op == 4) { r[0] = unit_from_u8((unsigned int)a[0]); r[1] = a[0] / 255.0f; }
 }
 
 }  // namespace ptb

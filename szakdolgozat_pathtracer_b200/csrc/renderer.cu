@@ -26,6 +26,7 @@
 #include "bvh_build.h"
 #include "host.h"
 #include "linear.cuh"
+#include "pool.cuh"
 
 namespace ptb {
 
@@ -70,6 +71,7 @@ struct ptb_context {
     unsigned long long* totals = nullptr;  // segments, hits, misses, launches since the last reset
     unsigned long long* launch_totals = nullptr;  // the same for the launch in flight ([3]: iterations of the fused pipeline)
     unsigned char* status = nullptr;       // one byte per slot (chunked pipelines)
+    float4* out_pixsum = nullptr; uint32_t out_pixsum_slots = 0;  // per-slot sample sums of the pool pipeline
     // linear estimator (env_importance_sampling != 0): pending shadow rays, allocated on first use
     float4 *shadow_o = nullptr, *shadow_d = nullptr, *shadow_c = nullptr; unsigned char* shadow_flag = nullptr; uint32_t shadow_slots = 0;
     int last_pipeline = 0;
@@ -120,6 +122,7 @@ void free_pool(ptb_context* c) {
     cudaFree(c->q_trace[0]); cudaFree(c->q_trace[1]); cudaFree(c->q_hit); cudaFree(c->q_miss); cudaFree(c->status);
     cudaFree(c->shadow_o); cudaFree(c->shadow_d); cudaFree(c->shadow_c); cudaFree(c->shadow_flag);
     c->shadow_o = c->shadow_d = c->shadow_c = nullptr; c->shadow_flag = nullptr; c->shadow_slots = 0;
+    cudaFree(c->out_pixsum); c->out_pixsum = nullptr; c->out_pixsum_slots = 0;
     c->status = nullptr;
     c->ray_o = c->ray_d = c->hit = c->atten_seed = c->pixsum = nullptr; c->misc = nullptr;
     c->q_trace[0] = c->q_trace[1] = c->q_hit = c->q_miss = nullptr;
@@ -288,6 +291,7 @@ int ptb_accel_build(ptb_context* ctx, ptb_scene* scene, const ptb_build_cfg* cfg
     bool built = build_bvh(d->verts, n, cfg, st, d->bvh, stats, err);
     if (!built && cfg.sah_refine) {
         // an SAH treelet can in principle grow deeper than the traversal stack: fall back to the plain LBVH (depth <= 62)
+        if (getenv("PTB_VERBOSE")) fprintf(stderr, "ptb_accel_build: refined build failed (%s), falling back to the plain LBVH\n", err.c_str());
         free_bvh(d->bvh);
         cfg.sah_refine = 0;
         built = build_bvh(d->verts, n, cfg, st, d->bvh, stats, err);
@@ -358,8 +362,26 @@ int ptb_launch(ptb_context* ctx, const ptb_Params* P, const ptb_render_cfg* cfg_
     if ((uint64_t)n_pixels * (uint64_t)n_sub > 0x7fffffffull) return fail(PTB_ERR_INVALID, "ptb_launch: subframes_per_launch * pixels too large");
     const uint32_t slots = n_pixels * (uint32_t)n_sub;
     const uint32_t iters = (uint32_t)cfg.spp_per_launch * (uint32_t)(cfg.max_depth + 1);
-    int rc = ensure_pool(ctx, slots, iters);
+
+    static const int env_pipe = getenv("PTB_PIPELINE") ? atoi(getenv("PTB_PIPELINE")) : -1;  // experiments only
+    int pipeline = cfg.pipeline > 0 ? cfg.pipeline : (env_pipe > 0 ? env_pipe : PTB_PIPELINE_DEFAULT);
+    if (pipeline < PTB_PIPELINE_QUEUES || pipeline > PTB_PIPELINE_POOL_FUSED) return fail(PTB_ERR_INVALID, "ptb_launch: unknown pipeline");
+    if (il_n > 1 && pipeline == PTB_PIPELINE_QUEUES) return fail(PTB_ERR_UNSUPPORTED, "ptb_launch: row interleave needs a chunked pipeline (2, 3 or 4)");
+    if (cfg.env_importance_sampling) pipeline = PTB_PIPELINE_CHUNK_STAGES;
+
+    // pool pipeline: persistent blocks own PTB_CHUNK positions each; path state is per position, not per slot
+    const uint32_t pool_blocks_needed = (slots + PTB_CHUNK - 1u) / PTB_CHUNK;
+    const bool pool_wide = pool_blocks_needed >= (uint32_t)ctx->num_sms * (1024u / PTB_CHUNK_THREADS);
+    const uint32_t pool_cap = (uint32_t)ctx->num_sms * (pool_wide ? 1024u / PTB_CHUNK_THREADS : 640u / PTB_CHUNK_THREADS);
+    const uint32_t pool_grid = pool_blocks_needed < pool_cap ? pool_blocks_needed : pool_cap;
+    const bool use_pool = pipeline == PTB_PIPELINE_POOL_FUSED;
+    int rc = ensure_pool(ctx, use_pool ? pool_grid * PTB_CHUNK : slots, iters);
     if (rc != PTB_OK) return rc;
+    if (use_pool && slots > ctx->out_pixsum_slots) {
+        cudaFree(ctx->out_pixsum); ctx->out_pixsum = nullptr; ctx->out_pixsum_slots = 0;
+        CU(cudaMalloc((void**)&ctx->out_pixsum, (size_t)slots * 16));
+        ctx->out_pixsum_slots = slots;
+    }
 
     FrameView f;
     f.W = P->image_width; f.H = P->image_height; f.row0 = row0; f.il_n = il_n; f.il_r = il_r; f.il_h = il_h; f.n_pixels = n_pixels; f.n_subframes = n_sub; f.subframe = P->subframe_index; f.dof = P->dof ? 1 : 0;
@@ -378,11 +400,6 @@ int ptb_launch(ptb_context* ctx, const ptb_Params* P, const ptb_render_cfg* cfg_
     q.trace[0] = ctx->q_trace[0]; q.trace[1] = ctx->q_trace[1]; q.hit = ctx->q_hit; q.miss = ctx->q_miss;
     q.counters = ctx->counters; q.trav_stats = ctx->trav_stats;
     const SceneView s = scene_view(d);
-
-    static const int env_pipe = getenv("PTB_PIPELINE") ? atoi(getenv("PTB_PIPELINE")) : -1;  // experiments only
-    int pipeline = cfg.pipeline > 0 ? cfg.pipeline : (env_pipe > 0 ? env_pipe : PTB_PIPELINE_DEFAULT);
-    if (pipeline < PTB_PIPELINE_QUEUES || pipeline > PTB_PIPELINE_CHUNK_FUSED) return fail(PTB_ERR_INVALID, "ptb_launch: unknown pipeline");
-    if (il_n > 1 && pipeline == PTB_PIPELINE_QUEUES) return fail(PTB_ERR_UNSUPPORTED, "ptb_launch: row interleave needs a chunked pipeline (2 or 3)");
 
     CU(cudaMemsetAsync(ctx->counters, 0, (size_t)(iters + 2) * 4 * sizeof(uint32_t), st));
     CU(cudaMemsetAsync(ctx->trav_stats, 0, 2 * sizeof(unsigned long long), st));
@@ -412,7 +429,6 @@ int ptb_launch(ptb_context* ctx, const ptb_Params* P, const ptb_render_cfg* cfg_
         lv.cdf.total = d->cdf_total; lv.cdf.w = d->env_w; lv.cdf.h = d->env_h;
         lv.shadow_o = ctx->shadow_o; lv.shadow_d = ctx->shadow_d; lv.shadow_c = ctx->shadow_c; lv.shadow_flag = ctx->shadow_flag;
         lv.nee = cfg.env_importance_sampling == 1 ? 1 : 0;
-        pipeline = PTB_PIPELINE_CHUNK_STAGES;
         const uint32_t chunks = (slots + PTB_CHUNK - 1u) / PTB_CHUNK;
         k_chunk_raygen<<<pix_blocks, 256, 0, st>>>(f, p, ctx->status);
         if (prof) CU(cudaEventRecord(ctx->events[1], st));
@@ -449,6 +465,24 @@ int ptb_launch(ptb_context* ctx, const ptb_Params* P, const ptb_render_cfg* cfg_
         }
         k_fold_counters<<<1, 256, 0, st>>>(ctx->counters, iters, ctx->launch_totals);
         launches += 1;
+    } else if (use_pool) {
+        // persistent block-local wavefront (pool.cuh): one kernel, camera rays included
+        unsigned int* max_iters = (unsigned int*)(ctx->launch_totals + 3);
+        PoolView pv;
+        pv.out_pixsum = ctx->out_pixsum; pv.next_slot = max_iters + 1;  // both words zeroed by the memset above
+        pv.n_slots = slots; pv.grid = pool_grid;
+        PathView ps = p; ps.n_slots = pool_grid * PTB_CHUNK;
+        if (prof) CU(cudaEventRecord(ctx->events[1], st));  // no separate raygen kernel
+        if (cfg.count_traversal) k_pool_fused<true, PTB_TRACE_QUANTUM, 5><<<pool_grid, PTB_CHUNK_THREADS, 0, st>>>(s, f, ps, pv, ctx->launch_totals, ctx->trav_stats, max_iters);
+        else if (pool_wide) k_pool_fused<false, PTB_TRACE_QUANTUM, 8><<<pool_grid, PTB_CHUNK_THREADS, 0, st>>>(s, f, ps, pv, ctx->launch_totals, ctx->trav_stats, max_iters);
+        else k_pool_fused<false, PTB_TRACE_QUANTUM, 5><<<pool_grid, PTB_CHUNK_THREADS, 0, st>>>(s, f, ps, pv, ctx->launch_totals, ctx->trav_stats, max_iters);
+        launches = 1;
+        prof_iters = 0;
+        if (prof) {
+            CU(cudaEventRecord(ctx->events[2], st)); CU(cudaEventRecord(ctx->events[3], st)); CU(cudaEventRecord(ctx->events[4], st));
+            prof_iters = 1;
+        }
+        p.pixsum = ctx->out_pixsum;  // what k_resolve folds
     } else {
         // block-local wavefront over chunks of the path pool (chunked.cuh)
         const uint32_t chunks = (slots + PTB_CHUNK - 1u) / PTB_CHUNK;
@@ -471,9 +505,18 @@ int ptb_launch(ptb_context* ctx, const ptb_Params* P, const ptb_render_cfg* cfg_
             // 64 registers / 8 blocks per SM once there are enough chunks to keep that many blocks busy (the fused kernel
             // is occupancy-limited: +12 % at 8 batched subframes), the unconstrained 94-register build for small frames
             const bool wide = chunks >= (uint32_t)ctx->num_sms * (1024u / PTB_CHUNK_THREADS) * 4u;
-            if (cfg.count_traversal) k_chunk_fused<true, PTB_TRACE_QUANTUM, 5><<<chunks, PTB_CHUNK_THREADS, 0, st>>>(s, f, p, ctx->status, ctx->launch_totals, ctx->trav_stats, max_iters);
-            else if (wide) k_chunk_fused<false, PTB_TRACE_QUANTUM, 8><<<chunks, PTB_CHUNK_THREADS, 0, st>>>(s, f, p, ctx->status, ctx->launch_totals, ctx->trav_stats, max_iters);
-            else k_chunk_fused<false, PTB_TRACE_QUANTUM, 5><<<chunks, PTB_CHUNK_THREADS, 0, st>>>(s, f, p, ctx->status, ctx->launch_totals, ctx->trav_stats, max_iters);
+            static const int env_park = getenv("PTB_PARK") ? atoi(getenv("PTB_PARK")) : -1;  // experiments only
+            static const int env_merge = getenv("PTB_MERGE") ? atoi(getenv("PTB_MERGE")) : -1;
+            const int park = env_park >= 0 ? env_park : 0, merge = env_merge >= 0 ? env_merge : 1;
+#define PTB_CF_LAUNCH(COUNT, MINB, PARK, MERGE) k_chunk_fused<COUNT, PTB_TRACE_QUANTUM, MINB, PARK, MERGE><<<chunks, PTB_CHUNK_THREADS, 0, st>>>(s, f, p, ctx->status, ctx->launch_totals, ctx->trav_stats, max_iters)
+            if (cfg.count_traversal) PTB_CF_LAUNCH(true, 5, 0, true);
+            else if (!wide) PTB_CF_LAUNCH(false, 5, 0, true);
+            else if (park == 0 && merge == 1) PTB_CF_LAUNCH(false, 8, 0, true);
+            else if (park == 24 && merge == 1) PTB_CF_LAUNCH(false, 8, 24, true);
+            else if (park == 0 && merge == 0) PTB_CF_LAUNCH(false, 8, 0, false);
+            else if (park == 24 && merge == 0) PTB_CF_LAUNCH(false, 8, 24, false);
+            else return fail(PTB_ERR_INVALID, "ptb_launch: unsupported PTB_PARK / PTB_MERGE");
+#undef PTB_CF_LAUNCH
             launches += 1;
             prof_iters = 0;
             if (prof) {  // a single kernel: everything between raygen and resolve is reported as "trace"
@@ -506,7 +549,7 @@ int ptb_launch_get_stats(ptb_context* ctx, ptb_launch_stats* out) {
     CU(cudaStreamSynchronize(ctx->last_stream));
     out->segments = lt[0]; out->hits = lt[1]; out->misses = lt[2];
     uint32_t used = 0;
-    if (ctx->last_pipeline == PTB_PIPELINE_CHUNK_FUSED) used = (uint32_t)(lt[3] & 0xffffffffull);
+    if (ctx->last_pipeline == PTB_PIPELINE_CHUNK_FUSED || ctx->last_pipeline == PTB_PIPELINE_POOL_FUSED) used = (uint32_t)(lt[3] & 0xffffffffull);
     else for (uint32_t it = 0; it < ctx->last_iters; ++it) if (h[(size_t)it * 4 + 0]) used = it + 1;
     out->paths = ctx->last_paths; out->iterations = used; out->kernel_launches = ctx->last_kernels;
     if (ctx->last_counted) { out->nodes_visited = tv[0]; out->tris_tested = tv[1]; }
@@ -731,7 +774,7 @@ int ptb_test_env_sample(ptb_context* ctx, unsigned long long handle, const float
 }
 
 int ptb_test_device_math(ptb_context* ctx, int op, const float* in, int in_stride, float* out, int out_stride, uint32_t n) {
-    if (!ctx || !in || !out || in_stride < 1 || out_stride < 1 || op < 0 || op > 3) return fail(PTB_ERR_INVALID, "ptb_test_device_math: bad arguments");
+    if (!ctx || !in || !out || in_stride < 1 || out_stride < 1 || op < 0 || op > 4) return fail(PTB_ERR_INVALID, "ptb_test_device_math: bad arguments");
     CU(cudaSetDevice(ctx->device));
     float *d_in = nullptr, *d_out = nullptr;
     CU(cudaMalloc((void**)&d_in, (size_t)n * in_stride * sizeof(float) + 16));

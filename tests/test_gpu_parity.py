@@ -14,12 +14,12 @@ from scenes import CAMERAS, load_config, random_rays
 
 pytestmark = pytest.mark.gpu
 
-# every parity test runs on all three pipelines (global queues / chunked stages / chunked fused): the results must be
-# bit-identical because a slot's arithmetic never depends on the order in which slots are processed
+# every parity test runs on all four pipelines (global queues / chunked stages / chunked fused / persistent pool): the
+# results must be bit-identical because a slot's arithmetic never depends on the order in which slots are processed
 PIPELINE = 0
 
 
-@pytest.fixture(autouse=True, params=[1, 2, 3], ids=["queues", "chunk-stages", "chunk-fused"])
+@pytest.fixture(autouse=True, params=[1, 2, 3, 4], ids=["queues", "chunk-stages", "chunk-fused", "pool-fused"])
 def _pipeline(request):
     global PIPELINE
     PIPELINE = request.param
@@ -94,6 +94,11 @@ def test_device_math_bit_exact(ptb, ctx, oh):
     asn = ctx.test_device_math(3, xs.reshape(-1, 1), 1)[:, 0]
     ref = np.array([L.orc_asin(float(a)) for a in xs], np.float32)
     assert np.array_equal(asn.view(np.uint32), ref.view(np.uint32))
+    # texel widening: the division-free b / 255.0f (kernels.cuh: unit_from_u8) against the device's own IEEE division and numpy
+    b = np.arange(256, dtype=np.float32)
+    u8 = ctx.test_device_math(4, b.reshape(-1, 1), 2)
+    assert np.array_equal(u8[:, 0].view(np.uint32), u8[:, 1].view(np.uint32))
+    assert np.array_equal(u8[:, 0].view(np.uint32), (b / np.float32(255.0)).view(np.uint32))
 
 
 def _check_bvh(nodes, tris, n_tris, max_leaf):
@@ -138,7 +143,7 @@ def test_bvh_structure_and_ray_queries(ptb, ctx, oh, assets, name, small, refine
         pytest.skip("the BVH does not depend on the render pipeline")
     sc = load_config(ptb, assets, name, small=small)
     handle, st = ctx.accel_build(sc, ptb.default_build_cfg(sah_refine=refine))
-    assert st.num_triangles == sc.num_triangles and st.max_depth < 64
+    assert st.num_triangles == sc.num_triangles and st.max_depth < 128
     nodes, tris = ctx.accel_read(handle)
     assert _check_bvh(nodes, tris, sc.num_triangles, 4) == st.num_nodes
     if refine and name == "c2":
@@ -373,8 +378,8 @@ def test_resolve_peers_single_device(ptb, ctx):
 def test_c3_full_pbr_parity_crop(ptb, ctx, oh, assets):
     """BASELINE config 3 scene: suitcase.obj with all four maps (albedo, normal, roughness, metallic, 2048^2 each) under a
     4096x2048 environment; close camera so that the mesh fills the crop: bit-exact accum and hit IDs."""
-    if PIPELINE != 3:
-        pytest.skip("one pipeline is enough for the large-texture scene (the others are covered on C1/C2)")
+    if PIPELINE not in (3, 4):
+        pytest.skip("the fused pipelines are enough for the large-texture scene (the others are covered on C1/C2)")
     sc = load_config(ptb, assets, "c3")
     m = sc.material(0)
     assert m.has_albedo and m.has_normal and m.has_roughness and m.has_metallic and m.albedo_w == 2048
@@ -393,7 +398,7 @@ def test_c3_full_pbr_parity_crop(ptb, ctx, oh, assets):
 
 def test_c2_full_frame_primary_hits(ptb, ctx, oh, assets):
     """BASELINE config 2 at its full size: all 2 073 600 primary-hit triangle IDs (DoF on) and the 1-sample image, bit-exact."""
-    if PIPELINE != 3:
+    if PIPELINE != 4:
         pytest.skip("full-frame check on the default pipeline")
     sc = load_config(ptb, assets, "c2")
     handle, _ = ctx.accel_build(sc)
