@@ -172,7 +172,7 @@ def main():
     ap.add_argument("--ref-rows", type=int, default=1080, help="rows of the frame per step of the CPU reference arm")
     ap.add_argument("--cpu-rows", type=int, default=1080, help="rows of the frame for the cpu_baseline sample of our arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--pipeline", type=int, default=3, help="1 global queues, 2 chunked stage kernels, 3 chunked fused (default)")
+    ap.add_argument("--pipeline", type=int, default=3, help="1 global queues, 2 chunked stage kernels, 3 chunked fused (default), 4 persistent pool")
     ap.add_argument("--config", default="c2", choices=list(CONFIGS))
     ap.add_argument("--split", default="samples", choices=["samples", "tiles"],
                     help="N > 1: split the frame's subframes across ranks (weak scaling, default) or its rows (tile partitioning, strong scaling)")
@@ -325,7 +325,7 @@ def main():
         return acc
     stage = profiled(args.pipeline)
     # (2) per-stage split from the same stages run as separate kernels (pipeline 2); explains where the time goes
-    stage_split = profiled(2) if args.pipeline == 3 else stage
+    stage_split = profiled(2) if args.pipeline in (3, 4) else stage
     # traversal work per segment, from one instrumented launch of subframe 0
     cfg_cnt = ptb.default_render_cfg(spp_per_launch=SPP_PER_LAUNCH, max_depth=DEPTH, write_frame=0, count_traversal=1, pipeline=args.pipeline)
     p = ptb.make_params(W, H, subframe_index=0, dof=True, **CAMERAS[CAMERA])
@@ -345,8 +345,8 @@ def main():
     peak, peak_src = measured_peaks()
     l2_peak = ctx.microbench_read(32 << 20, 40)    # 32 MiB working set: L2 -> SM read bandwidth
     hbm_read = ctx.microbench_read(2 << 30, 4)     # 2 GiB working set: HBM read bandwidth of the same kernel
-    if args.pipeline == 3:
-        kernel, kernel_ms, launches_k = "k_chunk_fused", stage["trace"], 1
+    if args.pipeline in (3, 4):
+        kernel, kernel_ms, launches_k = ("k_chunk_fused" if args.pipeline == 3 else "k_pool_fused"), stage["trace"], 1
         bytes_per_seg = trace_bytes_per_seg + shade_bytes_per_seg
     else:
         kernel, kernel_ms = ("k_chunk_trace" if args.pipeline == 2 else "k_trace"), stage["trace"]
@@ -367,7 +367,7 @@ def main():
         "algorithmic_bytes_per_segment": bytes_per_seg, "algorithmic_bytes_per_launch": bytes_per_seg * seg_per_step / launches_k,
         "avg_launch_ms": kernel_ms / launches_k, "launches_per_step": launches_k,
         "nodes_per_segment": nodes_per_seg, "tris_per_segment": tris_per_seg, "hit_fraction": hit_frac,
-        "note": "BVH (1.4 MB) and textures (4 MB) are L2-resident and the fused kernel keeps a chunk's path state in L1/L2 between stages, "
+        "note": "BVH (1.4 MB, huge primitives split off at the root) and textures (4 MB) are L2-resident and the fused kernel keeps a chunk's path state in L1/L2 between stages, "
                 "so most algorithmic bytes never reach HBM: ncu shows the kernels issue-bound (profiles/), the fraction is of the HBM copy peak",
         "share_of_step": kernel_ms / stage["total"] if stage["total"] > 0 else None,
         "stage_ms_per_step_separate_kernels": {k: v for k, v in stage_split.items()},
@@ -415,7 +415,8 @@ def main():
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "spp_per_step_per_gpu": SPP_PER_LAUNCH * LAUNCHES_PER_STEP, "split": ("tiles (16-row strips dealt round-robin)" if tiles else "samples") if multi else "none",
                        "l2": "no flush: the path pool of one step is 8 x 1920 x 1080 slots x 97 B = 1.6 GB (> 126 MB L2) and is rewritten every iteration",
-                       "pipeline": {1: "global queues", 2: "block-local wavefront, one kernel per stage and iteration", 3: "block-local wavefront, fused persistent kernel"}[args.pipeline],
+                       "pipeline": {1: "global queues", 2: "block-local wavefront, one kernel per stage and iteration", 3: "block-local wavefront, fused persistent kernel",
+                                    4: "persistent path pool (blocks own positions, slots handed out from one counter)"}[args.pipeline],
                        "subframes_per_launch": LAUNCHES_PER_STEP,
                        "multi_gpu": ("scene replicated, subframes split by rank; exchange: " + exchange_note) if multi else "single GPU, reference accumulate mode",
                        "bvh": {"triangles": bst.num_triangles, "nodes": bst.num_nodes, "max_depth": bst.max_depth, "sah": bst.sah_cost, "build_ms": bst.build_ms}},

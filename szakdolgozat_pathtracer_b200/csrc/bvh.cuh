@@ -96,7 +96,9 @@ PTB_DEV bool slab(float lox, float hix, float loy, float hiy, float loz, float h
 }
 
 #define PTB_TRAV_SENTINEL 0x7fffffff
+#ifndef PTB_TRACE_QUANTUM
 #define PTB_TRACE_QUANTUM 8  // traversal steps between two ray-fetch points (measured: 8 >= 16 > 4 on C2)
+#endif
 
 // Traversal state of one ray.  The stack lives in the caller's local memory (one entry per tree level; the
 // builder rejects trees deeper than PTB_BVH_STACK).

@@ -33,8 +33,7 @@ namespace ptb {
 #endif
 #define PTB_CHUNK (PTB_CHUNK_THREADS * PTB_CHUNK_SPT)  // slots per block
 
-// ST_BUSY: the slot's ray is parked half-traversed in a lane of the fused kernel (see chunk_stage_trace_suspend)
-enum SlotStatus : unsigned char { ST_DONE = 0, ST_TRACE = 1, ST_HIT = 2, ST_MISS = 3, ST_BUSY = 4 };
+enum SlotStatus : unsigned char { ST_DONE = 0, ST_TRACE = 1, ST_HIT = 2, ST_MISS = 3 };
 
 struct ChunkShared {
     unsigned short list[PTB_CHUNK];  // slot offsets inside the chunk, ascending
@@ -92,7 +91,7 @@ PTB_DEV unsigned int chunk_build_list(ChunkShared& sh, const unsigned char* __re
 }
 
 // One pass over the chunk's status bytes builds TWO lists: slots in state want_a ascending from the front of sh.list,
-// slots in state want_b ascending at its back (sh.list[PTB_CHUNK - nb ..)).  Block-uniform result.
+// slots in state want_b ascending at its back (sh.list[PTB_CHUNK - nb ..)); want_b = 0xff matches nothing.  Block-uniform.
 PTB_DEV void chunk_build_two(ChunkShared& sh, const unsigned char* __restrict__ status, uint32_t base, uint32_t n_slots,
                              unsigned char want_a, unsigned char want_b, unsigned int* na, unsigned int* nb) {
     const unsigned int tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -120,77 +119,6 @@ PTB_DEV void chunk_build_two(ChunkShared& sh, const unsigned char* __restrict__ 
     if (tid == 0) { sh.n = tot_a; sh.next = 0; }
     __syncthreads();
     *na = tot_a; *nb = tot_b;
-}
-
-// A ray parked between two trace stages of the fused kernel: everything else is recomputed from the slot's ray on resume.
-struct ParkedRay { HitRec best; int node, sp; uint32_t slot; bool active, primary; };
-
-// Trace stage of the fused kernel.  Like chunk_stage_trace, but a warp does not wait for its longest rays: once the
-// chunk's list is exhausted and fewer than PARK_BELOW of its lanes are still traversing, the unfinished rays are parked
-// (status ST_BUSY, traversal position kept in `parked` and in the lane's stack) and resumed at the next trace stage.
-// Which iteration finishes a ray has no influence on its result, so the output stays bit-identical.
-// allow_park is false in the tail of a chunk (short lists), where waiting is cheaper than extra iterations.
-template <bool COUNT, int QUANTUM, int PARK_BELOW>
-PTB_DEV void chunk_stage_trace_park(ChunkShared& sh, const SceneView& s, const FrameView& f, const PathView& p,
-                                    unsigned char* __restrict__ status, uint32_t base, unsigned int n, bool first_iteration,
-                                    bool allow_park, ParkedRay& parked, int* stack, TravCounters& tc) {
-    const unsigned lane = threadIdx.x & 31u;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    Trav t;
-    t.node = PTB_TRAV_SENTINEL; t.sp = 0; t.best.prim = -1; t.best.t = 0.0f; t.best.b1 = 0.0f; t.best.b2 = 0.0f;
-    uint32_t slot = 0;
-    bool have = false, primary = false, exhausted = n == 0u;
-    unsigned int hits = 0;
-    if (parked.active) {
-        slot = parked.slot;
-        const float4 o4 = p.ray_o[slot], d4 = p.ray_d[slot];
-        trav_begin(t, stack, mk3(o4), mk3(d4), f.tmin, f.tmax);  // stack[0] is the sentinel already; the rest is kept
-        t.best = parked.best; t.node = parked.node; t.sp = parked.sp;
-        primary = parked.primary;
-        have = true;
-        parked.active = false;
-    }
-    for (;;) {
-        __syncwarp();
-        if (!exhausted) {
-            const unsigned need = __ballot_sync(0xffffffffu, !have);
-            if (need) {
-                const int leader = __ffs(need) - 1;
-                const unsigned int cnt = (unsigned int)__popc(need);
-                unsigned int b0 = 0;
-                if ((int)lane == leader) b0 = atomicAdd(&sh.next, cnt);
-                b0 = __shfl_sync(0xffffffffu, b0, leader);
-                const unsigned int idx = b0 + (unsigned int)__popc(need & lt_mask);
-                if (!have && idx < n) {
-                    slot = base + sh.list[idx];
-                    const float4 o4 = p.ray_o[slot], d4 = p.ray_d[slot];
-                    trav_begin(t, stack, mk3(o4), mk3(d4), f.tmin, f.tmax);
-                    have = true; primary = first_iteration;
-                }
-                if (b0 + cnt >= n) exhausted = true;  // warp-uniform
-            }
-        }
-        const unsigned busy = __ballot_sync(0xffffffffu, have);
-        if (!busy) break;
-        if (exhausted && allow_park && __popc(busy) < PARK_BELOW) {
-            if (have) {
-                parked.best = t.best; parked.node = t.node; parked.sp = t.sp; parked.slot = slot; parked.primary = primary;
-                parked.active = true;
-                status[slot] = ST_BUSY;
-            }
-            break;
-        }
-        if (have && trav_run<COUNT>(t, stack, s.nodes, s.tris, QUANTUM, &tc)) {
-            have = false;
-            p.hit[slot] = make_float4(t.best.t, t.best.b1, t.best.b2, __int_as_float(t.best.prim));
-            const bool is_hit = t.best.prim >= 0;
-            status[slot] = is_hit ? ST_HIT : ST_MISS;
-            hits += is_hit ? 1u : 0u;
-            if (primary && f.aux_primary && slot < f.n_pixels) f.aux_primary[(size_t)image_row(f, slot / f.W) * f.W + slot % f.W] = t.best.prim;
-        }
-    }
-    for (int off = 16; off > 0; off >>= 1) hits += __shfl_xor_sync(0xffffffffu, hits, off);
-    if (lane == 0u && hits) atomicAdd(&sh.count[1], hits);
 }
 
 // ---- stage bodies over one chunk ---------------------------------------------------------------------------
@@ -369,7 +297,7 @@ __global__ void __launch_bounds__(PTB_CHUNK_THREADS) k_chunk_miss(SceneView s, F
 // One block = one chunk, from the first camera ray to the last sample of its pixels.  Two list passes per wavefront
 // iteration (one code copy, alternating phases): {TRACE, BUSY} before the trace stage, {HIT, MISS} before shade + miss.
 // totals[3] is not touched here (launch count is added by k_fold_counters' sibling on the host path).
-template <bool COUNT, int QUANTUM, int MINB, int PARK_BELOW, bool MERGE>
+template <bool COUNT, int QUANTUM, int MINB>
 __global__ void __launch_bounds__(PTB_CHUNK_THREADS, (MINB * 128) / PTB_CHUNK_THREADS) k_chunk_fused(SceneView s, FrameView f, PathView p, unsigned char* status,
                                                                   unsigned long long* totals, unsigned long long* trav_stats,
                                                                   unsigned int* max_iters_seen) {
@@ -377,24 +305,17 @@ __global__ void __launch_bounds__(PTB_CHUNK_THREADS, (MINB * 128) / PTB_CHUNK_TH
     const uint32_t base = blockIdx.x * PTB_CHUNK;
     if (threadIdx.x < 4) sh.count[threadIdx.x] = 0;
     TravCounters tc; tc.nodes = 0; tc.tris = 0;
-    int stack[PTB_BVH_STACK];
-    ParkedRay parked; parked.active = false; parked.primary = false; parked.slot = 0; parked.node = 0; parked.sp = 0;
-    parked.best.t = 0.0f; parked.best.b1 = 0.0f; parked.best.b2 = 0.0f; parked.best.prim = -1;
     unsigned int iter = 0;
     for (unsigned int phase = 0;; phase ^= 1u) {
         unsigned int na, nb;
-        chunk_build_two(sh, status, base, p.n_slots, phase ? ST_HIT : ST_TRACE, phase ? ST_MISS : ST_BUSY, &na, &nb);
+        chunk_build_two(sh, status, base, p.n_slots, phase ? ST_HIT : ST_TRACE, phase ? ST_MISS : (unsigned char)0xff, &na, &nb);
         if (phase == 0u) {
-            if (na == 0u && nb == 0u) break;  // nothing to trace, nothing parked: every pixel of the chunk is done
+            if (na == 0u) break;  // every pixel of the chunk has finished its samples
             if (threadIdx.x == 0) sh.count[0] += na;
-            chunk_stage_trace_park<COUNT, QUANTUM, PARK_BELOW>(sh, s, f, p, status, base, na, iter == 0, na >= 2u * PTB_CHUNK_THREADS, parked, stack, tc);
+            chunk_stage_trace<COUNT, QUANTUM>(sh, s, f, p, status, base, na, iter == 0, tc);
             ++iter;
         } else {
-            if (MERGE) chunk_stage_shade_miss(sh, s, f, p, status, base, na, nb);
-            else {
-                if (na) chunk_stage_shade(sh, s, f, p, status, base, na);
-                if (nb) chunk_stage_miss(sh, s, f, p, status, base, nb, (unsigned int)PTB_CHUNK - nb);
-            }
+            chunk_stage_shade_miss(sh, s, f, p, status, base, na, nb);
         }
         __syncthreads();  // status / hit records of this chunk are block-visible from here on
     }

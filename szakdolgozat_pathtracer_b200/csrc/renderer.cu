@@ -505,18 +505,9 @@ int ptb_launch(ptb_context* ctx, const ptb_Params* P, const ptb_render_cfg* cfg_
             // 64 registers / 8 blocks per SM once there are enough chunks to keep that many blocks busy (the fused kernel
             // is occupancy-limited: +12 % at 8 batched subframes), the unconstrained 94-register build for small frames
             const bool wide = chunks >= (uint32_t)ctx->num_sms * (1024u / PTB_CHUNK_THREADS) * 4u;
-            static const int env_park = getenv("PTB_PARK") ? atoi(getenv("PTB_PARK")) : -1;  // experiments only
-            static const int env_merge = getenv("PTB_MERGE") ? atoi(getenv("PTB_MERGE")) : -1;
-            const int park = env_park >= 0 ? env_park : 0, merge = env_merge >= 0 ? env_merge : 1;
-#define PTB_CF_LAUNCH(COUNT, MINB, PARK, MERGE) k_chunk_fused<COUNT, PTB_TRACE_QUANTUM, MINB, PARK, MERGE><<<chunks, PTB_CHUNK_THREADS, 0, st>>>(s, f, p, ctx->status, ctx->launch_totals, ctx->trav_stats, max_iters)
-            if (cfg.count_traversal) PTB_CF_LAUNCH(true, 5, 0, true);
-            else if (!wide) PTB_CF_LAUNCH(false, 5, 0, true);
-            else if (park == 0 && merge == 1) PTB_CF_LAUNCH(false, 8, 0, true);
-            else if (park == 24 && merge == 1) PTB_CF_LAUNCH(false, 8, 24, true);
-            else if (park == 0 && merge == 0) PTB_CF_LAUNCH(false, 8, 0, false);
-            else if (park == 24 && merge == 0) PTB_CF_LAUNCH(false, 8, 24, false);
-            else return fail(PTB_ERR_INVALID, "ptb_launch: unsupported PTB_PARK / PTB_MERGE");
-#undef PTB_CF_LAUNCH
+            if (cfg.count_traversal) k_chunk_fused<true, PTB_TRACE_QUANTUM, 5><<<chunks, PTB_CHUNK_THREADS, 0, st>>>(s, f, p, ctx->status, ctx->launch_totals, ctx->trav_stats, max_iters);
+            else if (wide) k_chunk_fused<false, PTB_TRACE_QUANTUM, 8><<<chunks, PTB_CHUNK_THREADS, 0, st>>>(s, f, p, ctx->status, ctx->launch_totals, ctx->trav_stats, max_iters);
+            else k_chunk_fused<false, PTB_TRACE_QUANTUM, 5><<<chunks, PTB_CHUNK_THREADS, 0, st>>>(s, f, p, ctx->status, ctx->launch_totals, ctx->trav_stats, max_iters);
             launches += 1;
             prof_iters = 0;
             if (prof) {  // a single kernel: everything between raygen and resolve is reported as "trace"
