@@ -30,7 +30,7 @@ struct TreeletShared {
     float lo[3][PTB_TREELET_MAX], hi[3][PTB_TREELET_MAX];
     unsigned int vals[PTB_TREELET_MAX];
     unsigned short perm[PTB_TREELET_MAX], tmp[PTB_TREELET_MAX];
-    float bin_lo[3][PTB_SAH_BINS][3], bin_hi[3][PTB_SAH_BINS][3];
+    int bin_lo[3][PTB_SAH_BINS][3], bin_hi[3][PTB_SAH_BINS][3];  // order-preserving integer images of floats (sah_key)
     unsigned int bin_cnt[3][PTB_SAH_BINS];
     TreeletTask stack[PTB_TREELET_MAX];
 };
@@ -54,6 +54,11 @@ __global__ void k_find_treelets(const int2* __restrict__ ranges, const int* __re
     if (p >= 0) { const int2 pr = ranges[p]; if (pr.y - pr.x + 1 <= treelet_max) return; }
     list[atomicAdd(count, 1u)] = i;
 }
+
+// order-preserving map float -> int (and back; it is an involution on the bit pattern): integer atomicMin / atomicMax
+// then order the floats
+__device__ __forceinline__ int sah_key(float f) { const int b = __float_as_int(f); return b >= 0 ? b : b ^ 0x7fffffff; }
+__device__ __forceinline__ float sah_unkey(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
 
 __device__ __forceinline__ float box_half_area(const float* lo, const float* hi) {
     const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
@@ -118,48 +123,54 @@ k_refine_treelets(const int* __restrict__ list, const unsigned int* __restrict__
                 ranges[slot] = make_int2(a + begin, a + end - 1);
             }
             const float node_area = box_half_area(nlo, nhi);
-            // binning: two passes, lane owns (axis, bin)
-            for (int pass = 0; pass < 2; ++pass) {
-                const int ax = pass == 0 ? (int)(lane >> 4) : 2;
-                const int mybin = (int)(lane & 15u);
-                const bool owner = pass == 0 || lane < 16u;
-                const float ext = chi[ax] - clo[ax];
-                const float scale = ext > 0.0f ? (float)PTB_SAH_BINS / ext : 0.0f;
-                float bl[3] = {3.4e38f, 3.4e38f, 3.4e38f}, bh[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
-                unsigned int cnt = 0;
-                if (owner) {
-                    for (int j = begin; j < end; ++j) {
-                        const int id = sh.perm[j];
-                        const float c = 0.5f * (sh.lo[ax][id] + sh.hi[ax][id]);
-                        int b = (int)((c - clo[ax]) * scale);
-                        b = b < 0 ? 0 : (b > PTB_SAH_BINS - 1 ? PTB_SAH_BINS - 1 : b);
-                        if (b == mybin) {
-                            cnt++;
-                            for (int d = 0; d < 3; ++d) { bl[d] = fminf(bl[d], sh.lo[d][id]); bh[d] = fmaxf(bh[d], sh.hi[d][id]); }
-                        }
-                    }
-                    sh.bin_cnt[ax][mybin] = cnt;
-                    for (int d = 0; d < 3; ++d) { sh.bin_lo[ax][mybin][d] = bl[d]; sh.bin_hi[ax][mybin][d] = bh[d]; }
+            // binning: the lanes stride over the node's triangles and fold them into the 3 x 16 bins with shared-memory
+            // atomics (min / max on order-preserving integer images of the floats, so the result is exact and does not
+            // depend on the order of arrival)
+            for (int e = (int)lane; e < 3 * PTB_SAH_BINS; e += 32) {
+                const int ax = e / PTB_SAH_BINS, bn = e % PTB_SAH_BINS;
+                sh.bin_cnt[ax][bn] = 0u;
+                for (int d = 0; d < 3; ++d) { sh.bin_lo[ax][bn][d] = 0x7f7fffff; sh.bin_hi[ax][bn][d] = sah_key(-3.4e38f); }
+            }
+            float scale[3];
+            for (int ax = 0; ax < 3; ++ax) { const float ext = chi[ax] - clo[ax]; scale[ax] = ext > 0.0f ? (float)PTB_SAH_BINS / ext : 0.0f; }
+            __syncwarp();
+            for (int j = begin + (int)lane; j < end; j += 32) {
+                const int id = sh.perm[j];
+                int kl[3], kh[3];
+                for (int d = 0; d < 3; ++d) { kl[d] = sah_key(sh.lo[d][id]); kh[d] = sah_key(sh.hi[d][id]); }
+                for (int ax = 0; ax < 3; ++ax) {
+                    const float c = 0.5f * (sh.lo[ax][id] + sh.hi[ax][id]);
+                    int bn = (int)((c - clo[ax]) * scale[ax]);
+                    bn = bn < 0 ? 0 : (bn > PTB_SAH_BINS - 1 ? PTB_SAH_BINS - 1 : bn);
+                    atomicAdd(&sh.bin_cnt[ax][bn], 1u);
+                    for (int d = 0; d < 3; ++d) { atomicMin(&sh.bin_lo[ax][bn][d], kl[d]); atomicMax(&sh.bin_hi[ax][bn][d], kh[d]); }
                 }
             }
             __syncwarp();
-            // 45 candidates (axis, plane): split after bin `plane`
+            // 45 candidates (axis, plane): split after bin `plane`.  Per axis, lanes 0..15 hold the running union of bins
+            // 0..lane (prefix scan), lanes 16..31 the union of bins (31 - lane)..15 (suffix scan); lane p < 15 then pairs
+            // its left side with the right side of lane 30 - p.
             float best_cost = 3.4e38f; int best_cand = -1; unsigned int best_nl = 0;
-            for (int cand = (int)lane; cand < 3 * (PTB_SAH_BINS - 1); cand += 32) {
-                const int ax = cand / (PTB_SAH_BINS - 1), plane = cand % (PTB_SAH_BINS - 1);
-                if (!(chi[ax] - clo[ax] > 0.0f)) continue;
-                float ll[3] = {3.4e38f, 3.4e38f, 3.4e38f}, lh[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
-                float rl[3] = {3.4e38f, 3.4e38f, 3.4e38f}, rh[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
-                unsigned int nl = 0, nr = 0;
-                for (int b = 0; b < PTB_SAH_BINS; ++b) {
-                    const unsigned int c = sh.bin_cnt[ax][b];
-                    if (!c) continue;
-                    if (b <= plane) { nl += c; for (int d = 0; d < 3; ++d) { ll[d] = fminf(ll[d], sh.bin_lo[ax][b][d]); lh[d] = fmaxf(lh[d], sh.bin_hi[ax][b][d]); } }
-                    else { nr += c; for (int d = 0; d < 3; ++d) { rl[d] = fminf(rl[d], sh.bin_lo[ax][b][d]); rh[d] = fmaxf(rh[d], sh.bin_hi[ax][b][d]); } }
+            for (int ax = 0; ax < 3; ++ax) {
+                const int bn = lane < 16u ? (int)lane : 31 - (int)lane;
+                float bl[3], bh[3];
+                for (int d = 0; d < 3; ++d) { bl[d] = sah_unkey(sh.bin_lo[ax][bn][d]); bh[d] = sah_unkey(sh.bin_hi[ax][bn][d]); }
+                unsigned int cnt = sh.bin_cnt[ax][bn];
+                for (int off = 1; off < 16; off <<= 1) {
+                    const unsigned int oc = __shfl_up_sync(0xffffffffu, cnt, off, 16);
+                    float ol[3], oh[3];
+                    for (int d = 0; d < 3; ++d) { ol[d] = __shfl_up_sync(0xffffffffu, bl[d], off, 16); oh[d] = __shfl_up_sync(0xffffffffu, bh[d], off, 16); }
+                    if ((int)(lane & 15u) >= off) { cnt += oc; for (int d = 0; d < 3; ++d) { bl[d] = fminf(bl[d], ol[d]); bh[d] = fmaxf(bh[d], oh[d]); } }
                 }
-                if (nl == 0 || nr == 0) continue;
-                const float cost = box_half_area(ll, lh) * (float)nl + box_half_area(rl, rh) * (float)nr;
-                if (cost < best_cost) { best_cost = cost; best_cand = cand; best_nl = nl; }
+                const float my_area = cnt ? box_half_area(bl, bh) : 0.0f;
+                const int partner = 30 - (int)lane;  // valid for lanes 0..14
+                const float r_area = __shfl_sync(0xffffffffu, my_area, partner & 31);
+                const unsigned int r_cnt = __shfl_sync(0xffffffffu, cnt, partner & 31);
+                if (lane < (unsigned)(PTB_SAH_BINS - 1) && chi[ax] - clo[ax] > 0.0f && cnt > 0u && r_cnt > 0u) {
+                    const float cost = my_area * (float)cnt + r_area * (float)r_cnt;
+                    const int cand = ax * (PTB_SAH_BINS - 1) + (int)lane;
+                    if (cost < best_cost) { best_cost = cost; best_cand = cand; best_nl = cnt; }
+                }
             }
             for (int off = 16; off > 0; off >>= 1) {
                 const float oc = __shfl_xor_sync(0xffffffffu, best_cost, off);
