@@ -29,50 +29,69 @@ namespace ptb {
 #define PTB_CHUNK_THREADS 256    // 8 slots per thread in the compaction step (measured on C2: 256 > 512 > 128)
 #endif
 #ifndef PTB_CHUNK_SPT
-#define PTB_CHUNK_SPT 8          // slots per thread: 8 or 16 (status bytes are read as 64-bit words)
+#define PTB_CHUNK_SPT 8          // default slots per thread (1, 2, 4, 8 or 16)
 #endif
-#define PTB_CHUNK (PTB_CHUNK_THREADS * PTB_CHUNK_SPT)  // slots per block
+#define PTB_CHUNK (PTB_CHUNK_THREADS * PTB_CHUNK_SPT)  // slots per block at the default SPT
+// The chunk helpers are templates on SPT = slots per thread (chunk = PTB_CHUNK_THREADS * SPT slots): the fused kernel uses
+// smaller chunks for small launches (a 600 x 400 frame has 117 chunks of 2048 slots -- less than one block per SM -- but
+// 938 chunks of 256), everything else uses the default through the aliases below.
 
 enum SlotStatus : unsigned char { ST_DONE = 0, ST_TRACE = 1, ST_HIT = 2, ST_MISS = 3 };
 
-struct ChunkShared {
-    unsigned short list[PTB_CHUNK];  // slot offsets inside the chunk, ascending
+template <int SPT = PTB_CHUNK_SPT>
+struct ChunkSharedT {
+    static constexpr unsigned int CHUNK = PTB_CHUNK_THREADS * SPT;
+    unsigned short list[PTB_CHUNK_THREADS * SPT];  // slot offsets inside the chunk, ascending
     unsigned int warp_sums[PTB_CHUNK_THREADS / 32];
     unsigned int warp_sums_b[PTB_CHUNK_THREADS / 32];
     unsigned int n;                  // list length
     unsigned int next;               // dynamic fetch cursor of the trace stage
     unsigned int count[4];           // per-block totals: segments, hits, misses, -
 };
+using ChunkShared = ChunkSharedT<>;
 
 // Compacts the offsets of the chunk's slots whose status == want into sh.list (ascending).  Block-uniform result.
 // bit k of the result is set when status byte k of this thread's PTB_CHUNK_SPT slots equals want (slots beyond n_slots
 // read as ST_DONE; `want` is never ST_DONE)
-PTB_DEV unsigned int chunk_status_words(const unsigned char* __restrict__ status, uint32_t first, uint32_t n_slots, unsigned long long* words) {
+// status bytes of this thread's SPT slots, packed little-endian into 64-bit words (slots beyond n_slots read as ST_DONE)
+template <int SPT>
+PTB_DEV void chunk_status_words(const unsigned char* __restrict__ status, uint32_t first, uint32_t n_slots, unsigned long long* words) {
+    if (SPT >= 8) {
 #pragma unroll
-    for (int w = 0; w < PTB_CHUNK_SPT / 8; ++w) {
-        const uint32_t f0 = first + 8u * w;
+        for (int w = 0; w < (SPT + 7) / 8; ++w) {
+            const uint32_t f0 = first + 8u * w;
+            unsigned long long bytes = 0ull;
+            if (f0 + 8u <= n_slots) bytes = *reinterpret_cast<const unsigned long long*>(status + f0);
+            else if (f0 < n_slots) for (uint32_t k = 0; f0 + k < n_slots; ++k) bytes |= (unsigned long long)status[f0 + k] << (8u * k);
+            words[w] = bytes;
+        }
+    } else {
         unsigned long long bytes = 0ull;
-        if (f0 + 8u <= n_slots) bytes = *reinterpret_cast<const unsigned long long*>(status + f0);
-        else if (f0 < n_slots) for (uint32_t k = 0; f0 + k < n_slots; ++k) bytes |= (unsigned long long)status[f0 + k] << (8u * k);
-        words[w] = bytes;
+        if (first + (uint32_t)SPT <= n_slots) {
+            if (SPT == 4) bytes = *reinterpret_cast<const unsigned int*>(status + first);
+            else if (SPT == 2) bytes = *reinterpret_cast<const unsigned short*>(status + first);
+            else bytes = status[first];
+        } else if (first < n_slots) for (uint32_t k = 0; first + k < n_slots; ++k) bytes |= (unsigned long long)status[first + k] << (8u * k);
+        words[0] = bytes;
     }
-    return 0u;
 }
+// bit k of the result is set when status byte k equals want (`want` is never ST_DONE, so padding never matches)
+template <int SPT>
 PTB_DEV unsigned int chunk_match(const unsigned long long* words, unsigned char want) {
     unsigned int m = 0;
 #pragma unroll
-    for (int w = 0; w < PTB_CHUNK_SPT / 8; ++w)
-#pragma unroll
-        for (int k = 0; k < 8; ++k) m |= (((unsigned int)(words[w] >> (8 * k)) & 0xffu) == (unsigned int)want ? 1u : 0u) << (8 * w + k);
+    for (int k = 0; k < SPT; ++k) m |= (((unsigned int)(words[k >> 3] >> (8 * (k & 7))) & 0xffu) == (unsigned int)want ? 1u : 0u) << k;
     return m;
 }
 
-PTB_DEV unsigned int chunk_build_list(ChunkShared& sh, const unsigned char* __restrict__ status, uint32_t base,
+// Compacts the offsets of the chunk's slots whose status == want into sh.list (ascending).  Block-uniform result.
+template <int SPT>
+PTB_DEV unsigned int chunk_build_list(ChunkSharedT<SPT>& sh, const unsigned char* __restrict__ status, uint32_t base,
                                       uint32_t n_slots, unsigned char want) {
     const unsigned int tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    unsigned long long words[PTB_CHUNK_SPT / 8];
-    chunk_status_words(status, base + tid * (unsigned int)PTB_CHUNK_SPT, n_slots, words);
-    unsigned int match = chunk_match(words, want);
+    unsigned long long words[(SPT + 7) / 8];
+    chunk_status_words<SPT>(status, base + tid * (unsigned int)SPT, n_slots, words);
+    unsigned int match = chunk_match<SPT>(words, want);
     const unsigned int mine = (unsigned int)__popc(match);
     unsigned int incl = mine;
 #pragma unroll
@@ -84,20 +103,21 @@ PTB_DEV unsigned int chunk_build_list(ChunkShared& sh, const unsigned char* __re
     for (unsigned int w = 0; w < PTB_CHUNK_THREADS / 32; ++w) { const unsigned int v = sh.warp_sums[w]; if (w < warp) warp_off += v; total += v; }
     unsigned int pos = warp_off + incl - mine;
     unsigned int m = match;
-    while (m) { const int k = __ffs(m) - 1; m &= m - 1u; sh.list[pos++] = (unsigned short)(tid * (unsigned int)PTB_CHUNK_SPT + (unsigned int)k); }
+    while (m) { const int k = __ffs(m) - 1; m &= m - 1u; sh.list[pos++] = (unsigned short)(tid * (unsigned int)SPT + (unsigned int)k); }
     if (tid == 0) { sh.n = total; sh.next = 0; }
     __syncthreads();
     return total;
 }
 
 // One pass over the chunk's status bytes builds TWO lists: slots in state want_a ascending from the front of sh.list,
-// slots in state want_b ascending at its back (sh.list[PTB_CHUNK - nb ..)); want_b = 0xff matches nothing.  Block-uniform.
-PTB_DEV void chunk_build_two(ChunkShared& sh, const unsigned char* __restrict__ status, uint32_t base, uint32_t n_slots,
+// slots in state want_b ascending at its back (sh.list[CHUNK - nb ..)); want_b = 0xff matches nothing.  Block-uniform.
+template <int SPT>
+PTB_DEV void chunk_build_two(ChunkSharedT<SPT>& sh, const unsigned char* __restrict__ status, uint32_t base, uint32_t n_slots,
                              unsigned char want_a, unsigned char want_b, unsigned int* na, unsigned int* nb) {
     const unsigned int tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    unsigned long long words[PTB_CHUNK_SPT / 8];
-    chunk_status_words(status, base + tid * (unsigned int)PTB_CHUNK_SPT, n_slots, words);
-    unsigned int ma = chunk_match(words, want_a), mb = chunk_match(words, want_b);
+    unsigned long long words[(SPT + 7) / 8];
+    chunk_status_words<SPT>(status, base + tid * (unsigned int)SPT, n_slots, words);
+    unsigned int ma = chunk_match<SPT>(words, want_a), mb = chunk_match<SPT>(words, want_b);
     // one packed inclusive warp scan for both counts (each <= 512 per warp: 16 bits are plenty)
     const unsigned int mine = (unsigned int)__popc(ma) | ((unsigned int)__popc(mb) << 16);
     unsigned int incl = mine;
@@ -113,17 +133,17 @@ PTB_DEV void chunk_build_two(ChunkShared& sh, const unsigned char* __restrict__ 
         tot_a += va; tot_b += vb;
     }
     unsigned int pa = off_a + (incl & 0xffffu) - (mine & 0xffffu);
-    unsigned int pb = (unsigned int)PTB_CHUNK - tot_b + off_b + (incl >> 16) - (mine >> 16);
-    while (ma) { const int k = __ffs(ma) - 1; ma &= ma - 1u; sh.list[pa++] = (unsigned short)(tid * (unsigned int)PTB_CHUNK_SPT + (unsigned int)k); }
-    while (mb) { const int k = __ffs(mb) - 1; mb &= mb - 1u; sh.list[pb++] = (unsigned short)(tid * (unsigned int)PTB_CHUNK_SPT + (unsigned int)k); }
+    unsigned int pb = ChunkSharedT<SPT>::CHUNK - tot_b + off_b + (incl >> 16) - (mine >> 16);
+    while (ma) { const int k = __ffs(ma) - 1; ma &= ma - 1u; sh.list[pa++] = (unsigned short)(tid * (unsigned int)SPT + (unsigned int)k); }
+    while (mb) { const int k = __ffs(mb) - 1; mb &= mb - 1u; sh.list[pb++] = (unsigned short)(tid * (unsigned int)SPT + (unsigned int)k); }
     if (tid == 0) { sh.n = tot_a; sh.next = 0; }
     __syncthreads();
     *na = tot_a; *nb = tot_b;
 }
 
 // ---- stage bodies over one chunk ---------------------------------------------------------------------------
-template <bool COUNT, int QUANTUM>
-PTB_DEV void chunk_stage_trace(ChunkShared& sh, const SceneView& s, const FrameView& f, const PathView& p,
+template <bool COUNT, int QUANTUM, int SPT>
+PTB_DEV void chunk_stage_trace(ChunkSharedT<SPT>& sh, const SceneView& s, const FrameView& f, const PathView& p,
                                unsigned char* __restrict__ status, uint32_t base, unsigned int n, bool first_iteration,
                                TravCounters& tc) {
     const unsigned lane = threadIdx.x & 31u;
@@ -168,7 +188,8 @@ PTB_DEV void chunk_stage_trace(ChunkShared& sh, const SceneView& s, const FrameV
     if (lane == 0u && hits) atomicAdd(&sh.count[1], hits);
 }
 
-PTB_DEV void chunk_stage_shade(ChunkShared& sh, const SceneView& s, const FrameView& f, const PathView& p,
+template <int SPT>
+PTB_DEV void chunk_stage_shade(ChunkSharedT<SPT>& sh, const SceneView& s, const FrameView& f, const PathView& p,
                                unsigned char* __restrict__ status, uint32_t base, unsigned int n, unsigned int list_off = 0) {
     for (unsigned int i = threadIdx.x; i < n; i += PTB_CHUNK_THREADS) {
         const uint32_t slot = base + sh.list[list_off + i];
@@ -182,7 +203,8 @@ PTB_DEV void chunk_stage_shade(ChunkShared& sh, const SceneView& s, const FrameV
     }
 }
 
-PTB_DEV void chunk_stage_miss(ChunkShared& sh, const SceneView& s, const FrameView& f, const PathView& p,
+template <int SPT>
+PTB_DEV void chunk_stage_miss(ChunkSharedT<SPT>& sh, const SceneView& s, const FrameView& f, const PathView& p,
                               unsigned char* __restrict__ status, uint32_t base, unsigned int n, unsigned int list_off = 0) {
     for (unsigned int i = threadIdx.x; i < n; i += PTB_CHUNK_THREADS) {
         const uint32_t slot = base + sh.list[list_off + i];
@@ -206,12 +228,13 @@ PTB_DEV void chunk_stage_miss(ChunkShared& sh, const SceneView& s, const FrameVi
 // stream, there is one stage barrier less per iteration, and the per-stage rounding loss (a list of n items keeps
 // ceil(n / threads) rounds busy) is paid once instead of twice.  Only the warp that straddles the hit/miss boundary
 // executes both bodies.
-PTB_DEV void chunk_stage_shade_miss(ChunkShared& sh, const SceneView& s, const FrameView& f, const PathView& p,
+template <int SPT>
+PTB_DEV void chunk_stage_shade_miss(ChunkSharedT<SPT>& sh, const SceneView& s, const FrameView& f, const PathView& p,
                                     unsigned char* __restrict__ status, uint32_t base, unsigned int n_hit, unsigned int n_miss) {
     const unsigned int total = n_hit + n_miss;
     for (unsigned int i = threadIdx.x; i < total; i += PTB_CHUNK_THREADS) {
         const bool is_hit = i < n_hit;
-        const uint32_t slot = base + sh.list[is_hit ? i : (unsigned int)PTB_CHUNK - total + i];
+        const uint32_t slot = base + sh.list[is_hit ? i : ChunkSharedT<SPT>::CHUNK - total + i];
         const float4 d4 = p.ray_d[slot], as = p.atten_seed[slot];
         const uint4 mi = p.misc[slot];
         Bounce b;
@@ -232,7 +255,8 @@ PTB_DEV void chunk_stage_shade_miss(ChunkShared& sh, const SceneView& s, const F
     }
 }
 
-PTB_DEV void chunk_flush_counts(ChunkShared& sh, unsigned long long* __restrict__ totals, unsigned long long* trav_stats,
+template <int SPT>
+PTB_DEV void chunk_flush_counts(ChunkSharedT<SPT>& sh, unsigned long long* __restrict__ totals, unsigned long long* trav_stats,
                                 const TravCounters& tc, bool count) {
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -297,12 +321,12 @@ __global__ void __launch_bounds__(PTB_CHUNK_THREADS) k_chunk_miss(SceneView s, F
 // One block = one chunk, from the first camera ray to the last sample of its pixels.  Two list passes per wavefront
 // iteration (one code copy, alternating phases): {TRACE, BUSY} before the trace stage, {HIT, MISS} before shade + miss.
 // totals[3] is not touched here (launch count is added by k_fold_counters' sibling on the host path).
-template <bool COUNT, int QUANTUM, int MINB>
+template <bool COUNT, int QUANTUM, int MINB, int SPT>
 __global__ void __launch_bounds__(PTB_CHUNK_THREADS, (MINB * 128) / PTB_CHUNK_THREADS) k_chunk_fused(SceneView s, FrameView f, PathView p, unsigned char* status,
                                                                   unsigned long long* totals, unsigned long long* trav_stats,
                                                                   unsigned int* max_iters_seen) {
-    __shared__ ChunkShared sh;
-    const uint32_t base = blockIdx.x * PTB_CHUNK;
+    __shared__ ChunkSharedT<SPT> sh;
+    const uint32_t base = blockIdx.x * ChunkSharedT<SPT>::CHUNK;
     if (threadIdx.x < 4) sh.count[threadIdx.x] = 0;
     TravCounters tc; tc.nodes = 0; tc.tris = 0;
     unsigned int iter = 0;

@@ -48,8 +48,8 @@ PTB_DEV void pool_build_two(PoolShared& sh, unsigned char want_a, unsigned char 
     unsigned long long words[PTB_CHUNK_SPT / 8];
 #pragma unroll
     for (int w = 0; w < PTB_CHUNK_SPT / 8; ++w) words[w] = *reinterpret_cast<const unsigned long long*>(sh.status + tid * PTB_CHUNK_SPT + 8 * w);
-    unsigned int ma = chunk_match(words, want_a), mb = chunk_match(words, want_b1);
-    if (want_b2 != want_b1) mb |= chunk_match(words, want_b2);
+    unsigned int ma = chunk_match<PTB_CHUNK_SPT>(words, want_a), mb = chunk_match<PTB_CHUNK_SPT>(words, want_b1);
+    if (want_b2 != want_b1) mb |= chunk_match<PTB_CHUNK_SPT>(words, want_b2);
     const unsigned int mine = (unsigned int)__popc(ma) | ((unsigned int)__popc(mb) << 16);
     unsigned int incl = mine;
 #pragma unroll

@@ -485,11 +485,11 @@ int ptb_launch(ptb_context* ctx, const ptb_Params* P, const ptb_render_cfg* cfg_
         p.pixsum = ctx->out_pixsum;  // what k_resolve folds
     } else {
         // block-local wavefront over chunks of the path pool (chunked.cuh)
-        const uint32_t chunks = (slots + PTB_CHUNK - 1u) / PTB_CHUNK;
-        k_chunk_raygen<<<pix_blocks, 256, 0, st>>>(f, p, ctx->status);
-        if (prof) CU(cudaEventRecord(ctx->events[1], st));
-        launches = 1;
         if (pipeline == PTB_PIPELINE_CHUNK_STAGES) {
+            const uint32_t chunks = (slots + PTB_CHUNK - 1u) / PTB_CHUNK;
+            k_chunk_raygen<<<pix_blocks, 256, 0, st>>>(f, p, ctx->status);
+            if (prof) CU(cudaEventRecord(ctx->events[1], st));
+            launches = 1;
             for (uint32_t it = 0; it < iters; ++it) {
                 if (cfg.count_traversal) k_chunk_trace<true, PTB_TRACE_QUANTUM><<<chunks, PTB_CHUNK_THREADS, 0, st>>>(s, f, p, ctx->status, ctx->launch_totals, ctx->trav_stats, (int)it);
                 else k_chunk_trace<false, PTB_TRACE_QUANTUM><<<chunks, PTB_CHUNK_THREADS, 0, st>>>(s, f, p, ctx->status, ctx->launch_totals, ctx->trav_stats, (int)it);
@@ -501,13 +501,34 @@ int ptb_launch(ptb_context* ctx, const ptb_Params* P, const ptb_render_cfg* cfg_
                 launches += 3;
             }
         } else {
+            // Chunk size by launch size: 8 slots per thread (2048-slot chunks) when that still gives 8 waves of blocks,
+            // otherwise fewer slots per thread so that a small frame (the reference's 600 x 400 / 1600 x 1200 launches of
+            // one subframe) spreads over the whole chip instead of running its per-pixel sample chains on a few warps per
+            // SM.  Measured (profiles/r1_experiments.md): 600 x 400 4.66 -> 2.50 ms, 1600 x 1200 7.36 -> 6.20 ms per launch.
+            static const int env_spt = getenv("PTB_SPT") ? atoi(getenv("PTB_SPT")) : 0;  // experiments only
+            const uint32_t blocks_per_sm = 1024u / PTB_CHUNK_THREADS;
+            const uint32_t full = (uint32_t)ctx->num_sms * blocks_per_sm;                  // resident blocks at 64 registers
+            int spt = 8;
+            while (spt > 1 && (slots + PTB_CHUNK_THREADS * (uint32_t)spt - 1u) / (PTB_CHUNK_THREADS * (uint32_t)spt) < 8u * full) spt >>= 1;
+            if (env_spt) spt = env_spt;
+            const uint32_t chunk = PTB_CHUNK_THREADS * (uint32_t)spt;
+            const uint32_t chunks = (slots + chunk - 1u) / chunk;
+            k_chunk_raygen<<<pix_blocks, 256, 0, st>>>(f, p, ctx->status);
+            if (prof) CU(cudaEventRecord(ctx->events[1], st));
+            launches = 1;
             unsigned int* max_iters = (unsigned int*)(ctx->launch_totals + 3);
-            // 64 registers / 8 blocks per SM once there are enough chunks to keep that many blocks busy (the fused kernel
-            // is occupancy-limited: +12 % at 8 batched subframes), the unconstrained 94-register build for small frames
-            const bool wide = chunks >= (uint32_t)ctx->num_sms * (1024u / PTB_CHUNK_THREADS) * 4u;
-            if (cfg.count_traversal) k_chunk_fused<true, PTB_TRACE_QUANTUM, 5><<<chunks, PTB_CHUNK_THREADS, 0, st>>>(s, f, p, ctx->status, ctx->launch_totals, ctx->trav_stats, max_iters);
-            else if (wide) k_chunk_fused<false, PTB_TRACE_QUANTUM, 8><<<chunks, PTB_CHUNK_THREADS, 0, st>>>(s, f, p, ctx->status, ctx->launch_totals, ctx->trav_stats, max_iters);
-            else k_chunk_fused<false, PTB_TRACE_QUANTUM, 5><<<chunks, PTB_CHUNK_THREADS, 0, st>>>(s, f, p, ctx->status, ctx->launch_totals, ctx->trav_stats, max_iters);
+            // 64 registers / 4 blocks per SM once there are enough chunks to keep that many blocks busy, the
+            // unconstrained ~100-register build for launches that cannot fill the chip anyway
+            const bool wide = chunks >= full;
+#define PTB_CF_LAUNCH(COUNT, MINB, SPT) k_chunk_fused<COUNT, PTB_TRACE_QUANTUM, MINB, SPT><<<chunks, PTB_CHUNK_THREADS, 0, st>>>(s, f, p, ctx->status, ctx->launch_totals, ctx->trav_stats, max_iters)
+#define PTB_CF_BY_SPT(COUNT, MINB) do { if (spt == 8) PTB_CF_LAUNCH(COUNT, MINB, 8); else if (spt == 4) PTB_CF_LAUNCH(COUNT, MINB, 4); \
+                                        else if (spt == 2) PTB_CF_LAUNCH(COUNT, MINB, 2); else PTB_CF_LAUNCH(COUNT, MINB, 1); } while (0)
+            if (spt != 8 && spt != 4 && spt != 2 && spt != 1) return fail(PTB_ERR_INVALID, "ptb_launch: unsupported PTB_SPT");
+            if (cfg.count_traversal) PTB_CF_LAUNCH(true, 5, 8);
+            else if (wide) PTB_CF_BY_SPT(false, 8);
+            else PTB_CF_BY_SPT(false, 5);
+#undef PTB_CF_BY_SPT
+#undef PTB_CF_LAUNCH
             launches += 1;
             prof_iters = 0;
             if (prof) {  // a single kernel: everything between raygen and resolve is reported as "trace"
