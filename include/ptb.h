@@ -136,8 +136,9 @@ typedef struct ptb_render_cfg {
                                  per-pixel sample chains. */
     int32_t pipeline;         /* 0 = default.  1: global ray queues, one kernel per stage and iteration;
                                  2: block-local wavefront over chunks of the path pool, one kernel per stage and
-                                    iteration; 3: the same stages fused into one persistent kernel per launch.
-                                 All three produce bit-identical results. */
+                                    iteration; 3: the same stages fused into one kernel per launch (default);
+                                 4: persistent path pool (blocks own positions, slots are handed out from one counter;
+                                    path state does not grow with the frame).  All produce bit-identical results. */
     int32_t row_begin, row_end; /* 0, 0 = the whole frame.  Otherwise only image rows [row_begin, row_end) are rendered (and only
                                  those rows of accum/frame/aux are touched): tile partitioning for multi-GPU single-pass frames.
                                  Every pixel is still seeded by its full-frame coordinates, so bands tile bit-identically. */
@@ -145,6 +146,8 @@ typedef struct ptb_render_cfg {
                                  `height` rows and this launch renders strips index, index + count, ... (load-balanced tile
                                  partitioning: sky strips are cheap, strips over the mesh are not).  Chunked pipelines only. */
     int32_t* aux_primary_hit; /* optional DEVICE int32[W*H]: primitive hit by the first segment of sample 0, -1 = miss */
+    int32_t chunk_slots_per_thread; /* pipeline 3: 0 = chosen from the launch size (default); 1, 2, 4 or 8 = slots per thread of
+                                 a 256-thread block, i.e. 256 .. 2048 path slots per chunk.  Results do not depend on it. */
 } ptb_render_cfg;
 
 typedef struct ptb_launch_stats {

@@ -511,6 +511,7 @@ int ptb_launch(ptb_context* ctx, const ptb_Params* P, const ptb_render_cfg* cfg_
             int spt = 8;
             while (spt > 1 && (slots + PTB_CHUNK_THREADS * (uint32_t)spt - 1u) / (PTB_CHUNK_THREADS * (uint32_t)spt) < 8u * full) spt >>= 1;
             if (env_spt) spt = env_spt;
+            if (cfg.chunk_slots_per_thread) spt = cfg.chunk_slots_per_thread;
             const uint32_t chunk = PTB_CHUNK_THREADS * (uint32_t)spt;
             const uint32_t chunks = (slots + chunk - 1u) / chunk;
             k_chunk_raygen<<<pix_blocks, 256, 0, st>>>(f, p, ctx->status);
@@ -523,7 +524,7 @@ int ptb_launch(ptb_context* ctx, const ptb_Params* P, const ptb_render_cfg* cfg_
 #define PTB_CF_LAUNCH(COUNT, MINB, SPT) k_chunk_fused<COUNT, PTB_TRACE_QUANTUM, MINB, SPT><<<chunks, PTB_CHUNK_THREADS, 0, st>>>(s, f, p, ctx->status, ctx->launch_totals, ctx->trav_stats, max_iters)
 #define PTB_CF_BY_SPT(COUNT, MINB) do { if (spt == 8) PTB_CF_LAUNCH(COUNT, MINB, 8); else if (spt == 4) PTB_CF_LAUNCH(COUNT, MINB, 4); \
                                         else if (spt == 2) PTB_CF_LAUNCH(COUNT, MINB, 2); else PTB_CF_LAUNCH(COUNT, MINB, 1); } while (0)
-            if (spt != 8 && spt != 4 && spt != 2 && spt != 1) return fail(PTB_ERR_INVALID, "ptb_launch: unsupported PTB_SPT");
+            if (spt != 8 && spt != 4 && spt != 2 && spt != 1) return fail(PTB_ERR_INVALID, "ptb_launch: chunk_slots_per_thread must be 0, 1, 2, 4 or 8");
             if (cfg.count_traversal) PTB_CF_LAUNCH(true, 5, 8);
             else if (wide) PTB_CF_BY_SPT(false, 8);
             else PTB_CF_BY_SPT(false, 5);

@@ -168,6 +168,40 @@ def test_bvh_structure_and_ray_queries(ptb, ctx, oh, assets, name, small, refine
     assert (prim >= 0).mean() > 0.2
 
 
+def test_bvh_builder_options(ptb, ctx, oh, assets):
+    """Builder variants must all give a valid tree and the same hits: 63-bit Morton keys, small treelets, leaf size 1 and 8;
+    and the huge-primitive split: the two floor triangles (the last two prims, optixSphere.cpp:598-646) sit in ONE leaf that
+    is a child of the root."""
+    if PIPELINE != 3:
+        pytest.skip("the BVH does not depend on the render pipeline")
+    sc = load_config(ptb, assets, "c2")
+    n = sc.num_triangles
+    rng = np.random.default_rng(5)
+    osc = oh.OracleScene.from_ptb(sc, guard=False)
+    v = osc.vertices[:, :3]
+    o, d = random_rays(rng, 4000, v[:-6].min(0), v[:-6].max(0))
+    ref = None
+    for kw in (dict(), dict(morton_bits=63), dict(treelet_size=32), dict(max_leaf_size=1), dict(max_leaf_size=8), dict(sah_refine=0, morton_bits=63)):
+        handle, st = ctx.accel_build(sc, ptb.default_build_cfg(**kw))
+        nodes, tris = ctx.accel_read(handle)
+        assert _check_bvh(nodes, tris, n, kw.get("max_leaf_size", 4)) == st.num_nodes, kw
+        if kw.get("max_leaf_size", 4) != 1:  # with leaf size 1 the two floor triangles are two leaves under one node next to the root
+            codes = nodes[0, 12:14].view(np.int32)
+            leaf = [c for c in codes if c < 0]
+            assert len(leaf) == 1, f"root must have exactly one leaf child (the huge primitives): {codes} {kw}"
+            first, cnt = (~leaf[0]) >> 3, ((~leaf[0]) & 7) + 1
+            assert cnt == 2 and sorted(tris[first:first + 2, 3].view(np.int32).tolist()) == [n - 2, n - 1], kw
+        got = ctx.trace_rays(handle, o, d)
+        if ref is None:
+            ref = got
+            for i in range(0, len(o), 40):
+                rp, rt, _, _ = oh.closest_hit("oracle", osc, o[i], d[i], use_bvh=0)
+                assert rp == got[0][i] and (rp < 0 or np.float32(rt) == got[1][i])
+        else:
+            for a, b in zip(ref, got):
+                assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), kw
+
+
 def test_c1_image_bit_exact_default_config(ptb, ctx, oh, assets):
     """Reference literals (10 spp, depth 20, DoF on), two subframes: accum bit-exact, frame within 1 LSB."""
     sc = load_config(ptb, assets, "c1", small=True)
@@ -260,6 +294,33 @@ def test_batched_subframes_bit_identical_to_consecutive_launches(ptb, ctx, asset
     assert seg == sum(s.segments for s in seq_st)
     assert np.array_equal(a.view(np.uint32), seq_a.view(np.uint32))
     assert np.array_equal(f, seq_f)
+
+
+def test_chunk_sizes_bit_identical(ptb, ctx, assets):
+    """The fused kernel picks its chunk size from the launch size (256 .. 2048 slots per block): every choice, and a ragged
+    last chunk, must give the same accumulator, frame, hit IDs and segment count."""
+    if PIPELINE != 3:
+        pytest.skip("chunk_slots_per_thread is a knob of pipeline 3")
+    sc = load_config(ptb, assets, "c2")
+    handle, _ = ctx.accel_build(sc)
+    W, H = 251, 67  # 16 817 slots: not a multiple of any chunk size
+    ref = None
+    for spt in (0, 1, 2, 4, 8):
+        a, f, h, st = _render_gpu(ptb, ctx, handle, W, H, dict(spp_per_launch=3, max_depth=6, chunk_slots_per_thread=spt), subframes=2, camera="monkey_close")
+        cur = (a.view(np.uint32), f, h, [s.segments for s in st])
+        if ref is None:
+            ref = cur
+        else:
+            assert all(np.array_equal(x, y) for x, y in zip(ref[:3], cur[:3])) and ref[3] == cur[3], spt
+    n = W * H
+    p = ptb.make_params(W, H)
+    d_accum, d_frame = ctx.alloc(n * 16), ctx.alloc(n * 4)
+    try:
+        p.accum_buffer, p.frame_buffer, p.handle = d_accum, d_frame, handle
+        with pytest.raises(ptb.PtbError):
+            ctx.launch(p, ptb.default_render_cfg(chunk_slots_per_thread=3, pipeline=3))
+    finally:
+        ctx.free(d_accum); ctx.free(d_frame)
 
 
 def test_demo_scene_parity(ptb, ctx, oh, assets):
@@ -398,8 +459,8 @@ def test_c3_full_pbr_parity_crop(ptb, ctx, oh, assets):
 
 def test_c2_full_frame_primary_hits(ptb, ctx, oh, assets):
     """BASELINE config 2 at its full size: all 2 073 600 primary-hit triangle IDs (DoF on) and the 1-sample image, bit-exact."""
-    if PIPELINE != 4:
-        pytest.skip("full-frame check on the default pipeline")
+    if PIPELINE not in (3, 4):
+        pytest.skip("full-frame check on the fused pipelines (3 = default, 2048-slot chunks at this size; 4 = persistent pool)")
     sc = load_config(ptb, assets, "c2")
     handle, _ = ctx.accel_build(sc)
     osc = oh.OracleScene.from_ptb(sc, guard=False)
