@@ -167,7 +167,7 @@ PTB_DEV void chunk_stage_trace(ChunkSharedT<SPT>& sh, const SceneView& s, const 
                 const unsigned int idx = b0 + (unsigned int)__popc(need & lt_mask);
                 if (!have && idx < n) {
                     slot = base + sh.list[idx];
-                    const float4 o4 = p.ray_o[slot], d4 = p.ray_d[slot];
+                    const float4 o4 = ldp(&p.ray_o[slot]), d4 = ldp(&p.ray_d[slot]);
                     trav_begin(t, stack, mk3(o4), mk3(d4), f.tmin, f.tmax);
                     have = true;
                 }
@@ -177,7 +177,7 @@ PTB_DEV void chunk_stage_trace(ChunkSharedT<SPT>& sh, const SceneView& s, const 
         if (!__any_sync(0xffffffffu, have)) break;
         if (have && trav_run<COUNT>(t, stack, s.nodes, s.tris, QUANTUM, &tc)) {
             have = false;
-            p.hit[slot] = make_float4(t.best.t, t.best.b1, t.best.b2, __int_as_float(t.best.prim));
+            stp(&p.hit[slot], make_float4(t.best.t, t.best.b1, t.best.b2, __int_as_float(t.best.prim)));
             const bool is_hit = t.best.prim >= 0;
             status[slot] = is_hit ? ST_HIT : ST_MISS;
             hits += is_hit ? 1u : 0u;
@@ -193,8 +193,8 @@ PTB_DEV void chunk_stage_shade(ChunkSharedT<SPT>& sh, const SceneView& s, const 
                                unsigned char* __restrict__ status, uint32_t base, unsigned int n, unsigned int list_off = 0) {
     for (unsigned int i = threadIdx.x; i < n; i += PTB_CHUNK_THREADS) {
         const uint32_t slot = base + sh.list[list_off + i];
-        const float4 o4 = p.ray_o[slot], d4 = p.ray_d[slot], h4 = p.hit[slot], as = p.atten_seed[slot];
-        const uint4 mi = p.misc[slot];
+        const float4 o4 = ldp(&p.ray_o[slot]), d4 = ldp(&p.ray_d[slot]), h4 = ldp(&p.hit[slot]), as = ldp(&p.atten_seed[slot]);
+        const uint4 mi = ldp(&p.misc[slot]);
         Bounce b;
         b.atten = mk3(as); b.seed = __float_as_uint(as.w);
         const int depth = (int)mi.y;
@@ -208,8 +208,8 @@ PTB_DEV void chunk_stage_miss(ChunkSharedT<SPT>& sh, const SceneView& s, const F
                               unsigned char* __restrict__ status, uint32_t base, unsigned int n, unsigned int list_off = 0) {
     for (unsigned int i = threadIdx.x; i < n; i += PTB_CHUNK_THREADS) {
         const uint32_t slot = base + sh.list[list_off + i];
-        const float4 d4 = p.ray_d[slot], as = p.atten_seed[slot];
-        const uint4 mi = p.misc[slot];
+        const float4 d4 = ldp(&p.ray_d[slot]), as = ldp(&p.atten_seed[slot]);
+        const uint4 mi = ldp(&p.misc[slot]);
         const float3 ray_dir = normalize(mk3(d4));
         const float u = 0.5f + det_atan2f(ray_dir.z, ray_dir.x) / (2.0f * PTB_PI_F);
         const float v = 0.5f - det_asinf(ray_dir.y) / PTB_PI_F;
@@ -235,12 +235,12 @@ PTB_DEV void chunk_stage_shade_miss(ChunkSharedT<SPT>& sh, const SceneView& s, c
     for (unsigned int i = threadIdx.x; i < total; i += PTB_CHUNK_THREADS) {
         const bool is_hit = i < n_hit;
         const uint32_t slot = base + sh.list[is_hit ? i : ChunkSharedT<SPT>::CHUNK - total + i];
-        const float4 d4 = p.ray_d[slot], as = p.atten_seed[slot];
-        const uint4 mi = p.misc[slot];
+        const float4 d4 = ldp(&p.ray_d[slot]), as = ldp(&p.atten_seed[slot]);
+        const uint4 mi = ldp(&p.misc[slot]);
         Bounce b;
         b.atten = mk3(as); b.seed = __float_as_uint(as.w);
         if (is_hit) {
-            const float4 o4 = p.ray_o[slot], h4 = p.hit[slot];
+            const float4 o4 = ldp(&p.ray_o[slot]), h4 = ldp(&p.hit[slot]);
             closest_hit(s, f, __float_as_int(h4.w), h4.y, h4.z, h4.x, mk3(o4), mk3(d4), (int)mi.y, b);
         } else {
             const float3 ray_dir = normalize(mk3(d4));
@@ -278,15 +278,15 @@ __global__ void __launch_bounds__(256) k_chunk_raygen(FrameView f, PathView p, u
     if (i >= p.n_slots) return;
     const uint32_t pix = i % f.n_pixels, sub = i / f.n_pixels;
     const uint32_t ix = pix % f.W, iy = image_row(f, pix / f.W);
-    p.pixsum[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    stp(&p.pixsum[i], make_float4(0.0f, 0.0f, 0.0f, 0.0f));
     if (iy >= f.H) { status[i] = ST_DONE; return; }  // padding rows of the last interleaved strip
     uint32_t seed = iy * f.W + ix + ((uint32_t)f.subframe + sub) * f.W * f.H;  // cu:316
     float3 o, d;
     start_sample(f, ix, iy, seed, o, d);
-    p.ray_o[i] = make_float4(o.x, o.y, o.z, 0.0f);
-    p.ray_d[i] = make_float4(d.x, d.y, d.z, 0.0f);
-    p.atten_seed[i] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(seed));
-    p.misc[i] = make_uint4(seed, (uint32_t)f.max_depth, 0u, __float_as_uint(-1.0f));  // .w: no BSDF pdf yet (linear.cuh)
+    stp(&p.ray_o[i], make_float4(o.x, o.y, o.z, 0.0f));
+    stp(&p.ray_d[i], make_float4(d.x, d.y, d.z, 0.0f));
+    stp(&p.atten_seed[i], make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(seed)));
+    stp(&p.misc[i], make_uint4(seed, (uint32_t)f.max_depth, 0u, __float_as_uint(-1.0f)));  // .w: no BSDF pdf yet (linear.cuh)
     status[i] = ST_TRACE;
 }
 

@@ -61,6 +61,21 @@ struct PathView {
     uint32_t n_slots;
 };
 
+// Path state is streamed: every record is read once per stage and rewritten by the next one, by whichever thread
+// handles the slot.  ld.global.cg / st.global.cg keep it out of L1, which is then left to what IS reused across rays: BVH
+// nodes, leaf triangles, vertex attributes, texels (all read through the read-only path).
+#ifndef PTB_STATE_CACHE_L1
+PTB_DEV float4 ldp(const float4* a) { return __ldcg(a); }
+PTB_DEV uint4 ldp(const uint4* a) { return __ldcg(a); }
+PTB_DEV void stp(float4* a, float4 v) { __stcg(a, v); }
+PTB_DEV void stp(uint4* a, uint4 v) { __stcg(a, v); }
+#else
+PTB_DEV float4 ldp(const float4* a) { return *a; }
+PTB_DEV uint4 ldp(const uint4* a) { return *a; }
+PTB_DEV void stp(float4* a, float4 v) { *a = v; }
+PTB_DEV void stp(uint4* a, uint4 v) { *a = v; }
+#endif
+
 // counters[iter*4 + 0] = rays to trace in iteration iter, +1 = hits, +2 = misses, +3 = k_trace's work counter
 struct QueueView {
     uint32_t* trace[2];
@@ -111,11 +126,11 @@ __global__ void __launch_bounds__(256) k_raygen_init(FrameView f, PathView p, Qu
     uint32_t seed = iy * f.W + ix + ((uint32_t)f.subframe + sub) * f.W * f.H;  // cu:316
     float3 o, d;
     start_sample(f, ix, iy, seed, o, d);
-    p.ray_o[i] = make_float4(o.x, o.y, o.z, 0.0f);
-    p.ray_d[i] = make_float4(d.x, d.y, d.z, 0.0f);
-    p.atten_seed[i] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(seed));
-    p.misc[i] = make_uint4(seed, (uint32_t)f.max_depth, 0u, 0u);
-    p.pixsum[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    stp(&p.ray_o[i], make_float4(o.x, o.y, o.z, 0.0f));
+    stp(&p.ray_d[i], make_float4(d.x, d.y, d.z, 0.0f));
+    stp(&p.atten_seed[i], make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(seed)));
+    stp(&p.misc[i], make_uint4(seed, (uint32_t)f.max_depth, 0u, 0u));
+    stp(&p.pixsum[i], make_float4(0.0f, 0.0f, 0.0f, 0.0f));
     q.trace[0][i] = i;
 }
 
@@ -146,7 +161,7 @@ __global__ void __launch_bounds__(128) k_trace(SceneView s, FrameView f, PathVie
         if (__any_sync(0xffffffffu, pending)) {
             const bool is_hit = t.best.prim >= 0;
             if (pending) {
-                p.hit[slot] = make_float4(t.best.t, t.best.b1, t.best.b2, __int_as_float(t.best.prim));
+                stp(&p.hit[slot], make_float4(t.best.t, t.best.b1, t.best.b2, __int_as_float(t.best.prim)));
                 if (iter == 0 && f.aux_primary && slot < f.n_pixels) f.aux_primary[(size_t)image_row(f, slot / f.W) * f.W + slot % f.W] = t.best.prim;
             }
             queue_push(q.hit, &q.counters[iter * 4 + 1], pending && is_hit, slot);
@@ -164,7 +179,7 @@ __global__ void __launch_bounds__(128) k_trace(SceneView s, FrameView f, PathVie
                 const uint32_t idx = base + (uint32_t)__popc(need & lt_mask);
                 if (!have && idx < n) {
                     slot = in[idx];
-                    const float4 o4 = p.ray_o[slot], d4 = p.ray_d[slot];
+                    const float4 o4 = ldp(&p.ray_o[slot]), d4 = ldp(&p.ray_d[slot]);
                     trav_begin(t, stack, mk3(o4), mk3(d4), f.tmin, f.tmax);
                     have = true;
                 }
@@ -408,26 +423,26 @@ PTB_DEV bool after_segment(const FrameView& f, const PathView& p, uint32_t slot,
     bool done = b.done != 0;
     if (!done) done = myrnd(seed_rg) > pr;  // short-circuit: no draw when payload.done
     if (!done) {
-        p.ray_o[slot] = make_float4(b.origin.x, b.origin.y, b.origin.z, 0.0f);
-        p.ray_d[slot] = make_float4(b.direction.x, b.direction.y, b.direction.z, 0.0f);
-        p.atten_seed[slot] = make_float4(b.atten.x, b.atten.y, b.atten.z, __uint_as_float(b.seed));
-        p.misc[slot] = make_uint4(seed_rg, (uint32_t)(depth - 1), sample, 0u);
+        stp(&p.ray_o[slot], make_float4(b.origin.x, b.origin.y, b.origin.z, 0.0f));
+        stp(&p.ray_d[slot], make_float4(b.direction.x, b.direction.y, b.direction.z, 0.0f));
+        stp(&p.atten_seed[slot], make_float4(b.atten.x, b.atten.y, b.atten.z, __uint_as_float(b.seed)));
+        stp(&p.misc[slot], make_uint4(seed_rg, (uint32_t)(depth - 1), sample, 0u));
         return true;
     }
     // cu:384-387; a path with done && !(p > 0) loops forever in the reference: it contributes 0 here
     const float3 path_rgb = pr > 0.0f ? b.radiance / pr : mk3(0.0f);
-    float4 sum = p.pixsum[slot];
+    float4 sum = ldp(&p.pixsum[slot]);
     sum.x = sum.x + path_rgb.x; sum.y = sum.y + path_rgb.y; sum.z = sum.z + path_rgb.z;
-    p.pixsum[slot] = sum;
+    stp(&p.pixsum[slot], sum);
     sample += 1u;
     if (sample >= (uint32_t)f.spp) return false;
     float3 o, d;
     const uint32_t pix = slot % f.n_pixels;
     start_sample(f, pix % f.W, image_row(f, pix / f.W), seed_rg, o, d);
-    p.ray_o[slot] = make_float4(o.x, o.y, o.z, 0.0f);
-    p.ray_d[slot] = make_float4(d.x, d.y, d.z, 0.0f);
-    p.atten_seed[slot] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(seed_rg));
-    p.misc[slot] = make_uint4(seed_rg, (uint32_t)f.max_depth, sample, 0u);
+    stp(&p.ray_o[slot], make_float4(o.x, o.y, o.z, 0.0f));
+    stp(&p.ray_d[slot], make_float4(d.x, d.y, d.z, 0.0f));
+    stp(&p.atten_seed[slot], make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(seed_rg)));
+    stp(&p.misc[slot], make_uint4(seed_rg, (uint32_t)f.max_depth, sample, 0u));
     return true;
 }
 
@@ -441,8 +456,8 @@ __global__ void __launch_bounds__(128) k_shade(SceneView s, FrameView f, PathVie
         bool again = false;
         if (active) {
             slot = q.hit[i];
-            const float4 o4 = p.ray_o[slot], d4 = p.ray_d[slot], h4 = p.hit[slot], as = p.atten_seed[slot];
-            const uint4 mi = p.misc[slot];
+            const float4 o4 = ldp(&p.ray_o[slot]), d4 = ldp(&p.ray_d[slot]), h4 = ldp(&p.hit[slot]), as = ldp(&p.atten_seed[slot]);
+            const uint4 mi = ldp(&p.misc[slot]);
             Bounce b;
             b.atten = mk3(as); b.seed = __float_as_uint(as.w);
             const int depth = (int)mi.y;
@@ -464,8 +479,8 @@ __global__ void __launch_bounds__(128) k_miss(SceneView s, FrameView f, PathView
         bool again = false;
         if (active) {
             slot = q.miss[i];
-            const float4 d4 = p.ray_d[slot], as = p.atten_seed[slot];
-            const uint4 mi = p.misc[slot];
+            const float4 d4 = ldp(&p.ray_d[slot]), as = ldp(&p.atten_seed[slot]);
+            const uint4 mi = ldp(&p.misc[slot]);
             const float3 ray_dir = normalize(mk3(d4));
             const float u = 0.5f + det_atan2f(ray_dir.z, ray_dir.x) / (2.0f * PTB_PI_F);
             const float v = 0.5f - det_asinf(ray_dir.y) / PTB_PI_F;
@@ -517,7 +532,7 @@ __global__ void __launch_bounds__(256) k_resolve(FrameView f, PathView p) {
     const size_t px = (size_t)iy * f.W + i % f.W;  // position in the caller's full-frame buffers
     float3 accum_color = mk3(0.0f);
     for (int sub = 0; sub < f.n_subframes; ++sub) {
-        const float4 sum = p.pixsum[(size_t)sub * f.n_pixels + i];
+        const float4 sum = ldp(&p.pixsum[(size_t)sub * f.n_pixels + i]);
         accum_color = mk3(sum) / (float)f.spp;  // cu:401
         const int subframe = f.subframe + sub;
         if (f.accumulate_mode == 1) {
