@@ -31,7 +31,8 @@ struct HitRec { float t, b1, b2; int prim; };
 
 struct RayShear { int kx, ky, kz; float Sx, Sy, Sz; };
 
-PTB_DEV RayShear ray_shear(float3 d) {
+// id = (1/d.x, 1/d.y, 1/d.z): Sz = 1 / d[kz] is one of its components (the same IEEE division), so it is not recomputed
+PTB_DEV RayShear ray_shear(float3 d, float3 id) {
     RayShear r;
     float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
     int kz = 0; float m = ax;
@@ -44,7 +45,7 @@ PTB_DEV RayShear ray_shear(float3 d) {
     float dz = comp(d, kz);
     r.Sx = comp(d, kx) / dz;
     r.Sy = comp(d, ky) / dz;
-    r.Sz = 1.0f / dz;
+    r.Sz = comp(id, kz);
     return r;
 }
 
@@ -113,7 +114,7 @@ struct Trav {
 
 PTB_DEV void trav_begin(Trav& t, int* stack, float3 o, float3 d, float tmin, float tmax) {
     t.o = o; t.id = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-    t.rs = ray_shear(d);
+    t.rs = ray_shear(d, t.id);
     t.tmin = tmin; t.tminp = tmin * 0.999f; t.tmax = tmax;
     t.best.t = tmax; t.best.b1 = 0.0f; t.best.b2 = 0.0f; t.best.prim = -1;
     stack[0] = PTB_TRAV_SENTINEL;

@@ -61,7 +61,7 @@ PTB_DEV void chunk_status_words(const unsigned char* __restrict__ status, uint32
         for (int w = 0; w < (SPT + 7) / 8; ++w) {
             const uint32_t f0 = first + 8u * w;
             unsigned long long bytes = 0ull;
-            if (f0 + 8u <= n_slots) bytes = *reinterpret_cast<const unsigned long long*>(status + f0);
+            if (f0 + 8u <= n_slots) bytes = __ldcs(reinterpret_cast<const unsigned long long*>(status + f0));
             else if (f0 < n_slots) for (uint32_t k = 0; f0 + k < n_slots; ++k) bytes |= (unsigned long long)status[f0 + k] << (8u * k);
             words[w] = bytes;
         }

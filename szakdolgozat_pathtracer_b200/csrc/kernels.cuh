@@ -310,9 +310,6 @@ PTB_DEV void closest_hit(const SceneView& s, const FrameView& f, int prim_idx, f
                          float3 ray_orig, float3 ray_dir, int depth, Bounce& io) {
     const DevMaterial& m = s.mats[__ldg(s.mat_ids + prim_idx)];
     const size_t vo = (size_t)prim_idx * 3;
-    const float3 v0 = mk3(__ldg(s.verts + vo)), v1 = mk3(__ldg(s.verts + vo + 1)), v2 = mk3(__ldg(s.verts + vo + 2));
-    float3 flat_normal = normalize(cross(v1 - v0, v2 - v0));
-    flat_normal = faceforward(flat_normal, -ray_dir, flat_normal);
 
     // getPayloadCH (cu:160-172): radiance/origin/direction/done restart from zero
     io.radiance = mk3(0.0f); io.origin = mk3(0.0f); io.direction = mk3(0.0f); io.done = 0;
@@ -320,15 +317,16 @@ PTB_DEV void closest_hit(const SceneView& s, const FrameView& f, int prim_idx, f
     const float3 n0 = mk3(__ldg(s.normals + vo)), n1 = mk3(__ldg(s.normals + vo + 1)), n2 = mk3(__ldg(s.normals + vo + 2));
     const float bary_beta = b1, bary_gamma = b2;
     const float bary_alpha = 1.0f - bary_beta - bary_gamma;
-    const float2 uv0 = __ldg(s.uvs + vo), uv1 = __ldg(s.uvs + vo + 1), uv2 = __ldg(s.uvs + vo + 2);
-    const float uvx = uv0.x * bary_alpha + uv1.x * bary_beta + uv2.x * bary_gamma;
-    float uvy = uv0.y * bary_alpha + uv1.y * bary_beta + uv2.y * bary_gamma;
-    uvy = 1.0f - uvy;
-
     float3 normal = bary_alpha * n0 + bary_beta * n1 + bary_gamma * n2;
     if (length(normal) > 0.01f) normal = normalize(normal);
     else { io.done = 1; return; }
-    if (dot(normal, ray_dir) > 0.0f) normal = flat_normal;
+    if (dot(normal, ray_dir) > 0.0f) {
+        // the flat normal (cu:631-638) is only ever used here, so the three vertex fetches and its normalisation are done
+        // for the few hits whose shading normal faces away from the ray, not for all of them (same value either way)
+        const float3 v0 = mk3(__ldg(s.verts + vo)), v1 = mk3(__ldg(s.verts + vo + 1)), v2 = mk3(__ldg(s.verts + vo + 2));
+        const float3 flat_normal = normalize(cross(v1 - v0, v2 - v0));
+        normal = faceforward(flat_normal, -ray_dir, flat_normal);
+    }
 
     const float3 hit_pos = ray_orig + t_hit * ray_dir;
     uint32_t seed = io.seed;
@@ -340,9 +338,18 @@ PTB_DEV void closest_hit(const SceneView& s, const FrameView& f, int prim_idx, f
     float3 normal_map = mk3(0.0f, 1.0f, 0.0f);
     float roughness = m.roughness;
     float metallicity = m.metallic ? 1.0f : 0.0f;
+    float uvx = 0.0f, uvy = 0.0f;  // interpolated texture coordinate (cu:650-659), fetched for textured materials only
+    bool have_uv = false;
 #pragma unroll 1
     for (int k = 0; k < 4; ++k) {
         if (m.tex[k].fmt == 0) continue;
+        if (!have_uv) {
+            const float2 uv0 = __ldg(s.uvs + vo), uv1 = __ldg(s.uvs + vo + 1), uv2 = __ldg(s.uvs + vo + 2);
+            uvx = uv0.x * bary_alpha + uv1.x * bary_beta + uv2.x * bary_gamma;
+            uvy = uv0.y * bary_alpha + uv1.y * bary_beta + uv2.y * bary_gamma;
+            uvy = 1.0f - uvy;
+            have_uv = true;
+        }
         const float4 c = sample_texture(m.tex[k], uvx, uvy);
         if (k == 0) diffuse_albedo = mk3(c);
         else if (k == 1) roughness = c.x;
@@ -384,9 +391,7 @@ PTB_DEV void closest_hit(const SceneView& s, const FrameView& f, int prim_idx, f
 
     const float3 light_dir = reflect(ray_dir, half_vec);
     r1 = myrnd(seed);
-    r2 = myrnd(seed);
-    float3 light_dir_diffuse = cosine_sample_hemisphere(r1, r2);
-    light_dir_diffuse = onb.inverse_transform(light_dir_diffuse);
+    r2 = myrnd(seed);  // the cosine-lobe direction itself (cu:754-757) is only needed when that lobe is chosen: see below
 
     const float f0s = (float)fabs((1.0 - (double)ior) / (1.0 + (double)ior));
     float3 F0 = mk3(f0s);
@@ -401,14 +406,15 @@ PTB_DEV void closest_hit(const SceneView& s, const FrameView& f, int prim_idx, f
     const float NdotH = fmaxf(dot(normal, half_vec), 1e-10f);
     const float VdotH = fmaxf(dot(-ray_dir, half_vec), 1e-10f);
     const float NdotV = fmaxf(dot(normal, -ray_dir), 0.0f);
-    const float IdotN = fabsf(dot(normal, normalize(light_dir)));
+    const float3 light_dir_n = normalize(light_dir);
+    const float IdotN = fabsf(dot(normal, light_dir_n));
     const float F_blend_factor = Fresnel_Schlick_float(NdotV, ior);
 
     const float specular_probability = metallicity + (1.0f - metallicity) * F_blend_factor;
     const float spdf = D * NdotH / (4.0f * VdotH);
     const float dpdf = 1.0f / PTB_PI_F;
-    if (myrnd(seed) < specular_probability) io.direction = normalize(light_dir);
-    else io.direction = normalize(light_dir_diffuse);
+    if (myrnd(seed) < specular_probability) io.direction = light_dir_n;
+    else io.direction = normalize(onb.inverse_transform(cosine_sample_hemisphere(r1, r2)));
     const float3 brdf = specular_probability * (brdf_specular / spdf) + (1.0f - specular_probability) * (diffuse_albedo / dpdf);
 
     if (length(brdf) >= 1e-10f) io.atten = io.atten * (brdf * IdotN);
