@@ -35,8 +35,16 @@ struct SceneView {
     const float4* env; int env_w, env_h;
 };
 
+// Exact unsigned division by a launch constant d for x < 2^31: q = (x * m) >> sh with m = ceil(2^sh / d),
+// sh = 31 + ceil(log2 d) (the error m*d - 2^sh is < d <= 2^(sh-31), so it cannot carry into the quotient for x < 2^31).
+// One 64-bit multiply instead of the ~20-instruction software division; every sample start needs three of them.
+struct FastDiv { unsigned long long m; uint32_t sh, d; };
+PTB_DEV uint32_t fd_div(uint32_t x, const FastDiv& fd) { return (uint32_t)(((unsigned long long)x * fd.m) >> fd.sh); }
+PTB_DEV uint32_t fd_mod(uint32_t x, const FastDiv& fd) { return x - fd_div(x, fd) * fd.d; }
+
 struct FrameView {
     uint32_t W, H;
+    FastDiv div_w, div_pixels;  // by W and by n_pixels
     uint32_t row0;       // first image row rendered by this launch (row band; 0 for the whole frame)
     uint32_t il_n, il_r, il_h;  // il_n > 1: interleaved strips of il_h rows, this launch renders strips il_r, il_r + il_n, ...
     uint32_t n_pixels;   // W * rows of the band
@@ -444,8 +452,9 @@ PTB_DEV bool after_segment(const FrameView& f, const PathView& p, uint32_t slot,
     sample += 1u;
     if (sample >= (uint32_t)f.spp) return false;
     float3 o, d;
-    const uint32_t pix = slot % f.n_pixels;
-    start_sample(f, pix % f.W, image_row(f, pix / f.W), seed_rg, o, d);
+    const uint32_t pix = fd_mod(slot, f.div_pixels);
+    const uint32_t prow = fd_div(pix, f.div_w);
+    start_sample(f, pix - prow * f.W, image_row(f, prow), seed_rg, o, d);
     stp(&p.ray_o[slot], make_float4(o.x, o.y, o.z, 0.0f));
     stp(&p.ray_d[slot], make_float4(d.x, d.y, d.z, 0.0f));
     stp(&p.atten_seed[slot], make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(seed_rg)));

@@ -196,9 +196,10 @@ PTB_DEV void pool_stage_shade_miss(PoolShared& sh, const SceneView& s, const Fra
         }
         // next camera ray of this position's pixel (cu:326-360): sample `sample`, stream state seed_rg
         p.pixsum[g] = sum;
-        const uint32_t pix = slot % f.n_pixels;
+        const uint32_t pix = fd_mod(slot, f.div_pixels);
+        const uint32_t prow = fd_div(pix, f.div_w);
         float3 o, d;
-        start_sample(f, pix % f.W, image_row(f, pix / f.W), seed_rg, o, d);
+        start_sample(f, pix - prow * f.W, image_row(f, prow), seed_rg, o, d);
         p.ray_o[g] = make_float4(o.x, o.y, o.z, 0.0f);
         p.ray_d[g] = make_float4(d.x, d.y, d.z, 0.0f);
         p.atten_seed[g] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(seed_rg));

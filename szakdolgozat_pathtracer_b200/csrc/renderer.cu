@@ -384,6 +384,14 @@ int ptb_launch(ptb_context* ctx, const ptb_Params* P, const ptb_render_cfg* cfg_
     }
 
     FrameView f;
+    auto make_fastdiv = [](uint32_t d) {
+        FastDiv fd; fd.d = d;
+        uint32_t L = 0; while ((1ull << L) < (unsigned long long)d) ++L;
+        fd.sh = 31u + L;
+        fd.m = (unsigned long long)((((unsigned __int128)1 << fd.sh) + d - 1) / d);
+        return fd;
+    };
+    f.div_w = make_fastdiv(P->image_width); f.div_pixels = make_fastdiv(n_pixels);
     f.W = P->image_width; f.H = P->image_height; f.row0 = row0; f.il_n = il_n; f.il_r = il_r; f.il_h = il_h; f.n_pixels = n_pixels; f.n_subframes = n_sub; f.subframe = P->subframe_index; f.dof = P->dof ? 1 : 0;
     f.eye = make_float3(P->eye.x, P->eye.y, P->eye.z); f.U = make_float3(P->U.x, P->U.y, P->U.z);
     f.V = make_float3(P->V.x, P->V.y, P->V.z); f.Wv = make_float3(P->W.x, P->W.y, P->W.z);
