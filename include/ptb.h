@@ -165,6 +165,8 @@ typedef struct ptb_build_cfg {
     int32_t sah_bins;      /* default 16 */
     int32_t treelet_size;  /* primitives per refinement treelet, default 512 */
     int32_t morton_bits;   /* 30 (default: 10 bits per axis) or 63 (21 bits per axis) */
+    int32_t bvh_width;     /* 0 (default): 4-wide traversal for large scenes, 2-wide otherwise; 2 or 4 force one.  The
+                              hit rule does not depend on the tree, so results are identical. */
 } ptb_build_cfg;
 
 typedef struct ptb_build_stats {

@@ -90,7 +90,7 @@ class LaunchStats(C.Structure):
 
 class BuildCfg(C.Structure):
     _fields_ = [("max_leaf_size", C.c_int32), ("sah_refine", C.c_int32), ("sah_bins", C.c_int32), ("treelet_size", C.c_int32),
-                ("morton_bits", C.c_int32)]
+                ("morton_bits", C.c_int32), ("bvh_width", C.c_int32)]
 
 
 class BuildStats(C.Structure):

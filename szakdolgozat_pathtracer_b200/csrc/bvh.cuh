@@ -122,6 +122,25 @@ PTB_DEV void trav_begin(Trav& t, int* stack, float3 o, float3 d, float tmin, flo
     t.node = 0;
 }
 
+// tests the triangles of one leaf against the ray (closest-hit rule of the header comment)
+template <bool COUNT>
+PTB_DEV void trav_leaf(Trav& t, const float4* __restrict__ tris, int code, TravCounters* cnt) {
+    const int first = code >> 3, count = (code & 7) + 1;
+    for (int i = 0; i < count; ++i) {
+        const float4* tp = tris + (size_t)(first + i) * 3;
+        const float4 a = __ldg(tp + 0), b = __ldg(tp + 1), c = __ldg(tp + 2);
+        if (COUNT) cnt->tris++;
+        float th, b1, b2;
+        // test against the ray's own tmax so that ties can be resolved by prim id
+        if (ray_tri(t.o, t.rs, mk3(a), mk3(b), mk3(c), t.tmin, t.tmax, &th, &b1, &b2)) {
+            const int prim = __float_as_int(a.w);
+            if (th < t.best.t || (th == t.best.t && t.best.prim >= 0 && prim < t.best.prim)) {
+                t.best.t = th; t.best.b1 = b1; t.best.b2 = b2; t.best.prim = prim;
+            }
+        }
+    }
+}
+
 // Runs at most `budget` steps ("while-while": descend through internal nodes until a leaf is reached, then test
 // the leaf's triangles).  Returns true when the ray is finished.
 template <bool COUNT>
@@ -147,21 +166,7 @@ PTB_DEV bool trav_run(Trav& t, int* stack, const float4* __restrict__ nodes, con
         }
         if (t.node == PTB_TRAV_SENTINEL) return true;
         if (t.node < 0) {
-            const int code = ~t.node;
-            const int first = code >> 3, count = (code & 7) + 1;
-            for (int i = 0; i < count; ++i) {
-                const float4* tp = tris + (size_t)(first + i) * 3;
-                const float4 a = __ldg(tp + 0), b = __ldg(tp + 1), c = __ldg(tp + 2);
-                if (COUNT) cnt->tris++;
-                float th, b1, b2;
-                // test against the ray's own tmax so that ties can be resolved by prim id
-                if (ray_tri(t.o, t.rs, mk3(a), mk3(b), mk3(c), t.tmin, t.tmax, &th, &b1, &b2)) {
-                    const int prim = __float_as_int(a.w);
-                    if (th < t.best.t || (th == t.best.t && t.best.prim >= 0 && prim < t.best.prim)) {
-                        t.best.t = th; t.best.b1 = b1; t.best.b2 = b2; t.best.prim = prim;
-                    }
-                }
-            }
+            trav_leaf<COUNT>(t, tris, ~t.node, cnt);
             t.node = stack[--t.sp];
             budget -= 2;
             if (t.node == PTB_TRAV_SENTINEL) return true;
@@ -170,13 +175,70 @@ PTB_DEV bool trav_run(Trav& t, int* stack, const float4* __restrict__ nodes, con
     return false;
 }
 
+// 4-wide traversal over the collapsed tree (bvh_build.cu: k_collapse4).  Node = 8 x float4 (128 B):
+//   q0 lo.x[4]  q1 hi.x[4]  q2 lo.y[4]  q3 hi.y[4]  q4 lo.z[4]  q5 hi.z[4]  q6 child codes[4]  (q7 pad)
+// Child codes as in the 2-wide tree (>= 0: node index, < 0: leaf code); unused slots carry NaN boxes.  Same hit rule, same
+// conservative slab test, so the result is identical to trav_run; the children that are hit are visited nearest first
+// (the others go on the stack farthest first).  One step costs about 2.3 x a 2-wide step but a ray needs half as many
+// DEPENDENT node fetches.
+#define PTB_SWAP_IF(c, a, b, ia, ib) do { if (c) { const float tf_ = a; a = b; b = tf_; const int ti_ = ia; ia = ib; ib = ti_; } } while (0)
 template <bool COUNT>
-PTB_DEV HitRec bvh_closest_hit(const float4* __restrict__ nodes, const float4* __restrict__ tris, float3 o, float3 d,
-                               float tmin, float tmax, TravCounters* cnt) {
+PTB_DEV bool trav_run4(Trav& t, int* stack, const float4* __restrict__ nodes4, const float4* __restrict__ tris, int budget,
+                       TravCounters* cnt) {
+    while (budget > 0) {
+        while ((unsigned)t.node < (unsigned)PTB_TRAV_SENTINEL && budget > 0) {
+            const float4* np = nodes4 + (size_t)t.node * 8;
+            const float4 lx = __ldg(np + 0), hx = __ldg(np + 1), ly = __ldg(np + 2), hy = __ldg(np + 3), lz = __ldg(np + 4), hz = __ldg(np + 5);
+            const float4 cc = __ldg(np + 6);
+            if (COUNT) cnt->nodes++;
+            float d0, d1, d2, d3;
+            const bool h0 = slab(lx.x, hx.x, ly.x, hy.x, lz.x, hz.x, t.o, t.id, t.tminp, t.best.t, &d0);
+            const bool h1 = slab(lx.y, hx.y, ly.y, hy.y, lz.y, hz.y, t.o, t.id, t.tminp, t.best.t, &d1);
+            const bool h2 = slab(lx.z, hx.z, ly.z, hy.z, lz.z, hz.z, t.o, t.id, t.tminp, t.best.t, &d2);
+            const bool h3 = slab(lx.w, hx.w, ly.w, hy.w, lz.w, hz.w, t.o, t.id, t.tminp, t.best.t, &d3);
+            const float far = 3.4e38f;
+            if (!h0) d0 = far; if (!h1) d1 = far; if (!h2) d2 = far; if (!h3) d3 = far;
+            int c0 = __float_as_int(cc.x), c1 = __float_as_int(cc.y), c2 = __float_as_int(cc.z), c3 = __float_as_int(cc.w);
+            // sorting network, ascending entry distance (misses sink to the end)
+            PTB_SWAP_IF(d1 < d0, d0, d1, c0, c1); PTB_SWAP_IF(d3 < d2, d2, d3, c2, c3);
+            PTB_SWAP_IF(d2 < d0, d0, d2, c0, c2); PTB_SWAP_IF(d3 < d1, d1, d3, c1, c3);
+            PTB_SWAP_IF(d2 < d1, d1, d2, c1, c2);
+            const int nh = (int)h0 + (int)h1 + (int)h2 + (int)h3;
+            if (nh == 0) t.node = stack[--t.sp];
+            else {
+                if (nh > 3) stack[t.sp++] = c3;
+                if (nh > 2) stack[t.sp++] = c2;
+                if (nh > 1) stack[t.sp++] = c1;
+                t.node = c0;
+            }
+            --budget;
+        }
+        if (t.node == PTB_TRAV_SENTINEL) return true;
+        if (t.node < 0) {
+            trav_leaf<COUNT>(t, tris, ~t.node, cnt);
+            t.node = stack[--t.sp];
+            budget -= 2;
+            if (t.node == PTB_TRAV_SENTINEL) return true;
+        }
+    }
+    return false;
+}
+
+// 2- or 4-wide, by what the scene was built with (uniform over the launch)
+template <bool COUNT>
+PTB_DEV bool trav_run_any(Trav& t, int* stack, const float4* __restrict__ nodes, const float4* __restrict__ nodes4,
+                          const float4* __restrict__ tris, int budget, TravCounters* cnt) {
+    if (nodes4) return trav_run4<COUNT>(t, stack, nodes4, tris, budget, cnt);
+    return trav_run<COUNT>(t, stack, nodes, tris, budget, cnt);
+}
+
+template <bool COUNT>
+PTB_DEV HitRec bvh_closest_hit(const float4* __restrict__ nodes, const float4* __restrict__ nodes4, const float4* __restrict__ tris,
+                               float3 o, float3 d, float tmin, float tmax, TravCounters* cnt) {
     int stack[PTB_BVH_STACK];
     Trav t;
     trav_begin(t, stack, o, d, tmin, tmax);
-    while (!trav_run<COUNT>(t, stack, nodes, tris, 1 << 20, cnt)) {}
+    while (!trav_run_any<COUNT>(t, stack, nodes, nodes4, tris, 1 << 20, cnt)) {}
     return t.best;
 }
 

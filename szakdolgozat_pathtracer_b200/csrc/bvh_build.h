@@ -7,12 +7,14 @@
 
 #include "../../include/ptb.h"
 
+#define PTB_WIDE_BVH_MIN_TRIS 1000000u  // bvh_width = 0 (auto): 4-wide traversal from this many triangles on (C5 with 0.33 M: -1 %, C4 with 4.6 M: +4 %)
 #define PTB_BVH_MAX_DEPTH 128 // traversal stack entries (bvh.cuh: PTB_BVH_STACK)
 
 namespace ptb {
 
 struct DeviceBvh {
     float4* nodes = nullptr;  // n_nodes x 4 float4 (64 B each), layout in bvh.cuh
+    float4* nodes4 = nullptr; // optional 4-wide copy: n_nodes x 8 float4 (128 B each, indexed like `nodes`), layout in bvh.cuh
     float4* tris = nullptr;   // n_tris x 3 float4 (48 B each), leaf order
     uint32_t n_nodes = 0, n_tris = 0;
 };

@@ -60,7 +60,7 @@ void ptb_default_render_cfg(ptb_render_cfg* cfg) {
 
 void ptb_default_build_cfg(ptb_build_cfg* cfg) {
     if (!cfg) return;
-    cfg->max_leaf_size = 4; cfg->sah_refine = 1; cfg->sah_bins = 16; cfg->treelet_size = 512; cfg->morton_bits = 30;
+    cfg->max_leaf_size = 4; cfg->sah_refine = 1; cfg->sah_bins = 16; cfg->treelet_size = 512; cfg->morton_bits = 30; cfg->bvh_width = 0;
 }
 
 int ptb_scene_load_obj(const char* const* files, int n_files, float scale, uint32_t material_seed, ptb_scene** out) {

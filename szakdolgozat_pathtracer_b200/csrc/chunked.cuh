@@ -175,7 +175,7 @@ PTB_DEV void chunk_stage_trace(ChunkSharedT<SPT>& sh, const SceneView& s, const 
             }
         }
         if (!__any_sync(0xffffffffu, have)) break;
-        if (have && trav_run<COUNT>(t, stack, s.nodes, s.tris, QUANTUM, &tc)) {
+        if (have && trav_run_any<COUNT>(t, stack, s.nodes, s.nodes4, s.tris, QUANTUM, &tc)) {
             have = false;
             stp(&p.hit[slot], make_float4(t.best.t, t.best.b1, t.best.b2, __int_as_float(t.best.prim)));
             const bool is_hit = t.best.prim >= 0;

@@ -29,7 +29,7 @@ struct DevMaterial {
 };
 
 struct SceneView {
-    const float4* nodes; const float4* tris;
+    const float4* nodes; const float4* nodes4; const float4* tris;  // nodes4: 4-wide copy of the tree or nullptr
     const float4* verts; const float4* normals; const float2* uvs; const uint32_t* mat_ids;
     const DevMaterial* mats;
     const float4* env; int env_w, env_h;
@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(128) k_trace(SceneView s, FrameView f, PathVie
         }
         if (!__any_sync(0xffffffffu, have)) break;
         if (have) {
-            if (trav_run<COUNT>(t, stack, s.nodes, s.tris, QUANTUM, &tc)) { have = false; pending = true; }
+            if (trav_run_any<COUNT>(t, stack, s.nodes, s.nodes4, s.tris, QUANTUM, &tc)) { have = false; pending = true; }
         }
     }
     if (COUNT) {
@@ -620,7 +620,7 @@ __global__ void k_trace_rays(SceneView s, const float* __restrict__ origins, con
     const float3 o = mk3(origins[3 * (size_t)i], origins[3 * (size_t)i + 1], origins[3 * (size_t)i + 2]);
     const float3 d = mk3(dirs[3 * (size_t)i], dirs[3 * (size_t)i + 1], dirs[3 * (size_t)i + 2]);
     TravCounters tc;
-    const HitRec h = bvh_closest_hit<false>(s.nodes, s.tris, o, d, tmin, tmax, &tc);
+    const HitRec h = bvh_closest_hit<false>(s.nodes, s.nodes4, s.tris, o, d, tmin, tmax, &tc);
     if (prim) prim[i] = h.prim;
     if (t) t[i] = h.t;
     if (b1) b1[i] = h.b1;

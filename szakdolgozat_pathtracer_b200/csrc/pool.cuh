@@ -103,7 +103,7 @@ PTB_DEV void pool_stage_trace(PoolShared& sh, const SceneView& s, const FrameVie
             }
         }
         if (!__any_sync(0xffffffffu, have)) break;
-        if (have && trav_run<COUNT>(t, stack, s.nodes, s.tris, QUANTUM, &tc)) {
+        if (have && trav_run_any<COUNT>(t, stack, s.nodes, s.nodes4, s.tris, QUANTUM, &tc)) {
             have = false;
             p.hit[gbase + pos] = make_float4(t.best.t, t.best.b1, t.best.b2, __int_as_float(t.best.prim));
             const bool is_hit = t.best.prim >= 0;

@@ -157,7 +157,7 @@ int ensure_pool(ptb_context* c, uint32_t slots, uint32_t iters) {
 
 SceneView scene_view(const DeviceScene* d) {
     SceneView s;
-    s.nodes = d->bvh.nodes; s.tris = d->bvh.tris;
+    s.nodes = d->bvh.nodes; s.nodes4 = d->bvh.nodes4; s.tris = d->bvh.tris;
     s.verts = d->verts; s.normals = d->normals; s.uvs = d->uvs; s.mat_ids = d->mat_ids; s.mats = d->mats;
     s.env = d->env; s.env_w = d->env_w; s.env_h = d->env_h;
     return s;

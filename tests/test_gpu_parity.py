@@ -169,7 +169,8 @@ def test_bvh_structure_and_ray_queries(ptb, ctx, oh, assets, name, small, refine
 
 
 def test_bvh_builder_options(ptb, ctx, oh, assets):
-    """Builder variants must all give a valid tree and the same hits: 63-bit Morton keys, small treelets, leaf size 1 and 8;
+    """Builder variants must all give a valid tree and the same hits: 63-bit Morton keys, small treelets, leaf size 1 and 8,
+    the 4-wide collapsed tree;
     and the huge-primitive split: the two floor triangles (the last two prims, optixSphere.cpp:598-646) sit in ONE leaf that
     is a child of the root."""
     if PIPELINE != 3:
@@ -181,7 +182,8 @@ def test_bvh_builder_options(ptb, ctx, oh, assets):
     v = osc.vertices[:, :3]
     o, d = random_rays(rng, 4000, v[:-6].min(0), v[:-6].max(0))
     ref = None
-    for kw in (dict(), dict(morton_bits=63), dict(treelet_size=32), dict(max_leaf_size=1), dict(max_leaf_size=8), dict(sah_refine=0, morton_bits=63)):
+    for kw in (dict(), dict(morton_bits=63), dict(treelet_size=32), dict(max_leaf_size=1), dict(max_leaf_size=8), dict(sah_refine=0, morton_bits=63),
+               dict(bvh_width=4), dict(bvh_width=4, sah_refine=0), dict(bvh_width=4, max_leaf_size=1), dict(bvh_width=2)):
         handle, st = ctx.accel_build(sc, ptb.default_build_cfg(**kw))
         nodes, tris = ctx.accel_read(handle)
         assert _check_bvh(nodes, tris, n, kw.get("max_leaf_size", 4)) == st.num_nodes, kw
@@ -321,6 +323,24 @@ def test_chunk_sizes_bit_identical(ptb, ctx, assets):
             ctx.launch(p, ptb.default_render_cfg(chunk_slots_per_thread=3, pipeline=3))
     finally:
         ctx.free(d_accum); ctx.free(d_frame)
+
+
+def test_wide_bvh_render_bit_identical(ptb, ctx, oh, assets):
+    """4-wide traversal (the default for large scenes) against the 2-wide one and the oracle: same image, bit for bit."""
+    if PIPELINE not in (1, 3, 4):
+        pytest.skip("pipeline 2 shares the traversal code of pipeline 3")
+    sc = load_config(ptb, assets, "c2")
+    W, H = 160, 90
+    kw = dict(spp_per_launch=3, max_depth=6)
+    res = []
+    for width in (2, 4):
+        handle, st = ctx.accel_build(sc, ptb.default_build_cfg(bvh_width=width))
+        a, f, h, stl = _render_gpu(ptb, ctx, handle, W, H, kw, camera="monkey_close")
+        res.append((a.view(np.uint32), f, h, stl[0].segments))
+    assert all(np.array_equal(x, y) for x, y in zip(res[0][:3], res[1][:3])) and res[0][3] == res[1][3]
+    osc = oh.OracleScene.from_ptb(sc, guard=False)
+    ca, cf, ch, cseg = _render_cpu(oh, ptb, osc, W, H, kw, camera="monkey_close")
+    assert np.array_equal(res[1][0], ca.view(np.uint32)) and np.array_equal(res[1][2], ch) and res[1][3] == cseg
 
 
 def test_demo_scene_parity(ptb, ctx, oh, assets):

@@ -29,12 +29,13 @@ ap.add_argument("--pipeline", type=int, default=0)
 ap.add_argument("--refine", type=int, default=1)
 ap.add_argument("--morton", type=int, default=30)
 ap.add_argument("--treelet", type=int, default=256)
+ap.add_argument("--width", dest="bvh_width", type=int, default=0) if False else ap.add_argument("--bvh-width", type=int, default=0)
 a = ap.parse_args()
 
 ctx = ptb.Context(0)
 sc = load_config(ptb, make_assets, a.config)
 t0 = time.time()
-handle, bst = ctx.accel_build(sc, ptb.default_build_cfg(max_leaf_size=a.leaf, sah_refine=a.refine, morton_bits=a.morton, treelet_size=a.treelet))
+handle, bst = ctx.accel_build(sc, ptb.default_build_cfg(max_leaf_size=a.leaf, sah_refine=a.refine, morton_bits=a.morton, treelet_size=a.treelet, bvh_width=a.bvh_width))
 print(f"build: {bst.num_triangles} tris, {bst.num_nodes} nodes, {bst.num_leaves} leaves, depth {bst.max_depth}, sah {bst.sah_cost:.2f}, "
       f"{bst.build_ms:.3f} ms device, {1e3 * (time.time() - t0):.1f} ms wall incl. upload")
 W, H = a.width, a.height
