@@ -82,6 +82,14 @@ PTB_DEV bool ray_tri(float3 org, const RayShear& rs, float3 p0, float3 p1, float
 
 struct TravCounters { uint32_t nodes, tris; };
 
+// Prefetch of what a stack entry points at (node or first triangle of a leaf) into L1, issued when the entry is pushed:
+// by the time it is popped the fetch has been under way for a whole subtree.  Only for trees that do not fit the caches
+// (4-wide traversal, PTB_WIDE_BVH_MIN_TRIS): C4 +1.5 %.
+PTB_DEV void trav_prefetch4(const float4* __restrict__ nodes4, const float4* __restrict__ tris, int code) {
+    const void* a = code >= 0 ? (const void*)(nodes4 + (size_t)code * 8) : (const void*)(tris + (size_t)((~code) >> 3) * 3);
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
+}
+
 // Conservative slab test of one child box against [tmin, tbest].  Leaf boxes are padded at build time
 // (bvh_build.cu: k_leaf_boxes) and the far distance is widened, so a box is never rejected when one of its
 // triangles would pass ray_tri.  tminp = tmin * 0.999.
@@ -206,9 +214,9 @@ PTB_DEV bool trav_run4(Trav& t, int* stack, const float4* __restrict__ nodes4, c
             const int nh = (int)h0 + (int)h1 + (int)h2 + (int)h3;
             if (nh == 0) t.node = stack[--t.sp];
             else {
-                if (nh > 3) stack[t.sp++] = c3;
-                if (nh > 2) stack[t.sp++] = c2;
-                if (nh > 1) stack[t.sp++] = c1;
+                if (nh > 3) { stack[t.sp++] = c3; trav_prefetch4(nodes4, tris, c3); }
+                if (nh > 2) { stack[t.sp++] = c2; trav_prefetch4(nodes4, tris, c2); }
+                if (nh > 1) { stack[t.sp++] = c1; trav_prefetch4(nodes4, tris, c1); }
                 t.node = c0;
             }
             --budget;
