@@ -5,20 +5,21 @@
 // over a pool that is larger than L2 (1.6 GB at 8 subframes): both kernels sat at ~45 % of HBM peak, stalled on
 // long-scoreboard, with an L2 hit rate below 30 % even for the 2 MB of geometry.
 //
-// Layout: one status byte per slot (ST_TRACE / ST_HIT / ST_MISS / ST_DONE).  A block owns PTB_CHUNK (2048)
-// consecutive slots.  Every stage first compacts the slots of its chunk that are in the wanted state into a list
-// in shared memory (8 status bytes per thread, warp ballot-free popcount + block scan; the list is ascending, so
-// the state accesses that follow are coalesced and fully use their sectors), then runs the stage body over that
-// list with all lanes busy:
-//   trace   lanes fetch rays from the shared list dynamically (shared-memory atomic per warp) and advance them
-//           in quanta (trav_run), as in k_trace
-//   shade   closest hit + Russian roulette + path regeneration
-//   miss    environment lookup + path regeneration
+// Layout: one status byte per slot (ST_TRACE / ST_HIT / ST_MISS / ST_DONE).  A block owns a CHUNK of consecutive slots
+// (256 threads x 1..8 slots per thread; 2048 slots for large launches, fewer for small ones so that they still fill the
+// chip).  Every stage first compacts the slots of its chunk that are in the wanted state(s) into ascending lists in
+// shared memory (status bytes read as words, popcount + one packed warp scan + block scan; ascending lists make the
+// state accesses that follow coalesced and whole-sector), then runs the stage body over the list with all lanes busy:
+//   trace        lanes fetch rays from the shared list dynamically (one shared-memory atomic per warp) and advance
+//                them in quanta (trav_run / trav_run4)
+//   shade, miss  closest hit or environment lookup, then Russian roulette + accumulation + path regeneration
 // Two drivers share the stage bodies:
-//   k_chunk_trace / k_chunk_shade / k_chunk_miss   one kernel per stage and wavefront iteration
-//   k_chunk_fused                                  a block loops trace -> shade -> miss over ITS chunk until every
-//                                                  pixel of the chunk has finished its samples: one launch, the
-//                                                  chunk's 96 KB of path state stays in L2/L1 between stages.
+//   k_chunk_trace / k_chunk_shade / k_chunk_miss   one kernel per stage and wavefront iteration (pipeline 2)
+//   k_chunk_fused                                  a block alternates {TRACE} -> trace and {HIT, MISS} -> shade+miss (one
+//                                                  merged stage) over ITS chunk until every pixel of the chunk has
+//                                                  finished its samples: one launch, the chunk's path state is re-read
+//                                                  out of L2 between stages (pipeline 3, the default).
+// Path state is read and written with evict-first hints (kernels.cuh: ldp / stp).
 // Counters (segments, hits, misses) are summed per block and added to the context totals once per block.
 #pragma once
 #include "kernels.cuh"

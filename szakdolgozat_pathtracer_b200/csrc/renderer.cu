@@ -3,16 +3,17 @@
 //
 // One ptb_launch() = one optixLaunch of the reference (optixSphere.cpp:1403-1418):
 // every pixel renders spp_per_launch samples, the result is folded into
-// Params.accum_buffer and tonemapped into Params.frame_buffer.  Internally:
+// Params.accum_buffer and tonemapped into Params.frame_buffer.  Internally
+// (ptb_render_cfg.pipeline):
 //
-//   k_raygen_init
-//   repeat spp*(max_depth+1) times:   k_trace -> k_shade, k_miss
-//   k_resolve
+//   3 (default)  k_chunk_raygen, k_chunk_fused (all wavefront iterations in one kernel), k_resolve
+//   4            k_pool_fused (persistent path pool, camera rays included), k_resolve
+//   2            k_chunk_raygen, spp*(max_depth+1) x { k_chunk_trace, k_chunk_shade, k_chunk_miss }, k_resolve
+//   1            k_raygen_init, spp*(max_depth+1) x { k_trace, k_shade, k_miss } over global queues, k_resolve
 //
 // All kernels of a launch go to the caller's stream without any host
-// synchronisation; queue sizes live in device memory (one counter triple per
-// iteration, zeroed by a single memset at launch start), so an iteration whose
-// queue is empty costs three no-op launches.
+// synchronisation; counters live in device memory and are folded into the
+// context's running totals by k_fold_totals at the end of the launch.
 #include <cuda_runtime.h>
 
 #include <cmath>

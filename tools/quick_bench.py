@@ -29,7 +29,7 @@ ap.add_argument("--pipeline", type=int, default=0)
 ap.add_argument("--refine", type=int, default=1)
 ap.add_argument("--morton", type=int, default=30)
 ap.add_argument("--treelet", type=int, default=256)
-ap.add_argument("--width", dest="bvh_width", type=int, default=0) if False else ap.add_argument("--bvh-width", type=int, default=0)
+ap.add_argument("--bvh-width", type=int, default=0)
 a = ap.parse_args()
 
 ctx = ptb.Context(0)
