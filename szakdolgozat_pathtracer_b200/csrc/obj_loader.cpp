@@ -17,10 +17,13 @@
 //     result (optixSphere.cpp:431, `materials` is never used).
 #include "host.h"
 
+#include <algorithm>
 #include <cmath>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 
 namespace ptb {
 
@@ -90,46 +93,45 @@ float parse_real(const char** token) {
 
 inline int fix_index(int idx, int n) { return idx > 0 ? idx - 1 : (idx == 0 ? 0 : n + idx); }
 
-struct Triple { int v, vt, vn; };
+// A face vertex as written in the file: raw 1-based / relative integers, ABSENT where a field is missing.  The
+// indices are resolved (fix_index) once the number of elements parsed BEFORE the face is known, which for a chunk in
+// the middle of the file is only the case after all chunks have been counted.
+const int ABSENT = INT32_MIN;
+struct RawTriple { int v, vt, vn; };
 
 // i, i/j, i//k, i/j/k
-Triple parse_triple(const char** token, int nv, int nvn, int nvt) {
-    Triple t = {-1, -1, -1};
-    t.v = fix_index(atoi(*token), nv);
+RawTriple parse_triple(const char** token) {
+    RawTriple t = {ABSENT, ABSENT, ABSENT};
+    t.v = atoi(*token);
     (*token) += strcspn(*token, "/ \t\r");
     if ((*token)[0] != '/') return t;
     (*token)++;
     if ((*token)[0] == '/') {
         (*token)++;
-        t.vn = fix_index(atoi(*token), nvn);
+        t.vn = atoi(*token);
         (*token) += strcspn(*token, "/ \t\r");
         return t;
     }
-    t.vt = fix_index(atoi(*token), nvt);
+    t.vt = atoi(*token);
     (*token) += strcspn(*token, "/ \t\r");
     if ((*token)[0] != '/') return t;
     (*token)++;
-    t.vn = fix_index(atoi(*token), nvn);
+    t.vn = atoi(*token);
     (*token) += strcspn(*token, "/ \t\r");
     return t;
 }
 
-}  // namespace
+// what one chunk of the file contributes
+struct Chunk {
+    std::vector<float> v, vn, vt;
+    std::vector<RawTriple> corners;     // 3 per triangle, fanned
+    std::vector<uint32_t> tri_counts;   // per triangle: elements of THIS chunk parsed before its face line (v, vn, vt)
+};
 
-bool load_obj(const std::string& path, ObjMesh& mesh, std::string& err) {
-    FILE* f = fopen(path.c_str(), "rb");
-    if (!f) { err = "Cannot open file [" + path + "]"; return false; }
-    std::string data;
-    char buf[1 << 16];
-    size_t n;
-    while ((n = fread(buf, 1, sizeof(buf), f)) > 0) data.append(buf, n);
-    fclose(f);
-
-    mesh = ObjMesh();
-    std::vector<Triple> face;
-    size_t pos = 0;
+void parse_chunk(const std::string& data, size_t pos, size_t end, Chunk& out) {
+    std::vector<RawTriple> face;
     std::string line;
-    while (pos < data.size()) {
+    while (pos < end) {
         // one line, accepting \n, \r\n and \r endings
         size_t e = pos;
         while (e < data.size() && data[e] != '\n' && data[e] != '\r') e++;
@@ -143,32 +145,98 @@ bool load_obj(const std::string& path, ObjMesh& mesh, std::string& err) {
         if (token[0] == 'v' && is_space(token[1])) {
             token += 2;
             float x = parse_real(&token), y = parse_real(&token), z = parse_real(&token);
-            mesh.v.push_back(x); mesh.v.push_back(y); mesh.v.push_back(z);
+            out.v.push_back(x); out.v.push_back(y); out.v.push_back(z);
         } else if (token[0] == 'v' && token[1] == 'n' && is_space(token[2])) {
             token += 3;
             float x = parse_real(&token), y = parse_real(&token), z = parse_real(&token);
-            mesh.vn.push_back(x); mesh.vn.push_back(y); mesh.vn.push_back(z);
+            out.vn.push_back(x); out.vn.push_back(y); out.vn.push_back(z);
         } else if (token[0] == 'v' && token[1] == 't' && is_space(token[2])) {
             token += 3;
             float x = parse_real(&token), y = parse_real(&token);
-            mesh.vt.push_back(x); mesh.vt.push_back(y);
+            out.vt.push_back(x); out.vt.push_back(y);
         } else if (token[0] == 'f' && is_space(token[1])) {
             token += 2;
             token += strspn(token, " \t");
             face.clear();
             while (token[0] != '\0' && token[0] != '\r' && token[0] != '\n') {
-                face.push_back(parse_triple(&token, (int)(mesh.v.size() / 3), (int)(mesh.vn.size() / 3), (int)(mesh.vt.size() / 2)));
+                face.push_back(parse_triple(&token));
                 token += strspn(token, " \t\r");
             }
             for (size_t k = 2; k < face.size(); ++k) {
-                const Triple tri[3] = {face[0], face[k - 1], face[k]};
-                for (int c = 0; c < 3; ++c) {
-                    ObjIndex ix; ix.v = tri[c].v; ix.vt = tri[c].vt; ix.vn = tri[c].vn;
-                    mesh.indices.push_back(ix);
-                }
+                out.corners.push_back(face[0]); out.corners.push_back(face[k - 1]); out.corners.push_back(face[k]);
+                out.tri_counts.push_back((uint32_t)(out.v.size() / 3)); out.tri_counts.push_back((uint32_t)(out.vn.size() / 3));
+                out.tri_counts.push_back((uint32_t)(out.vt.size() / 2));
             }
         }
         // g / o / s / usemtl / mtllib carry nothing the reference uses
+    }
+}
+
+}  // namespace
+
+// The file is cut at line ends into one chunk per host thread (at least 4 MB each); the chunks are parsed concurrently
+// and stitched together in file order, so the result is the same as a single sequential pass.
+bool load_obj(const std::string& path, ObjMesh& mesh, std::string& err) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) { err = "Cannot open file [" + path + "]"; return false; }
+    std::string data;
+    if (fseek(f, 0, SEEK_END) == 0) { const long sz = ftell(f); if (sz > 0) data.reserve((size_t)sz); fseek(f, 0, SEEK_SET); }
+    char buf[1 << 16];
+    size_t n;
+    while ((n = fread(buf, 1, sizeof(buf), f)) > 0) data.append(buf, n);
+    fclose(f);
+
+    unsigned hw = std::thread::hardware_concurrency();
+    if (hw == 0) hw = 1;
+    size_t min_chunk = 4u << 20;
+    if (const char* e = getenv("PTB_OBJ_CHUNK_BYTES")) { min_chunk = (size_t)std::max(1L, atol(e)); hw = 64; }  // tests: force many chunks
+    size_t n_chunks = std::min<size_t>(hw, data.size() / min_chunk + 1);
+    std::vector<size_t> cut(n_chunks + 1, data.size());
+    cut[0] = 0;
+    for (size_t k = 1; k < n_chunks; ++k) {
+        size_t p = data.size() / n_chunks * k;
+        if (p < cut[k - 1]) p = cut[k - 1];
+        while (p < data.size() && data[p] != '\n' && data[p] != '\r') p++;  // to the end of the line that is cut
+        if (p < data.size() && data[p] == '\r' && p + 1 < data.size() && data[p + 1] == '\n') p++;
+        cut[k] = p < data.size() ? p + 1 : data.size();
+    }
+    std::vector<Chunk> chunks(n_chunks);
+    {
+        std::vector<std::thread> pool;
+        for (size_t k = 1; k < n_chunks; ++k) pool.emplace_back([&, k]() { parse_chunk(data, cut[k], cut[k + 1], chunks[k]); });
+        parse_chunk(data, cut[0], cut[1], chunks[0]);
+        for (std::thread& th : pool) th.join();
+    }
+
+    mesh = ObjMesh();
+    std::vector<size_t> ov(n_chunks + 1, 0), ovn(n_chunks + 1, 0), ovt(n_chunks + 1, 0), oc(n_chunks + 1, 0);
+    for (size_t k = 0; k < n_chunks; ++k) {
+        ov[k + 1] = ov[k] + chunks[k].v.size() / 3; ovn[k + 1] = ovn[k] + chunks[k].vn.size() / 3;
+        ovt[k + 1] = ovt[k] + chunks[k].vt.size() / 2; oc[k + 1] = oc[k] + chunks[k].corners.size();
+    }
+    mesh.v.resize(ov[n_chunks] * 3); mesh.vn.resize(ovn[n_chunks] * 3); mesh.vt.resize(ovt[n_chunks] * 2);
+    mesh.indices.resize(oc[n_chunks]);
+    auto stitch = [&](size_t k) {
+        const Chunk& c = chunks[k];
+        if (!c.v.empty()) memcpy(&mesh.v[ov[k] * 3], c.v.data(), c.v.size() * sizeof(float));
+        if (!c.vn.empty()) memcpy(&mesh.vn[ovn[k] * 3], c.vn.data(), c.vn.size() * sizeof(float));
+        if (!c.vt.empty()) memcpy(&mesh.vt[ovt[k] * 2], c.vt.data(), c.vt.size() * sizeof(float));
+        for (size_t i = 0; i < c.corners.size(); ++i) {
+            const uint32_t* cnt = &c.tri_counts[(i / 3) * 3];
+            const int nv = (int)(ov[k] + cnt[0]), nvn = (int)(ovn[k] + cnt[1]), nvt = (int)(ovt[k] + cnt[2]);
+            const RawTriple& r = c.corners[i];
+            ObjIndex ix;
+            ix.v = fix_index(r.v, nv);
+            ix.vt = r.vt == ABSENT ? -1 : fix_index(r.vt, nvt);
+            ix.vn = r.vn == ABSENT ? -1 : fix_index(r.vn, nvn);
+            mesh.indices[oc[k] + i] = ix;
+        }
+    };
+    {
+        std::vector<std::thread> pool;
+        for (size_t k = 1; k < n_chunks; ++k) pool.emplace_back(stitch, k);
+        stitch(0);
+        for (std::thread& th : pool) th.join();
     }
     const int nv = (int)(mesh.v.size() / 3), nvn = (int)(mesh.vn.size() / 3), nvt = (int)(mesh.vt.size() / 2);
     for (const ObjIndex& ix : mesh.indices) {

@@ -14,9 +14,11 @@
 //  * a face vertex without a texcoord index gets uv = (0,0) (the reference
 //    indexes attrib.texcoords[-2], optixSphere.cpp:485-489);
 //  * the floor triangles get uv = (0,0) (left uninitialised at optixSphere.cpp:620-646).
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <random>
+#include <thread>
 
 #include "host.h"
 
@@ -61,38 +63,65 @@ bool build_scene_from_obj(const std::vector<std::string>& files, float scale, ui
     scene.tris.clear(); scene.mat_ids.clear(); scene.mats.clear();
     HostRng rng(material_seed);
     float minHeight = 10.0f;  // optixSphere.cpp:418
-    for (size_t i = 0; i < files.size(); ++i) {
-        ObjMesh mesh;
-        if (!load_obj(files[i], mesh, err)) { err = "Failed to load/parse .obj file: " + err; return false; }  // optixSphere.cpp:441-443
-        const size_t startIndex = scene.tris.size();
-        const bool have_vt = !mesh.vt.empty();
-        for (size_t t = 0; t + 2 < mesh.indices.size(); t += 3) {
-            ptb_float4 vertices[3], normals[3];
-            ptb_float2 uv[3];
-            for (int v = 0; v < 3; ++v) {
-                const ObjIndex& idx = mesh.indices[t + (size_t)v];
-                float vx = mesh.v[3 * (size_t)idx.v + 0] * scale;
-                float vy = mesh.v[3 * (size_t)idx.v + 1] * scale;
-                float vz = mesh.v[3 * (size_t)idx.v + 2] * scale;
-                vertices[v] = f4(vx, vy, vz, 0.0f);
-                if (idx.vn >= 0) {
-                    float nx = mesh.vn[3 * (size_t)idx.vn + 0], ny = mesh.vn[3 * (size_t)idx.vn + 1], nz = mesh.vn[3 * (size_t)idx.vn + 2];
-                    float inv = 1.0f / sqrtf(nx * nx + ny * ny + nz * nz);  // sutil normalize()
-                    normals[v] = f4(nx * inv, ny * inv, nz * inv, 0.0f);
-                } else {
-                    normals[v] = f4(0.0f, 1.0f, 0.0f, 0.0f);  // optixSphere.cpp:480-482
+
+    // Parse and flatten the files concurrently (one task per file, as many threads as the host offers): the result of a
+    // file does not depend on the others, and everything order-dependent -- triangle order, material indices, the
+    // material RNG, which error is reported -- is settled afterwards in file order.
+    struct PerFile { bool ok = false; std::string err; std::vector<ptb_TriangleData> tris; float min_y = 3.4e38f; };
+    std::vector<PerFile> per(files.size());
+    {
+        std::atomic<size_t> next(0);
+        auto work = [&]() {
+            for (size_t i = next++; i < files.size(); i = next++) {
+                PerFile& pf = per[i];
+                ObjMesh mesh;
+                pf.ok = load_obj(files[i], mesh, pf.err);
+                if (!pf.ok) continue;
+                const bool have_vt = !mesh.vt.empty();
+                pf.tris.reserve(mesh.indices.size() / 3);
+                for (size_t t = 0; t + 2 < mesh.indices.size(); t += 3) {
+                    ptb_float4 vertices[3], normals[3];
+                    ptb_float2 uv[3];
+                    for (int v = 0; v < 3; ++v) {
+                        const ObjIndex& idx = mesh.indices[t + (size_t)v];
+                        float vx = mesh.v[3 * (size_t)idx.v + 0] * scale;
+                        float vy = mesh.v[3 * (size_t)idx.v + 1] * scale;
+                        float vz = mesh.v[3 * (size_t)idx.v + 2] * scale;
+                        vertices[v] = f4(vx, vy, vz, 0.0f);
+                        if (idx.vn >= 0) {
+                            float nx = mesh.vn[3 * (size_t)idx.vn + 0], ny = mesh.vn[3 * (size_t)idx.vn + 1], nz = mesh.vn[3 * (size_t)idx.vn + 2];
+                            float inv = 1.0f / sqrtf(nx * nx + ny * ny + nz * nz);  // sutil normalize()
+                            normals[v] = f4(nx * inv, ny * inv, nz * inv, 0.0f);
+                        } else {
+                            normals[v] = f4(0.0f, 1.0f, 0.0f, 0.0f);  // optixSphere.cpp:480-482
+                        }
+                        if (have_vt && idx.vt >= 0) { uv[v].x = mesh.vt[2 * (size_t)idx.vt + 0]; uv[v].y = mesh.vt[2 * (size_t)idx.vt + 1]; }
+                        else { uv[v].x = 0.0f; uv[v].y = 0.0f; }
+                    }
+                    for (int v = 0; v < 3; ++v) if (vertices[v].y < pf.min_y) pf.min_y = vertices[v].y;  // optixSphere.cpp:497-499
+                    ptb_TriangleData tri;
+                    memset(&tri, 0, sizeof(tri));
+                    tri.v0 = vertices[0]; tri.v1 = vertices[1]; tri.v2 = vertices[2];
+                    tri.n0 = normals[0]; tri.n1 = normals[1]; tri.n2 = normals[2];
+                    tri.uv0 = uv[0]; tri.uv1 = uv[1]; tri.uv2 = uv[2];
+                    pf.tris.push_back(tri);
                 }
-                if (have_vt && idx.vt >= 0) { uv[v].x = mesh.vt[2 * (size_t)idx.vt + 0]; uv[v].y = mesh.vt[2 * (size_t)idx.vt + 1]; }
-                else { uv[v].x = 0.0f; uv[v].y = 0.0f; }
             }
-            for (int v = 0; v < 3; ++v) if (vertices[v].y < minHeight) minHeight = vertices[v].y;  // optixSphere.cpp:497-499
-            ptb_TriangleData tri;
-            memset(&tri, 0, sizeof(tri));
-            tri.v0 = vertices[0]; tri.v1 = vertices[1]; tri.v2 = vertices[2];
-            tri.n0 = normals[0]; tri.n1 = normals[1]; tri.n2 = normals[2];
-            tri.uv0 = uv[0]; tri.uv1 = uv[1]; tri.uv2 = uv[2];
-            scene.tris.push_back(tri);
-        }
+        };
+        unsigned nthreads = std::thread::hardware_concurrency();
+        if (nthreads == 0) nthreads = 1;
+        if (nthreads > files.size()) nthreads = (unsigned)files.size();
+        std::vector<std::thread> pool;
+        for (unsigned k = 1; k < nthreads; ++k) pool.emplace_back(work);
+        work();
+        for (std::thread& th : pool) th.join();
+    }
+    for (size_t i = 0; i < files.size(); ++i) {
+        if (!per[i].ok) { err = "Failed to load/parse .obj file: " + per[i].err; return false; }  // optixSphere.cpp:441-443
+        const size_t startIndex = scene.tris.size();
+        scene.tris.insert(scene.tris.end(), per[i].tris.begin(), per[i].tris.end());
+        std::vector<ptb_TriangleData>().swap(per[i].tris);
+        if (per[i].min_y < minHeight) minHeight = per[i].min_y;
 
         // optixSphere.cpp:516-582: textures by file-name convention, else a random material.
         Material m;
