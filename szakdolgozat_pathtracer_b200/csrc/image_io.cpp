@@ -13,6 +13,9 @@
 
 #include <zlib.h>
 
+#include <atomic>
+#include <thread>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -387,42 +390,60 @@ bool load_exr_float4(const std::string& path, std::vector<float>& rgba, int& w, 
     memcpy(offsets.data(), &f[pos], (size_t)nblocks * 8);
     rgba.assign((size_t)w * h * 4, 0.0f);
     for (size_t i = 3; i < rgba.size(); i += 4) rgba[i] = 1.0f;
-    std::vector<uint8_t> block, tmp;
-    for (int b = 0; b < nblocks; ++b) {
-        size_t p = (size_t)offsets[(size_t)b];
-        if (!need(p, 8)) { err = "EXR: bad chunk offset"; return false; }
-        int y0 = (int)rd32(p) - dw[1];
-        uint32_t csize = rd32(p + 4);
-        p += 8;
-        if (!need(p, csize) || y0 < 0 || y0 >= h) { err = "EXR: bad chunk"; return false; }
-        int nl = std::min(lines_per_block, h - y0);
-        size_t expected = line_bytes * (size_t)nl;
-        if (compression == 0 || csize == expected) block.assign(&f[p], &f[p] + csize);
-        else if (compression == 1) {
-            if (!exr_rle_decode(&f[p], csize, block, expected)) { err = "EXR: RLE decode failed"; return false; }
-            exr_unpredict_interleave(block);
-        } else {
-            if (!zlib_inflate(&f[p], csize, block, expected, err)) return false;
-            exr_unpredict_interleave(block);
-        }
-        if (block.size() != expected) { err = "EXR: unexpected chunk size"; return false; }
-        for (int l = 0; l < nl; ++l) {
-            const uint8_t* line = block.data() + line_bytes * (size_t)l;
-            float* dst = &rgba[(size_t)(y0 + l) * w * 4];
-            for (int s = 0; s < 4; ++s) {
-                int c = slot_of[s];
-                if (c < 0) continue;
-                const uint8_t* src = line + chan_off[(size_t)c];
-                for (int x = 0; x < w; ++x) {
-                    float v;
-                    if (chans[(size_t)c].type == 1) { uint16_t hb; memcpy(&hb, src + (size_t)x * 2, 2); v = half_to_float(hb); }
-                    else if (chans[(size_t)c].type == 2) memcpy(&v, src + (size_t)x * 4, 4);
-                    else { uint32_t u; memcpy(&u, src + (size_t)x * 4, 4); v = (float)u; }
-                    dst[(size_t)x * 4 + s] = v;
+    // The chunks (1 or 16 scanlines each) are independent: decode them on all host threads.  The first error in chunk order
+    // is the one reported, as in a sequential pass.
+    std::vector<std::string> block_err((size_t)nblocks);
+    std::atomic<int> next_block(0);
+    auto decode = [&]() {
+        std::vector<uint8_t> block;
+        for (int b = next_block++; b < nblocks; b = next_block++) {
+            std::string& berr = block_err[(size_t)b];
+            size_t p = (size_t)offsets[(size_t)b];
+            if (!need(p, 8)) { berr = "EXR: bad chunk offset"; continue; }
+            int y0 = (int)rd32(p) - dw[1];
+            uint32_t csize = rd32(p + 4);
+            p += 8;
+            if (!need(p, csize) || y0 < 0 || y0 >= h) { berr = "EXR: bad chunk"; continue; }
+            int nl = std::min(lines_per_block, h - y0);
+            size_t expected = line_bytes * (size_t)nl;
+            if (compression == 0 || csize == expected) block.assign(&f[p], &f[p] + csize);
+            else if (compression == 1) {
+                if (!exr_rle_decode(&f[p], csize, block, expected)) { berr = "EXR: RLE decode failed"; continue; }
+                exr_unpredict_interleave(block);
+            } else {
+                if (!zlib_inflate(&f[p], csize, block, expected, berr)) { if (berr.empty()) berr = "EXR: inflate failed"; continue; }
+                exr_unpredict_interleave(block);
+            }
+            if (block.size() != expected) { berr = "EXR: unexpected chunk size"; continue; }
+            for (int l = 0; l < nl; ++l) {
+                const uint8_t* line = block.data() + line_bytes * (size_t)l;
+                float* dst = &rgba[(size_t)(y0 + l) * w * 4];
+                for (int s = 0; s < 4; ++s) {
+                    int c = slot_of[s];
+                    if (c < 0) continue;
+                    const uint8_t* src = line + chan_off[(size_t)c];
+                    for (int x = 0; x < w; ++x) {
+                        float v;
+                        if (chans[(size_t)c].type == 1) { uint16_t hb; memcpy(&hb, src + (size_t)x * 2, 2); v = half_to_float(hb); }
+                        else if (chans[(size_t)c].type == 2) memcpy(&v, src + (size_t)x * 4, 4);
+                        else { uint32_t u; memcpy(&u, src + (size_t)x * 4, 4); v = (float)u; }
+                        dst[(size_t)x * 4 + s] = v;
+                    }
                 }
             }
         }
+    };
+    {
+        unsigned nthreads = std::thread::hardware_concurrency();
+        if (nthreads == 0) nthreads = 1;
+        if ((int)nthreads > nblocks) nthreads = (unsigned)nblocks;
+        if ((size_t)w * h < (1u << 16)) nthreads = 1;
+        std::vector<std::thread> pool;
+        for (unsigned k = 1; k < nthreads; ++k) pool.emplace_back(decode);
+        decode();
+        for (std::thread& th : pool) th.join();
     }
+    for (int b = 0; b < nblocks; ++b) if (!block_err[(size_t)b].empty()) { err = block_err[(size_t)b]; return false; }
     return true;
 }
 
