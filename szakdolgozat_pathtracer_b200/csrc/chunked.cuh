@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(PTB_CHUNK_THREADS) k_chunk_miss(SceneView s, F
 // iteration (one code copy, alternating phases): {TRACE, BUSY} before the trace stage, {HIT, MISS} before shade + miss.
 // totals[3] is not touched here (launch count is added by k_fold_counters' sibling on the host path).
 template <bool COUNT, int QUANTUM, int MINB, int SPT>
-__global__ void __launch_bounds__(PTB_CHUNK_THREADS, (MINB * 128) / PTB_CHUNK_THREADS) k_chunk_fused(SceneView s, FrameView f, PathView p, unsigned char* status,
+__global__ void __launch_bounds__(PTB_CHUNK_THREADS, (MINB * 128 + PTB_CHUNK_THREADS - 1) / PTB_CHUNK_THREADS) k_chunk_fused(SceneView s, FrameView f, PathView p, unsigned char* status,
                                                                   unsigned long long* totals, unsigned long long* trav_stats,
                                                                   unsigned int* max_iters_seen) {
     __shared__ ChunkSharedT<SPT> sh;
