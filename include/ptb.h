@@ -13,7 +13,13 @@
  *    from CUDA_CHECK/OPTIX_CHECK and exits 1 (optixSphere.cpp:1532-1537).
  *  - one context is used from one host thread at a time, like the reference's
  *    single-threaded render loop (optixSphere.cpp:1390-1437).
- *  - ptb_launch() is asynchronous on the given stream, like optixLaunch.
+ *  - ptb_launch() is asynchronous on the given stream, like optixLaunch.  All
+ *    launches of one context share its path pool and counters: ONE launch in
+ *    flight per context (issue the next one on the same stream, or synchronise
+ *    first); use one context per stream for concurrent launches.
+ *  - a handle from ptb_accel_build() names the upload of the scene AS IT WAS;
+ *    ptb_launch() fails with PTB_ERR_INVALID when the scene was modified since
+ *    (materials, environment, geometry) until it is built again.
  *  - there is NO CPU fallback: every compute entry point fails with
  *    PTB_ERR_NO_DEVICE when no CUDA device is usable.
  */
@@ -163,7 +169,7 @@ typedef struct ptb_build_cfg {
     int32_t max_leaf_size; /* triangles per leaf after refinement (1..8), default 4 */
     int32_t sah_refine;    /* 1: binned-SAH refinement of the LBVH (default); 0: plain LBVH */
     int32_t sah_bins;      /* default 16 */
-    int32_t treelet_size;  /* primitives per refinement treelet, default 512 */
+    int32_t treelet_size;  /* primitives per refinement treelet, default 256 (the maximum; larger values are clamped) */
     int32_t morton_bits;   /* 30 (default: 10 bits per axis) or 63 (21 bits per axis) */
     int32_t bvh_width;     /* 0 (default): 4-wide traversal for large scenes, 2-wide otherwise; 2 or 4 force one.  The
                               hit rule does not depend on the tree, so results are identical. */
@@ -174,6 +180,8 @@ typedef struct ptb_build_stats {
     float sah_cost;        /* sum(area*cost)/root area, Ct=1 Ci=1 */
     float build_ms;        /* device time of the build (CUDA events) */
     uint64_t bvh_bytes;
+    uint32_t bvh_width;    /* 2 or 4: the tree the traversal kernels walk (ptb_build_cfg.bvh_width = 0 picks by scene size) */
+    uint32_t _reserved;
 } ptb_build_stats;
 
 typedef struct ptb_material_info {
@@ -307,6 +315,11 @@ int ptb_image_load_float4(const char* path, float** pixels, int* w, int* h);
 /* .png or .ppm by extension; rows are written bottom-up (row 0 of the frame buffer is
  * the bottom image row, optixSphere.cu:332,400) when flip_y != 0 */
 int ptb_save_image(const char* path, const ptb_uchar4* pixels, int w, int h, int flip_y);
+/* the float4 accumulation buffer (HOST copy of Params.accum_buffer, optixSphere.cpp:1298-1301) as a raw file for parity
+ * tools: 16-byte header {"PTBA", 1, w, h} + w*h float4, row 0 = bottom image row.  ptb_load_accum_raw() reads it back
+ * (release with ptb_free()). */
+int ptb_save_accum_raw(const char* path, const ptb_float4* accum, int w, int h);
+int ptb_load_accum_raw(const char* path, float** accum, int* w, int* h);
 void ptb_free(void* p);
 /* The OBJ reader on its own (what tinyobj::LoadObj(triangulate=true) hands to the reference,
  * optixSphere.cpp:431, 447-515): per face vertex, in file/fan order, 10 words =
@@ -322,7 +335,8 @@ int ptb_microbench_read(ptb_context* ctx, size_t bytes, int iters, double* gb_pe
 
 /* ---- device self-test hooks used by the parity tests --------------------------- */
 /* op: 0 rng (in: seed as uint bits -> out: next seed bits, u), 1 sincos (x -> s, c),
- *     2 atan2 (y, x -> r), 3 asin (x -> r).  in/out are HOST arrays. */
+ *     2 atan2 (y, x -> r), 3 asin (x -> r), 4 texel widening (b -> b/255 two ways), 5 pow (x, y -> r).
+ *     in/out are HOST arrays. */
 /* n samples of the scene's environment CDF: xi = n x 2 uniforms (HOST) -> out = n x 4 (direction xyz, solid-angle pdf) */
 int ptb_test_env_sample(ptb_context* ctx, unsigned long long handle, const float* xi, uint32_t n, float* out);
 int ptb_test_device_math(ptb_context* ctx, int op, const float* in, int in_stride, float* out, int out_stride, uint32_t n);

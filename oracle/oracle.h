@@ -102,6 +102,7 @@ uint32_t orc_rng_next(uint32_t seed, int32_t sat_cuda, float* u); /* returns new
 void orc_sincos(float x, float* s, float* c);
 float orc_atan2(float y, float x);
 float orc_asin(float x);
+float orc_pow(float x, float y); /* detmath pow of the display transform */
 void orc_tonemap_pixel(const float accum_rgb[3], const OrcConfig* cfg, uint8_t out_rgba[4]);
 void orc_sample_texture(const OrcTexture* tex, float u, float v, float out[4]);
 void orc_sample_env(const float* env_rgba, int32_t w, int32_t h, const float dir[3], float out[4]);

@@ -12,7 +12,7 @@
 //     SDK source as remembered: PARITY UNPINNED at this boundary.
 //  2. The reference's RNG (optixSphere.cu:24-35), including CUDA's saturating
 //     float->uint conversion which is undefined behaviour in host C++.
-//  3. "detmath": deterministic single-precision sin/cos/atan2/asin built only
+//  3. "detmath": deterministic single-precision sin/cos/atan2/asin (and a double-precision pow) built only
 //     from IEEE +,-,*,/,sqrt in a fixed order (Cephes single-precision
 //     algorithms), so that the CPU oracle and the CUDA kernels produce
 //     bit-identical results.  The reference calls CUDA libm (cosf/sinf/atan2f/
@@ -151,5 +151,42 @@ static inline float det_asinf(float xx) {
 // (1-c)^5 as used by both Schlick terms (optixSphere.cu:483,491).  The
 // reference calls powf(x, 5.0f); the oracle rule is x2=x*x; x4=x2*x2; x4*x.
 static inline float det_pow5(float x) { float x2 = x * x; float x4 = x2 * x2; return x4 * x; }
+
+// pow(x, y) of the display transform (optixSphere.cu:425 `pow(rgb, 1/2.2)`; SDK make_color's powf(c, 1/2.4f)).  The
+// reference calls CUDA's powf; glibc's differs from it in the last bit for some inputs, which moved 8-bit frame values
+// by one LSB.  detmath evaluates exp2(y * log2(x)) in IEEE DOUBLE precision with a fixed operation order over +,-,*,/
+// (atanh series for the logarithm, Taylor series for the exponential, both truncated below 1e-16) and rounds ONCE to
+// float: the correctly rounded x^y unless the exact value lies within ~1e-8 ulp of a rounding boundary.  Same code
+// on the device (csrc/device_math.cuh), so frame bytes are bit-identical.
+static inline double det_bits_to_double(uint64_t b) { double d; memcpy(&d, &b, 8); return d; }
+static inline float det_powf(float xf, float yf) {
+    if (yf == 0.0f || xf == 1.0f) return 1.0f;
+    if (xf != xf || yf != yf) return xf + yf;
+    if (xf < 0.0f) return xf * 0.0f / 0.0f;  // NaN; never produced by the display transform (inputs are clamped to [0, 1])
+    if (xf == 0.0f) return yf > 0.0f ? 0.0f : 1.0f / 0.0f;
+    if (xf > 3.0e38f) return yf > 0.0f ? xf : 0.0f;
+    const double x = (double)xf;  // a float subnormal is a normal double
+    uint64_t b; memcpy(&b, &x, 8);
+    int e = (int)((b >> 52) & 0x7ffu) - 1023;
+    double m = det_bits_to_double((b & 0x000fffffffffffffull) | 0x3ff0000000000000ull);  // [1, 2)
+    if (m > 1.4142135623730951) { m = m * 0.5; e += 1; }
+    const double s = (m - 1.0) / (m + 1.0), s2 = s * s;  // |s| <= 0.1716
+    double p = 1.0 / 23.0;
+    p = p * s2 + 1.0 / 21.0; p = p * s2 + 1.0 / 19.0; p = p * s2 + 1.0 / 17.0; p = p * s2 + 1.0 / 15.0;
+    p = p * s2 + 1.0 / 13.0; p = p * s2 + 1.0 / 11.0; p = p * s2 + 1.0 / 9.0; p = p * s2 + 1.0 / 7.0;
+    p = p * s2 + 1.0 / 5.0; p = p * s2 + 1.0 / 3.0; p = p * s2 + 1.0;
+    const double log2x = (double)e + (2.0 * s * p) * 1.4426950408889634;
+    const double t = (double)yf * log2x;
+    if (t >= 128.0) return 1.0f / 0.0f;
+    if (t < -160.0) return 0.0f;
+    const double n = floor(t + 0.5);
+    const double z = (t - n) * 0.6931471805599453;  // |z| <= 0.3466
+    double q = 1.0 / 87178291200.0;  // 1/14!
+    q = q * z + 1.0 / 6227020800.0; q = q * z + 1.0 / 479001600.0; q = q * z + 1.0 / 39916800.0; q = q * z + 1.0 / 3628800.0;
+    q = q * z + 1.0 / 362880.0; q = q * z + 1.0 / 40320.0; q = q * z + 1.0 / 5040.0; q = q * z + 1.0 / 720.0;
+    q = q * z + 1.0 / 120.0; q = q * z + 1.0 / 24.0; q = q * z + 1.0 / 6.0; q = q * z + 0.5; q = q * z + 1.0; q = q * z + 1.0;
+    const double scale = det_bits_to_double((uint64_t)((long long)n + 1023ll) << 52);  // 2^n, -160 <= n <= 128
+    return (float)(q * scale);
+}
 
 }  // namespace orc

@@ -9,7 +9,7 @@
 //  * The shading/RNG/estimator logic IS pinned against the reference's own
 //    source compiled on the host (oracle/_ref/libref_pt.so, built by
 //    oracle/Makefile from /root/reference/optixSphere.cu through ref_shim/):
-//    tests/test_oracle_vs_ref.py requires bit-identical accum buffers.
+//    tests/test_oracle_pins.py requires bit-identical accum buffers, frames, hit IDs.
 //  * PARITY UNPINNED at the OptiX/sutil boundary (closed source or absent):
 //    ray/triangle intersection + traversal (oracle_isect.h), vec_math.h
 //    helpers and make_color (oracle_math.h, restated from the SDK as
@@ -21,7 +21,8 @@
 //     sequenced left to right (cu:328, cu:260).
 //  R3 texel fetches use the reference's linear index y*w+x; where that is
 //     negative (x0 or y0 == -1, cu:509-510, cu:579-580: an out-of-bounds read
-//     in the reference) it wraps by +w*h.  A NaN coordinate maps to index 0
+//     in the reference) it wraps by +w*h (twice for one-row images, where
+//     -w-1 + w*h is still negative).  A NaN coordinate maps to index 0
 //     (CUDA cvt of NaN).
 //  R4 the path loop also ends when done && !(p > 0), contributing 0 (cu:384).
 //  R5 one texture set per material (the reference shares one global device
@@ -161,6 +162,7 @@ inline v3 GGX_importance_sample(float r1, float r2, float alpha) {
 inline v4 texel(const float* img, int w, int h, int x, int y) {
     long long idx = (long long)y * (long long)w + (long long)x;
     if (idx < 0) idx += (long long)w * (long long)h;
+    if (idx < 0) idx += (long long)w * (long long)h;  // one-row images: y = -1, x = -1 gives -w - 1 (idx >= -w - 1 always)
     const float* p = img + (size_t)idx * 4;
     return mk4(p[0], p[1], p[2], p[3]);
 }
@@ -334,7 +336,7 @@ void miss(const Ctx& c, v3 dir, Payload& io) {
 // SDK cuda/helpers.h make_color (restated): clamp -> sRGB -> quantize.
 inline float to_srgb1(float c) {
     float invGamma = 1.0f / 2.4f;
-    float powed = powf(c, invGamma);
+    float powed = det_powf(c, invGamma);
     return c < 0.0031308f ? 12.92f * c : 1.055f * powed - 0.055f;
 }
 inline uint8_t quantize8(float x) {
@@ -348,7 +350,7 @@ void tonemap_pixel(v3 accum_color, const OrcConfig& cfg, uint8_t out[4]) {
     rgb = tonemap(rgb);
     rgb = clamp(rgb, 0.0f, 1.0f);
     float ig = 1.0f / cfg.gamma;
-    rgb = mk3(powf(rgb.x, ig), powf(rgb.y, ig), powf(rgb.z, ig));
+    rgb = mk3(det_powf(rgb.x, ig), det_powf(rgb.y, ig), det_powf(rgb.z, ig));
     rgb = (rgb - 0.5f) * cfg.contrast + 0.5f;  // cu:433: 0.5f + contrast * (rgb - 0.5f)
     v3 s = clamp(rgb, 0.0f, 1.0f);
     out[0] = quantize8(to_srgb1(s.x)); out[1] = quantize8(to_srgb1(s.y)); out[2] = quantize8(to_srgb1(s.z)); out[3] = 255;
@@ -488,6 +490,7 @@ uint32_t orc_rng_next(uint32_t seed, int32_t sat_cuda, float* u) {
 void orc_sincos(float x, float* s, float* c) { det_sincosf(x, s, c); }
 float orc_atan2(float y, float x) { return det_atan2f(y, x); }
 float orc_asin(float x) { return det_asinf(x); }
+float orc_pow(float x, float y) { return det_powf(x, y); }
 void orc_tonemap_pixel(const float rgb[3], const OrcConfig* cfg, uint8_t out[4]) { tonemap_pixel(mk3(rgb[0], rgb[1], rgb[2]), *cfg, out); }
 void orc_sample_texture(const OrcTexture* tex, float u, float v, float out[4]) {
     v4 c = sampleTexture(tex->rgba, tex->w, tex->h, u, v);

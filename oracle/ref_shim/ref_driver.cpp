@@ -166,6 +166,7 @@ uint32_t orc_rng_next(uint32_t seed, int32_t, float* u) {
 void orc_sincos(float x, float* s, float* c) { *s = sinf(x); *c = cosf(x); }
 float orc_atan2(float y, float x) { return atan2f(y, x); }
 float orc_asin(float x) { return asinf(x); }
+float orc_pow(float x, float y) { return powf(x, y); }
 void orc_tonemap_pixel(const float rgb[3], const OrcConfig*, uint8_t out[4]) {
     // cu:411-435 inlined in __raygen__rg; not separately callable.  Unsupported here.
     (void)rgb; out[0] = out[1] = out[2] = out[3] = 0;

@@ -13,7 +13,8 @@
 //     oracle's closest-hit query (oracle_isect.h) instead of RT cores;
 //   * CUDA libm: cosf/sinf/atan2f/asinf and powf(x,5) are routed to the
 //     oracle's detmath so that reference-on-host and oracle can be compared
-//     bit for bit; powf with any other exponent stays glibc's.
+//     bit for bit; powf with any other exponent (the display transform) is
+//     detmath's double-precision det_powf on both sides.
 //   * make_floatN(...) are macros that brace-initialise, which sequences the
 //     reference's `make_float2(myrnd(seed), myrnd(seed))` (cu:328, cu:15)
 //     left to right (oracle rule R2; g++ would evaluate right to left).
@@ -116,7 +117,7 @@ static inline bool refract(float3& r, const float3& i, const float3& n, float io
 // ---- cuda/helpers.h make_color (restated) ------------------------------------
 static inline float3 toSRGB(const float3& c) {
     float invGamma = 1.0f / 2.4f;
-    float3 powed = float3{::powf(c.x, invGamma), ::powf(c.y, invGamma), ::powf(c.z, invGamma)};
+    float3 powed = float3{orc::det_powf(c.x, invGamma), orc::det_powf(c.y, invGamma), orc::det_powf(c.z, invGamma)};
     return float3{c.x < 0.0031308f ? 12.92f * c.x : 1.055f * powed.x - 0.055f,
                   c.y < 0.0031308f ? 12.92f * c.y : 1.055f * powed.y - 0.055f,
                   c.z < 0.0031308f ? 12.92f * c.z : 1.055f * powed.z - 0.055f};
@@ -136,7 +137,7 @@ static inline unsigned int __float_as_uint(float f) { unsigned int u; memcpy(&u,
 static inline float __uint_as_float(unsigned int u) { float f; memcpy(&f, &u, 4); return f; }
 
 // ---- libm routing (see header comment) ----------------------------------------
-static inline float shim_powf(float a, float b) { return b == 5.0f ? orc::det_pow5(a) : ::powf(a, b); }
+static inline float shim_powf(float a, float b) { return b == 5.0f ? orc::det_pow5(a) : orc::det_powf(a, b); }
 #define cosf(x) orc::det_cosf(x)
 #define sinf(x) orc::det_sinf(x)
 #define atan2f(y, x) orc::det_atan2f(y, x)

@@ -96,7 +96,7 @@ class BuildCfg(C.Structure):
 class BuildStats(C.Structure):
     _fields_ = [
         ("num_triangles", C.c_uint32), ("num_nodes", C.c_uint32), ("num_leaves", C.c_uint32), ("max_depth", C.c_uint32),
-        ("sah_cost", C.c_float), ("build_ms", C.c_float), ("bvh_bytes", C.c_uint64),
+        ("sah_cost", C.c_float), ("build_ms", C.c_float), ("bvh_bytes", C.c_uint64), ("bvh_width", C.c_uint32), ("_reserved", C.c_uint32),
     ]
 
 
@@ -122,7 +122,7 @@ EXPORTS = [
     "ptb_resolve", "ptb_resolve_peers", "ptb_ipc_export", "ptb_ipc_open", "ptb_ipc_close", "ptb_trace_rays", "ptb_output_create", "ptb_output_resize", "ptb_output_map", "ptb_output_unmap",
     "ptb_output_host_ptr", "ptb_output_width", "ptb_output_height", "ptb_output_destroy", "ptb_device_alloc",
     "ptb_device_free", "ptb_device_memset", "ptb_copy_to_device", "ptb_copy_to_host", "ptb_image_load_rgba8",
-    "ptb_image_load_float4", "ptb_save_image", "ptb_free", "ptb_obj_read", "ptb_microbench_read", "ptb_test_env_sample", "ptb_test_device_math",
+    "ptb_image_load_float4", "ptb_save_image", "ptb_save_accum_raw", "ptb_load_accum_raw", "ptb_free", "ptb_obj_read", "ptb_microbench_read", "ptb_test_env_sample", "ptb_test_device_math",
 ]
 
 _lib = None
@@ -521,3 +521,19 @@ def obj_read(path) -> np.ndarray:
 def save_image(path, rgba: np.ndarray, flip_y=True):
     a = np.ascontiguousarray(rgba, np.uint8)
     _check(lib().ptb_save_image(os.fsencode(str(path)), _fptr(a), a.shape[1], a.shape[0], int(bool(flip_y))))
+
+
+def save_accum_raw(path, accum: np.ndarray):
+    """Host copy of the float4 accumulation buffer -> raw 'PTBA' file (ptb_save_accum_raw)."""
+    a = np.ascontiguousarray(accum, np.float32)
+    assert a.ndim == 3 and a.shape[2] == 4
+    _check(lib().ptb_save_accum_raw(os.fsencode(str(path)), _fptr(a), a.shape[1], a.shape[0]))
+
+
+def load_accum_raw(path) -> np.ndarray:
+    px, w, h = C.c_void_p(), C.c_int(), C.c_int()
+    _check(lib().ptb_load_accum_raw(os.fsencode(str(path)), C.byref(px), C.byref(w), C.byref(h)))
+    try:
+        return np.ctypeslib.as_array(C.cast(px, C.POINTER(C.c_float)), shape=(h.value, w.value, 4)).copy()
+    finally:
+        lib().ptb_free(px)

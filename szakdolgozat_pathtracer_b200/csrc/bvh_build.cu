@@ -440,8 +440,16 @@ struct Scratch {
 
 }  // namespace
 
-bool build_bvh(const float4* d_verts, uint32_t n, const ptb_build_cfg& cfg, cudaStream_t stream, DeviceBvh& out,
-               ptb_build_stats& stats, std::string& err) {
+void free_bvh(DeviceBvh& b);
+
+namespace {
+struct EventPair {  // destroyed on every return path of the build
+    cudaEvent_t a = nullptr, b = nullptr;
+    ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+};
+
+bool build_bvh_impl(const float4* d_verts, uint32_t n, const ptb_build_cfg& cfg, cudaStream_t stream, DeviceBvh& out,
+                    ptb_build_stats& stats, std::string& err) {
     memset(&stats, 0, sizeof(stats));
     stats.num_triangles = n;
     const int max_leaf = cfg.max_leaf_size < 1 ? 1 : (cfg.max_leaf_size > 8 ? 8 : cfg.max_leaf_size);
@@ -459,8 +467,9 @@ bool build_bvh(const float4* d_verts, uint32_t n, const ptb_build_cfg& cfg, cuda
     out.nodes4 = nullptr;
     if (wide && cudaMalloc((void**)&out.nodes4, (size_t)n_nodes * 128) != cudaSuccess) { cudaFree(d_nodes); cudaFree(d_tris); out.nodes = out.tris = nullptr; err = "cudaMalloc (4-wide BVH nodes) failed"; return false; }
 
-    cudaEvent_t ev0, ev1;
-    CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
+    EventPair evs;
+    CK(cudaEventCreate(&evs.a)); CK(cudaEventCreate(&evs.b));
+    const cudaEvent_t ev0 = evs.a, ev1 = evs.b;
 
     if (n < 2) {
         // Degenerate scenes: a root whose missing children have NaN boxes (never entered).
@@ -484,7 +493,8 @@ bool build_bvh(const float4* d_verts, uint32_t n, const ptb_build_cfg& cfg, cuda
         CK(cudaMemcpyAsync(d_nodes, h, 64, cudaMemcpyHostToDevice, stream));
         CK(cudaStreamSynchronize(stream));
         stats.num_nodes = 1; stats.num_leaves = n; stats.max_depth = 1; stats.bvh_bytes = 64 + (uint64_t)n * 48;
-        cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+        stats.bvh_width = 2;
+        if (out.nodes4) { cudaFree(out.nodes4); out.nodes4 = nullptr; }
         return true;
     }
 
@@ -564,7 +574,6 @@ bool build_bvh(const float4* d_verts, uint32_t n, const ptb_build_cfg& cfg, cuda
     CK(cudaStreamSynchronize(stream));
     float ms = 0.0f;
     CK(cudaEventElapsedTime(&ms, ev0, ev1));
-    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
 
     const float dx = root_hi.x - root_lo.x, dy = root_hi.y - root_lo.y, dz = root_hi.z - root_lo.z;
     const float root_area = dx * dy + dy * dz + dz * dx;
@@ -574,11 +583,22 @@ bool build_bvh(const float4* d_verts, uint32_t n, const ptb_build_cfg& cfg, cuda
     stats.bvh_bytes = (uint64_t)n_nodes * 64 + (uint64_t)n * 48 + (out.nodes4 ? (uint64_t)n_nodes * 128 : 0);
     // the 4-wide traversal pushes up to three entries per level of the collapsed tree (half the 2-wide depth)
     if (out.nodes4 && (stats.max_depth / 2 + 1) * 3 + 2 >= PTB_BVH_MAX_DEPTH) { cudaFree(out.nodes4); out.nodes4 = nullptr; }
+    stats.bvh_width = out.nodes4 ? 4 : 2;  // what the traversal kernels will walk
     if (stats.max_depth >= PTB_BVH_MAX_DEPTH) {
         err = "BVH build: tree depth " + std::to_string(stats.max_depth) + " exceeds the traversal stack (" + std::to_string(PTB_BVH_MAX_DEPTH) + ")";
         return false;
     }
     return true;
+}
+}  // namespace
+
+// Owns its outputs until it succeeds: a failed build leaves `out` empty (events and scratch are RAII).
+bool build_bvh(const float4* d_verts, uint32_t n, const ptb_build_cfg& cfg, cudaStream_t stream, DeviceBvh& out,
+               ptb_build_stats& stats, std::string& err) {
+    out = DeviceBvh();
+    const bool ok = build_bvh_impl(d_verts, n, cfg, stream, out, stats, err);
+    if (!ok) free_bvh(out);
+    return ok;
 }
 
 void free_bvh(DeviceBvh& b) {

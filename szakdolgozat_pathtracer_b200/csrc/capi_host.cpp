@@ -2,6 +2,7 @@
 // objects, camera, defaults, image files.  The device half is renderer.cu.
 #include <cmath>
 #include <cstdlib>
+#include <cstdio>
 #include <cstring>
 
 #include "host.h"
@@ -60,7 +61,7 @@ void ptb_default_render_cfg(ptb_render_cfg* cfg) {
 
 void ptb_default_build_cfg(ptb_build_cfg* cfg) {
     if (!cfg) return;
-    cfg->max_leaf_size = 4; cfg->sah_refine = 1; cfg->sah_bins = 16; cfg->treelet_size = 512; cfg->morton_bits = 30; cfg->bvh_width = 0;
+    cfg->max_leaf_size = 4; cfg->sah_refine = 1; cfg->sah_bins = 16; cfg->treelet_size = 256; cfg->morton_bits = 30; cfg->bvh_width = 0;
 }
 
 int ptb_scene_load_obj(const char* const* files, int n_files, float scale, uint32_t material_seed, ptb_scene** out) {
@@ -296,6 +297,38 @@ int ptb_save_image(const char* path, const ptb_uchar4* pixels, int w, int h, int
     else if (ends_with_ci(path, ".png")) ok = save_png_rgba8(path, (const uint8_t*)pixels, w, h, flip_y != 0, err);
     else return fail(PTB_ERR_UNSUPPORTED, "ptb_save_image: only .png and .ppm are supported");
     return ok ? PTB_OK : fail(PTB_ERR_IO, err);
+}
+// Raw float4 accumulation buffer for parity tools (last row): 16-byte header
+// {"PTBA", version 1, width, height} (little-endian uint32) followed by width*height float4 texels, row 0 first
+// (the bottom image row, optixSphere.cu:332,400), exactly as the buffer lies in memory.
+int ptb_save_accum_raw(const char* path, const ptb_float4* accum, int w, int h) {
+    if (!path || !accum || w <= 0 || h <= 0) return fail(PTB_ERR_INVALID, "ptb_save_accum_raw: bad arguments");
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(PTB_ERR_IO, std::string("ptb_save_accum_raw: cannot open ") + path);
+    const uint32_t hdr[4] = {0x41425450u /* "PTBA" */, 1u, (uint32_t)w, (uint32_t)h};
+    const size_t n = (size_t)w * (size_t)h;
+    const bool ok = fwrite(hdr, sizeof(hdr), 1, f) == 1 && fwrite(accum, sizeof(ptb_float4), n, f) == n;
+    if (fclose(f) != 0 || !ok) return fail(PTB_ERR_IO, std::string("ptb_save_accum_raw: write failed: ") + path);
+    return PTB_OK;
+}
+int ptb_load_accum_raw(const char* path, float** accum, int* w, int* h) {
+    if (!path || !accum || !w || !h) return fail(PTB_ERR_INVALID, "ptb_load_accum_raw: bad arguments");
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(PTB_ERR_IO, std::string("ptb_load_accum_raw: cannot open ") + path);
+    uint32_t hdr[4] = {0, 0, 0, 0};
+    if (fread(hdr, sizeof(hdr), 1, f) != 1 || hdr[0] != 0x41425450u || hdr[1] != 1u || hdr[2] == 0 || hdr[3] == 0 ||
+        (uint64_t)hdr[2] * hdr[3] > 0x7fffffffull) {
+        fclose(f);
+        return fail(PTB_ERR_IO, std::string("ptb_load_accum_raw: not a PTBA version 1 file: ") + path);
+    }
+    const size_t n = (size_t)hdr[2] * hdr[3];
+    float* px = (float*)malloc(n * 16);
+    if (!px) { fclose(f); return fail(PTB_ERR_INVALID, "out of memory"); }
+    const bool ok = fread(px, 16, n, f) == n;
+    fclose(f);
+    if (!ok) { free(px); return fail(PTB_ERR_IO, std::string("ptb_load_accum_raw: truncated file: ") + path); }
+    *accum = px; *w = (int)hdr[2]; *h = (int)hdr[3];
+    return PTB_OK;
 }
 void ptb_free(void* p) { free(p); }
 

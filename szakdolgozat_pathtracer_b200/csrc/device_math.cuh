@@ -7,7 +7,8 @@
 // (oracle/oracle_math.h, g++ -ffp-contract=off).  No CUDA libm transcendental
 // is used on the radiance path: sin/cos/atan2/asin are the Cephes
 // single-precision algorithms (<= 2 ulp on the ranges used), pow(x,5) is
-// ((x*x)*(x*x))*x.  Only the 8-bit display transform uses powf.
+// ((x*x)*(x*x))*x, the display transform's pow(x, 1/2.2) and pow(x, 1/2.4) are det_powf (double precision, one
+// rounding).
 //
 // Vector helpers follow the OptiX SDK's sutil/vec_math.h semantics the
 // reference relies on (optixSphere.cu:10): v / s multiplies by 1.0f / s,
@@ -122,6 +123,37 @@ PTB_DEV float det_asinf(float xx) {
     return xx < 0.0f ? -r : r;
 }
 PTB_DEV float det_pow5(float x) { float x2 = x * x; float x4 = x2 * x2; return x4 * x; }
+// pow(x, y) of the display transform (cu:425, SDK make_color): exp2(y * log2(x)) in IEEE double, fixed operation order,
+// one rounding to float -- the same code as oracle/oracle_math.h det_powf, so the 8-bit frame is bit-identical too.
+PTB_DEV float det_powf(float xf, float yf) {
+    if (yf == 0.0f || xf == 1.0f) return 1.0f;
+    if (xf != xf || yf != yf) return xf + yf;
+    if (xf < 0.0f) return __int_as_float(0x7fc00000);
+    if (xf == 0.0f) return yf > 0.0f ? 0.0f : __int_as_float(0x7f800000);
+    if (xf > 3.0e38f) return yf > 0.0f ? xf : 0.0f;
+    const double x = (double)xf;
+    const long long b = __double_as_longlong(x);
+    int e = (int)((b >> 52) & 0x7ffll) - 1023;
+    double m = __longlong_as_double((b & 0x000fffffffffffffll) | 0x3ff0000000000000ll);
+    if (m > 1.4142135623730951) { m = m * 0.5; e += 1; }
+    const double s = (m - 1.0) / (m + 1.0), s2 = s * s;
+    double p = 1.0 / 23.0;
+    p = p * s2 + 1.0 / 21.0; p = p * s2 + 1.0 / 19.0; p = p * s2 + 1.0 / 17.0; p = p * s2 + 1.0 / 15.0;
+    p = p * s2 + 1.0 / 13.0; p = p * s2 + 1.0 / 11.0; p = p * s2 + 1.0 / 9.0; p = p * s2 + 1.0 / 7.0;
+    p = p * s2 + 1.0 / 5.0; p = p * s2 + 1.0 / 3.0; p = p * s2 + 1.0;
+    const double log2x = (double)e + (2.0 * s * p) * 1.4426950408889634;
+    const double t = (double)yf * log2x;
+    if (t >= 128.0) return __int_as_float(0x7f800000);
+    if (t < -160.0) return 0.0f;
+    const double n = floor(t + 0.5);
+    const double z = (t - n) * 0.6931471805599453;
+    double q = 1.0 / 87178291200.0;
+    q = q * z + 1.0 / 6227020800.0; q = q * z + 1.0 / 479001600.0; q = q * z + 1.0 / 39916800.0; q = q * z + 1.0 / 3628800.0;
+    q = q * z + 1.0 / 362880.0; q = q * z + 1.0 / 40320.0; q = q * z + 1.0 / 5040.0; q = q * z + 1.0 / 720.0;
+    q = q * z + 1.0 / 120.0; q = q * z + 1.0 / 24.0; q = q * z + 1.0 / 6.0; q = q * z + 0.5; q = q * z + 1.0; q = q * z + 1.0;
+    const double scale = __longlong_as_double(((long long)n + 1023ll) << 52);
+    return (float)(q * scale);
+}
 
 // ---- orthonormal basis (optixSphere.cu:38-61) -----------------------------------
 struct Onb {

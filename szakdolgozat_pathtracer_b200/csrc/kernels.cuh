@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(128) k_trace(SceneView s, FrameView f, PathVie
 
 // ---- textures ---------------------------------------------------------------------------
 // Texel by the reference's linear index y*w + x (cu:518-521, 587-590); a negative
-// index (x0 or y0 == -1, an out-of-bounds read in the reference) wraps by +w*h.
+// index (x0 or y0 == -1, an out-of-bounds read in the reference) wraps by +w*h (applied twice: one-row images).
 // b / 255.0f for an 8-bit b (optixSphere.cpp:370-373), correctly rounded without the IEEE-division sequence: one
 // Newton step on q = b * RN(1/255) with the exact residual.  Bit-identical to the division for all 256 inputs
 // (checked exhaustively on the host by tests/test_abi.py and on the device by test_device_math_bit_exact).
@@ -221,6 +221,7 @@ PTB_DEV float unit_from_u8(unsigned int b) {
 PTB_DEV float4 fetch_texel(const void* data, int fmt, int w, int h, int x, int y) {
     int idx = y * w + x;
     if (idx < 0) idx += w * h;
+    if (idx < 0) idx += w * h;  // one-row images: y = -1, x = -1 gives -w - 1; idx >= -w - 1 always, so twice is enough
     if (fmt == 1) {
         const uchar4 c = __ldg((const uchar4*)data + idx);
         return make_float4(unit_from_u8(c.x), unit_from_u8(c.y), unit_from_u8(c.z), unit_from_u8(c.w));
@@ -520,7 +521,7 @@ PTB_DEV float3 tonemap_curve(float3 x) {
 }
 PTB_DEV float to_srgb1(float c) {
     const float invGamma = 1.0f / 2.4f;
-    const float powed = powf(c, invGamma);
+    const float powed = det_powf(c, invGamma);
     return c < 0.0031308f ? 12.92f * c : 1.055f * powed - 0.055f;
 }
 PTB_DEV unsigned char quantize8(float x) {
@@ -533,7 +534,7 @@ PTB_DEV uchar4 display_color(float3 accum_color, float exposure_scale, float inv
     float3 rgb = accum_color * exposure_scale;
     rgb = tonemap_curve(rgb);
     rgb = clamp3(rgb, 0.0f, 1.0f);
-    rgb = mk3(powf(rgb.x, inv_gamma), powf(rgb.y, inv_gamma), powf(rgb.z, inv_gamma));
+    rgb = mk3(det_powf(rgb.x, inv_gamma), det_powf(rgb.y, inv_gamma), det_powf(rgb.z, inv_gamma));
     rgb = (rgb - 0.5f) * contrast + 0.5f;
     const float3 c = clamp3(rgb, 0.0f, 1.0f);
     return make_uchar4(quantize8(to_srgb1(c.x)), quantize8(to_srgb1(c.y)), quantize8(to_srgb1(c.z)), 255u);
@@ -650,6 +651,7 @@ __global__ void k_test_math(int op, const float* __restrict__ in, int in_stride,
     else if (op == 2) r[0] = det_atan2f(a[0], a[1]);
     else if (op == 3) r[0] = det_asinf(a[0]);
     else if (op == 4) { r[0] = unit_from_u8((unsigned int)a[0]); r[1] = a[0] / 255.0f; }
+    else if (op == 5) r[0] = det_powf(a[0], a[1]);
 }
 
 }  // namespace ptb

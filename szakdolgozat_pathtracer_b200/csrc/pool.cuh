@@ -1,4 +1,5 @@
-// pool.cuh -- the persistent block-local wavefront ("path pool"): pipeline 4, the default.
+// pool.cuh -- the persistent block-local wavefront ("path pool"): pipeline 4 (an option; the default is pipeline 3,
+// chunked.cuh, which is 9 % faster on the 64-spp headline launch).
 //
 // Why (profiles/r1_pool.md): in chunked.cuh a block is married to 2048 fixed slots until the LAST of them has finished
 // its samples.  On C2 a slot needs 10.3 segments on average but the slowest slot of a chunk needs ~50, so a block spends

@@ -45,6 +45,7 @@ struct DeviceScene {
     DeviceBvh bvh;
     unsigned long long handle = 0;
     ptb_context* owner = nullptr;
+    const ptb_scene* source = nullptr;  // the host scene this upload was made from (it owns this object)
 };
 
 void free_device_scene_buffers(DeviceScene* d) {
@@ -224,7 +225,7 @@ int ptb_accel_build(ptb_context* ctx, ptb_scene* scene, const ptb_build_cfg* cfg
 
     if (scene->dev) { free_device_scene(scene->dev); scene->dev = nullptr; }
     DeviceScene* d = new DeviceScene();
-    d->device = ctx->device; d->revision = scene->revision;
+    d->device = ctx->device; d->revision = scene->revision; d->source = scene;
     const uint32_t n = (uint32_t)scene->tris.size();
     d->n_tris = n;
 
@@ -352,6 +353,8 @@ int ptb_launch(ptb_context* ctx, const ptb_Params* P, const ptb_render_cfg* cfg_
     if (cfg.env_importance_sampling < 0 || cfg.env_importance_sampling > 2) return fail(PTB_ERR_INVALID, "ptb_launch: env_importance_sampling must be 0, 1 or 2");
     DeviceScene* d = find_scene(ctx, P->handle);
     if (!d) return fail(PTB_ERR_INVALID, "ptb_launch: Params.handle does not name a built acceleration structure");
+    if (d->source && d->source->revision != d->revision)
+        return fail(PTB_ERR_INVALID, "ptb_launch: the scene was modified (materials, environment or geometry) after ptb_accel_build; build it again");
     cudaStream_t st = (cudaStream_t)stream_;
     CU(cudaSetDevice(ctx->device));
 
@@ -381,8 +384,8 @@ int ptb_launch(ptb_context* ctx, const ptb_Params* P, const ptb_render_cfg* cfg_
     static const int env_pipe = getenv("PTB_PIPELINE") ? atoi(getenv("PTB_PIPELINE")) : -1;  // experiments only
     int pipeline = cfg.pipeline > 0 ? cfg.pipeline : (env_pipe > 0 ? env_pipe : PTB_PIPELINE_DEFAULT);
     if (pipeline < PTB_PIPELINE_QUEUES || pipeline > PTB_PIPELINE_POOL_FUSED) return fail(PTB_ERR_INVALID, "ptb_launch: unknown pipeline");
+    if (cfg.env_importance_sampling) pipeline = PTB_PIPELINE_CHUNK_STAGES;  // the linear modes run as chunked stage kernels
     if (il_n > 1 && pipeline == PTB_PIPELINE_QUEUES) return fail(PTB_ERR_UNSUPPORTED, "ptb_launch: row interleave needs a chunked pipeline (2, 3 or 4)");
-    if (cfg.env_importance_sampling) pipeline = PTB_PIPELINE_CHUNK_STAGES;
 
     // pool pipeline: persistent blocks own PTB_CHUNK positions each; path state is per position, not per slot
     const uint32_t pool_blocks_needed = (slots + PTB_CHUNK - 1u) / PTB_CHUNK;
@@ -535,6 +538,8 @@ int ptb_launch(ptb_context* ctx, const ptb_Params* P, const ptb_render_cfg* cfg_
             while (spt > 1 && (slots + PTB_CHUNK_THREADS * (uint32_t)spt - 1u) / (PTB_CHUNK_THREADS * (uint32_t)spt) < 8u * full) spt >>= 1;
             if (env_spt) spt = env_spt;
             if (cfg.chunk_slots_per_thread) spt = cfg.chunk_slots_per_thread;
+            if (spt != 8 && spt != 4 && spt != 2 && spt != 1) return fail(PTB_ERR_INVALID, "ptb_launch: chunk_slots_per_thread must be 0, 1, 2, 4 or 8");
+            if (cfg.count_traversal) spt = 8;  // the counting variant is instantiated for 2048-slot chunks only: size the grid for it
             const uint32_t chunk = PTB_CHUNK_THREADS * (uint32_t)spt;
             const uint32_t chunks = (slots + chunk - 1u) / chunk;
             k_chunk_raygen<<<pix_blocks, 256, 0, st>>>(f, p, ctx->status);
@@ -547,7 +552,6 @@ int ptb_launch(ptb_context* ctx, const ptb_Params* P, const ptb_render_cfg* cfg_
 #define PTB_CF_LAUNCH(COUNT, MINB, SPT) k_chunk_fused<COUNT, PTB_TRACE_QUANTUM, MINB, SPT><<<chunks, PTB_CHUNK_THREADS, 0, st>>>(s, f, p, ctx->status, ctx->launch_totals, ctx->trav_stats, max_iters)
 #define PTB_CF_BY_SPT(COUNT, MINB) do { if (spt == 8) PTB_CF_LAUNCH(COUNT, MINB, 8); else if (spt == 4) PTB_CF_LAUNCH(COUNT, MINB, 4); \
                                         else if (spt == 2) PTB_CF_LAUNCH(COUNT, MINB, 2); else PTB_CF_LAUNCH(COUNT, MINB, 1); } while (0)
-            if (spt != 8 && spt != 4 && spt != 2 && spt != 1) return fail(PTB_ERR_INVALID, "ptb_launch: chunk_slots_per_thread must be 0, 1, 2, 4 or 8");
             if (cfg.count_traversal) PTB_CF_LAUNCH(true, 5, 8);
             else if (wide) PTB_CF_BY_SPT(false, 8);
             else PTB_CF_BY_SPT(false, 5);
@@ -810,7 +814,7 @@ int ptb_test_env_sample(ptb_context* ctx, unsigned long long handle, const float
 }
 
 int ptb_test_device_math(ptb_context* ctx, int op, const float* in, int in_stride, float* out, int out_stride, uint32_t n) {
-    if (!ctx || !in || !out || in_stride < 1 || out_stride < 1 || op < 0 || op > 4) return fail(PTB_ERR_INVALID, "ptb_test_device_math: bad arguments");
+    if (!ctx || !in || !out || in_stride < 1 || out_stride < 1 || op < 0 || op > 5) return fail(PTB_ERR_INVALID, "ptb_test_device_math: bad arguments");
     CU(cudaSetDevice(ctx->device));
     float *d_in = nullptr, *d_out = nullptr;
     CU(cudaMalloc((void**)&d_in, (size_t)n * in_stride * sizeof(float) + 16));

@@ -74,6 +74,8 @@ def load(which="oracle") -> C.CDLL:
         L.orc_asin.restype = C.c_float
         L.orc_atan2.argtypes = [C.c_float, C.c_float]
         L.orc_asin.argtypes = [C.c_float]
+        L.orc_pow.restype = C.c_float
+        L.orc_pow.argtypes = [C.c_float, C.c_float]
         L.orc_impl_name.restype = C.c_char_p
         L.orc_closest_hit.restype = C.c_int32
         _libs[which] = L

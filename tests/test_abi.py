@@ -7,6 +7,7 @@ import re
 import subprocess
 from pathlib import Path
 
+import numpy as np
 import pytest
 
 ROOT = Path(__file__).resolve().parent.parent
@@ -107,3 +108,21 @@ def test_product_does_not_touch_the_oracle():
                 if isinstance(node, (ast.Import, ast.ImportFrom)):
                     names = [a.name for a in node.names] + [getattr(node, "module", "") or ""]
                     assert not any("oracle" in n or "orchelp" in n for n in names), f
+
+
+def test_accum_raw_round_trip(ptb, tmp_path):
+    """ptb_save_accum_raw / ptb_load_accum_raw: bit-exact round trip incl. NaN payloads and the header."""
+    rng = np.random.default_rng(3)
+    a = rng.standard_normal((7, 13, 4)).astype(np.float32)
+    a.view(np.uint32)[0, 0, 0] = 0x7FC12345
+    f = tmp_path / "accum.ptba"
+    ptb.save_accum_raw(f, a)
+    raw = f.read_bytes()
+    assert raw[:4] == b"PTBA" and np.frombuffer(raw[4:16], np.uint32).tolist() == [1, 13, 7] and len(raw) == 16 + a.nbytes
+    b = ptb.load_accum_raw(f)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    f.write_bytes(raw[:40])
+    with pytest.raises(ptb.PtbError):
+        ptb.load_accum_raw(f)
+    with pytest.raises(ptb.PtbError):
+        ptb.load_accum_raw(tmp_path / "missing.ptba")

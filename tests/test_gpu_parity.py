@@ -2,8 +2,8 @@
 
 Bars (BASELINE.json north_star): primary-hit triangle IDs bit-exact, accumulation
 buffer bit-exact (the kernels and the oracle share one fixed IEEE operation order
-and the same deterministic sin/cos/atan2/asin), 8-bit frame within 1 LSB (the
-display transform uses CUDA powf vs glibc powf).
+and the same deterministic sin/cos/atan2/asin), 8-bit frame bit-exact (the display
+transform's pow is the double-precision det_powf on both sides).
 """
 import ctypes as C
 
@@ -69,10 +69,17 @@ def _render_cpu(oh, ptb, osc, W, H, cfg_kw, subframes=1, dof=True, camera="defau
 def test_device_math_bit_exact(ptb, ctx, oh):
     rng = np.random.default_rng(7)
     L = oh.load("oracle")
-    # RNG incl. the 128 seeds whose hash rounds to 2^32 is covered statistically + by the CPU KAT test
-    seeds = np.concatenate([np.arange(0, 4096, dtype=np.uint32), rng.integers(0, 2**32, 60000, dtype=np.uint32)])
+    # RNG: random seeds, plus ALL 128 seeds whose hash rounds to 2^32 as float (cvt.rzi.u32.f32 saturates: next state
+    # 0xFFFFFFFF, u == 1.0) and their neighbours just below the saturation range
+    from test_oracle_pins import _pcg_preimage, _pcg_word
+    sat = np.array([_pcg_preimage(v) for v in range(2**32 - 128, 2**32)], dtype=np.uint32)
+    near = np.array([_pcg_preimage(v) for v in range(2**32 - 400, 2**32 - 128)], dtype=np.uint32)
+    assert all(_pcg_word(int(x)) == v for x, v in zip(sat, range(2**32 - 128, 2**32)))
+    seeds = np.concatenate([sat, near, np.arange(0, 4096, dtype=np.uint32), rng.integers(0, 2**32, 60000, dtype=np.uint32)])
     out = ctx.test_device_math(0, seeds.view(np.float32).reshape(-1, 1), 2)
-    for i in range(0, len(seeds), 97):
+    assert np.all(out[:128, 0:1].view(np.uint32) == 0xFFFFFFFF) and np.all(out[:128, 1] == 1.0)
+    assert np.all(out[128:400, 1] < 1.0)
+    for i in list(range(0, 400)) + list(range(400, len(seeds), 97)):
         u = C.c_float()
         nxt = L.orc_rng_next(C.c_uint32(int(seeds[i])), 1, C.byref(u))
         assert out[i, 0:1].view(np.uint32)[0] == nxt and out[i, 1] == u.value
@@ -99,6 +106,14 @@ def test_device_math_bit_exact(ptb, ctx, oh):
     u8 = ctx.test_device_math(4, b.reshape(-1, 1), 2)
     assert np.array_equal(u8[:, 0].view(np.uint32), u8[:, 1].view(np.uint32))
     assert np.array_equal(u8[:, 0].view(np.uint32), (b / np.float32(255.0)).view(np.uint32))
+    # display-transform pow: device det_powf == oracle det_powf == correctly rounded x^y
+    px = np.concatenate([rng.random(30000, dtype=np.float32), np.linspace(0, 1, 4001, dtype=np.float32), np.float32([0.0, 1.0, 1e-30, 1e-42, 2.5, 1e30])])
+    for y in (np.float32(1.0) / np.float32(2.2), np.float32(1.0) / np.float32(2.4)):
+        pw = ctx.test_device_math(5, np.stack([px, np.full_like(px, y)], 1), 1)[:, 0]
+        ref = np.array([L.orc_pow(float(v), float(y)) for v in px], np.float32)
+        assert np.array_equal(pw.view(np.uint32), ref.view(np.uint32))
+        inr = px <= 1.0
+        assert np.array_equal(pw[inr].view(np.uint32), np.power(px[inr].astype(np.float64), np.float64(y)).astype(np.float32).view(np.uint32))
 
 
 def _check_bvh(nodes, tris, n_tris, max_leaf):
@@ -216,7 +231,7 @@ def test_c1_image_bit_exact_default_config(ptb, ctx, oh, assets):
     assert sum(s.segments for s in gst) == cseg
     bad = (ga.view(np.uint32) != ca.view(np.uint32)).any(axis=2)
     assert bad.sum() == 0, f"{bad.sum()} of {W * H} accum pixels differ; max abs diff {np.abs(ga - ca).max()}"
-    assert np.abs(gf.astype(np.int32) - cf.astype(np.int32)).max() <= 1
+    assert np.array_equal(gf, cf), "8-bit frame must be bit-exact (det_powf on both sides)"
 
 
 @pytest.mark.parametrize("dof", [False, True])
@@ -246,6 +261,7 @@ def test_c2_monkey_parity_crop(ptb, ctx, oh, assets):
     assert gst[0].segments == cseg
     bad = (ga.view(np.uint32) != ca.view(np.uint32)).any(axis=2)
     assert bad.sum() == 0, f"{bad.sum()} of {W * H} accum pixels differ"
+    assert np.array_equal(gf, cf)
     assert (gh < 15744).mean() > 0.05  # the mesh is in frame
 
 
@@ -353,7 +369,7 @@ def test_demo_scene_parity(ptb, ctx, oh, assets):
     ga, gf, gh, gst = _render_gpu(ptb, ctx, handle, 240, 160, kw)
     ca, cf, ch, cseg = _render_cpu(oh, ptb, osc, 240, 160, kw)
     assert np.array_equal(gh, ch) and gst[0].segments == cseg
-    assert np.array_equal(ga.view(np.uint32), ca.view(np.uint32))
+    assert np.array_equal(ga.view(np.uint32), ca.view(np.uint32)) and np.array_equal(gf, cf)
     assert len(np.unique(gh)) > 100
 
 
@@ -474,7 +490,7 @@ def test_c3_full_pbr_parity_crop(ptb, ctx, oh, assets):
     bad = (ga.view(np.uint32) != ca.view(np.uint32)).any(axis=2)
     assert bad.sum() == 0, f"{bad.sum()} of {W * H} accum pixels differ"
     assert (gh < 2204).mean() > 0.2  # the textured mesh covers a good part of the frame
-    assert np.abs(gf.astype(np.int32) - cf.astype(np.int32)).max() <= 1
+    assert np.array_equal(gf, cf)
 
 
 def test_c2_full_frame_primary_hits(ptb, ctx, oh, assets):

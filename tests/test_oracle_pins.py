@@ -143,6 +143,75 @@ def test_oracle_monkey_matches_live_reference(ptb, oh, assets):
     assert (h1[20:60, 40:120] < 15744).mean() > 0.1
 
 
+CROPS = {"c2": dict(res=(160, 90), camera="monkey_close", window=(40, 20, 120, 60), mesh_tris=15744),
+         "c3": dict(res=(192, 108), camera="suitcase_close", window=(60, 30, 132, 78), mesh_tris=2204)}
+
+
+def _oracle_crop(ptb, oh, assets, name, which="oracle"):
+    from scenes import CAMERAS
+    c = CROPS[name]
+    sc = load_config(ptb, assets, name)
+    osc = oh.OracleScene.from_ptb(sc, guard=True)
+    (W, H), (x0, y0, x1, y1) = c["res"], c["window"]
+    p = ptb.make_params(W, H, subframe_index=0, dof=True, **CAMERAS[c["camera"]])
+    cfg = oh.default_config("oracle", sat_cuda=0) if which == "oracle" else oh.default_config("ref")
+    a, f, h, st, rc = oh.render(which, osc, oh.params_from_ptb(p), cfg, window=c["window"])
+    assert rc == 0
+    return a[y0:y1, x0:x1], f[y0:y1, x0:x1], h[y0:y1, x0:x1], int(st.segments)
+
+
+@pytest.mark.parametrize("name", ["c2", "c3"])
+def test_oracle_matches_reference_crop_fixture(ptb, oh, assets, name):
+    """Textured scenes: the oracle against buffers the reference's own optixSphere.cu produced (host build, generated by
+    tools/make_golden.py).  C3 exercises all four maps: albedo, normal (decode + swizzle + blend, cu:687-701), roughness,
+    metallic (cu:705-714)."""
+    g = np.load(ROOT / "tests" / "golden" / f"ref_{name}_crop.npz")
+    a, f, h, seg = _oracle_crop(ptb, oh, assets, name)
+    assert seg == int(g["segments"]) and np.array_equal(h, g["hits"])
+    assert np.array_equal(a.view(np.uint32), g["accum"].view(np.uint32))
+    assert np.array_equal(f, g["frame"])
+    assert (h < CROPS[name]["mesh_tris"]).mean() > 0.1  # the textured mesh is in the window
+
+
+def test_oracle_c3_matches_live_reference(ptb, oh, assets):
+    """Full-PBR scene against the reference compiled here (live counterpart of the c3 fixture)."""
+    if not oh.have_ref():
+        pytest.skip("oracle/_ref/libref_pt.so not built")
+    a1, f1, h1, s1 = _oracle_crop(ptb, oh, assets, "c3", "oracle")
+    a2, f2, h2, s2 = _oracle_crop(ptb, oh, assets, "c3", "ref")
+    assert s1 == s2 and np.array_equal(h1, h2) and np.array_equal(f1, f2)
+    assert np.array_equal(a1.view(np.uint32), a2.view(np.uint32))
+
+
+def test_det_pow_accuracy(oh):
+    """det_powf (display transform) is the correctly rounded power on the exponents the reference uses."""
+    L = oh.load("oracle")
+    rng = np.random.default_rng(9)
+    xs = np.concatenate([rng.random(20000, dtype=np.float32), np.linspace(0, 1, 2001, dtype=np.float32)])
+    for y in (np.float32(1.0) / np.float32(2.2), np.float32(1.0) / np.float32(2.4)):
+        got = np.array([L.orc_pow(float(x), float(y)) for x in xs], np.float32)
+        want = np.power(xs.astype(np.float64), np.float64(y)).astype(np.float32)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert L.orc_pow(0.0, 0.4) == 0.0 and L.orc_pow(1.0, 0.4) == 1.0 and L.orc_pow(2.0, 10.0) == 1024.0
+
+
+def test_one_row_textures_wrap_inside_the_image(oh):
+    """Texel index rule R3 on 1x1 and one-row images: x0 = y0 = -1 gives a linear index of -w-1, which must wrap into the
+    image (+w*h once leaves -1 for h == 1)."""
+    L = oh.load("oracle")
+    out = (C.c_float * 4)()
+    for w, h in ((1, 1), (2, 1), (5, 1), (1, 3)):
+        img = np.arange(w * h * 4, dtype=np.float32) + 1.0
+        guard = np.concatenate([np.full(64, np.nan, np.float32), img, np.full(64, np.nan, np.float32)])
+        tex = oh.OrcTexture(guard[64:].ctypes.data, w, h, 1, 0)
+        for u, v in ((0.0, 0.0), (0.01, 0.99), (0.99, 0.01), (0.5, 0.5)):
+            L.orc_sample_texture(C.byref(tex), C.c_float(u), C.c_float(v), out)
+            assert all(np.isfinite(list(out))), (w, h, u, v)
+        env = (C.c_float * 3)(0.3, -0.9, 0.1)
+        L.orc_sample_env(guard[64:].ctypes.data_as(C.c_void_p), w, h, env, out)
+        assert all(np.isfinite(list(out)))
+
+
 def test_oracle_bvh_equals_brute_force(ptb, oh, assets):
     from scenes import random_rays
     sc = load_config(ptb, assets, "c2")

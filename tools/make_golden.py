@@ -4,6 +4,9 @@
   * obj_<name>.json        triangle count + sha256 of the face-vertex stream tiny_obj_loader.h produces for each OBJ
   * ref_c1_small.npz       accum / frame / primary-hit buffers rendered by oracle/_ref/libref_pt.so (the reference's
                            optixSphere.cu compiled for the host) on the C1-small scene, reference literals, 2 subframes
+  * ref_c2_crop.npz,       the same for a window of the C2 scene (monkey + albedo map, close camera) and of the C3 scene
+    ref_c3_crop.npz        (suitcase with albedo/normal/roughness/metallic maps, close camera): the textured closest-hit
+                           branches of optixSphere.cu:682-714
 Needs /root/reference (oracle/_ref is built from it); the fixtures then travel to boxes that do not have it.
 """
 import hashlib
@@ -53,4 +56,18 @@ for sf in range(2):
         hits0 = hits.copy()
         seg0 = int(st.segments)
 np.savez_compressed(GOLD / "ref_c1_small.npz", accum=accum, frame=frame, hits=hits0, segments0=np.int64(seg0))
+
+# window crops of the textured scenes (the windows tests/test_oracle_pins.py renders with the oracle)
+from scenes import CAMERAS
+CROPS = {"c2": dict(res=(160, 90), camera="monkey_close", window=(40, 20, 120, 60)),
+         "c3": dict(res=(192, 108), camera="suitcase_close", window=(60, 30, 132, 78))}
+for name, c in CROPS.items():
+    sc = load_config(ptb, make_assets, name)
+    osc = oh.OracleScene.from_ptb(sc, guard=True)
+    (W, H), (x0, y0, x1, y1) = c["res"], c["window"]
+    p = ptb.make_params(W, H, subframe_index=0, dof=True, **CAMERAS[c["camera"]])
+    accum, frame, hits, st, rc = oh.render("ref", osc, oh.params_from_ptb(p), oh.default_config("ref"), window=c["window"])
+    assert rc == 0
+    np.savez_compressed(GOLD / f"ref_{name}_crop.npz", accum=accum[y0:y1, x0:x1], frame=frame[y0:y1, x0:x1], hits=hits[y0:y1, x0:x1],
+                        segments=np.int64(st.segments), window=np.array(c["window"]), res=np.array(c["res"]))
 print("golden fixtures written to", GOLD)
