@@ -48,6 +48,9 @@ extern "C" {
 #define PTB_PIPELINE_POOL_FUSED 4
 #define PTB_PIPELINE_DEFAULT PTB_PIPELINE_CHUNK_FUSED
 
+#define PTB_ARITH_EXACT 0
+#define PTB_ARITH_FAST 1
+
 /* ---- data layouts shared with the reference (optixSphere.h) ---------------
  * Layout-identical to the CUDA vector types the reference uses; the sizes and
  * offsets are pinned by tests against oracle/_ref/ref_probe. */
@@ -154,6 +157,12 @@ typedef struct ptb_render_cfg {
     int32_t* aux_primary_hit; /* optional DEVICE int32[W*H]: primitive hit by the first segment of sample 0, -1 = miss */
     int32_t chunk_slots_per_thread; /* pipeline 3: 0 = chosen from the launch size (default); 1, 2, 4 or 8 = slots per thread of
                                  a 256-thread block, i.e. 256 .. 2048 path slots per chunk.  Results do not depend on it. */
+    int32_t arith_mode;       /* PTB_ARITH_EXACT (0, default): one fixed IEEE operation order, no FMA contraction, software
+                                 sin/cos: accumulation buffer and frame are BIT-IDENTICAL to the CPU oracle.
+                                 PTB_ARITH_FAST (1): the reference's own build mode (--use_fast_math):
+                                 FMA contraction and MUFU reciprocal / square root / sin / cos in the shading code.  Camera
+                                 rays and ray-triangle tests stay exact, so primary-hit IDs are bit-identical; images agree
+                                 within the RMSE bound tests/test_gpu_fast_mode.py states.  Pipelines 2 and 3 only. */
 } ptb_render_cfg;
 
 typedef struct ptb_launch_stats {

@@ -21,6 +21,7 @@ _ROOT = _PKG.parent
 LIB_PATH = Path(os.environ["PTB_LIB"]) if os.environ.get("PTB_LIB") else _PKG / "libptb.so"  # PTB_LIB: A/B builds of the same library (experiments)
 
 PTB_OK, PTB_ERR_INVALID, PTB_ERR_IO, PTB_ERR_CUDA, PTB_ERR_UNSUPPORTED, PTB_ERR_NO_DEVICE = range(6)
+PTB_ARITH_EXACT, PTB_ARITH_FAST = 0, 1  # ptb_render_cfg.arith_mode
 
 
 class PtbError(RuntimeError):
@@ -77,7 +78,7 @@ class RenderCfg(C.Structure):
         ("exposure", C.c_float), ("gamma", C.c_float), ("contrast", C.c_float),
         ("accumulate_mode", C.c_int32), ("write_frame", C.c_int32), ("env_importance_sampling", C.c_int32),
         ("count_traversal", C.c_int32), ("profile_stages", C.c_int32), ("subframes_per_launch", C.c_int32), ("pipeline", C.c_int32), ("row_begin", C.c_int32), ("row_end", C.c_int32), ("row_interleave_count", C.c_int32), ("row_interleave_index", C.c_int32),
-        ("row_interleave_height", C.c_int32), ("aux_primary_hit", C.c_void_p), ("chunk_slots_per_thread", C.c_int32),
+        ("row_interleave_height", C.c_int32), ("aux_primary_hit", C.c_void_p), ("chunk_slots_per_thread", C.c_int32), ("arith_mode", C.c_int32),
     ]
 
 

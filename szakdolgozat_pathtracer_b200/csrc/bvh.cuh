@@ -23,7 +23,7 @@
 #pragma once
 #include "device_math.cuh"
 
-namespace ptb {
+namespace PTB_NS {
 
 #define PTB_BVH_STACK 128
 
@@ -31,6 +31,8 @@ struct HitRec { float t, b1, b2; int prim; };
 
 struct RayShear { int kx, ky, kz; float Sx, Sy, Sz; };
 
+// Everything from here to ray_tri decides which triangle a ray hits, so it is written with the ex_* operations (IEEE
+// round to nearest, immune to FMA contraction and to approximate division): bit-identical in the exact and the fast build.
 // id = (1/d.x, 1/d.y, 1/d.z): Sz = 1 / d[kz] is one of its components (the same IEEE division), so it is not recomputed
 PTB_DEV RayShear ray_shear(float3 d, float3 id) {
     RayShear r;
@@ -43,8 +45,8 @@ PTB_DEV RayShear ray_shear(float3 d, float3 id) {
     if (comp(d, kz) < 0.0f) { int t = kx; kx = ky; ky = t; }
     r.kx = kx; r.ky = ky; r.kz = kz;
     float dz = comp(d, kz);
-    r.Sx = comp(d, kx) / dz;
-    r.Sy = comp(d, ky) / dz;
+    r.Sx = ex_div(comp(d, kx), dz);
+    r.Sy = ex_div(comp(d, ky), dz);
     r.Sz = comp(id, kz);
     return r;
 }
@@ -52,31 +54,33 @@ PTB_DEV RayShear ray_shear(float3 d, float3 id) {
 // true and (t,b1,b2) when tmin < t < tmax
 PTB_DEV bool ray_tri(float3 org, const RayShear& rs, float3 p0, float3 p1, float3 p2, float tmin, float tmax,
                      float* t_out, float* b1_out, float* b2_out) {
-    float3 A = p0 - org, B = p1 - org, C = p2 - org;
+    const float3 A = mk3(ex_sub(p0.x, org.x), ex_sub(p0.y, org.y), ex_sub(p0.z, org.z));
+    const float3 B = mk3(ex_sub(p1.x, org.x), ex_sub(p1.y, org.y), ex_sub(p1.z, org.z));
+    const float3 C = mk3(ex_sub(p2.x, org.x), ex_sub(p2.y, org.y), ex_sub(p2.z, org.z));
     float Akz = comp(A, rs.kz), Bkz = comp(B, rs.kz), Ckz = comp(C, rs.kz);
-    float Ax = comp(A, rs.kx) - rs.Sx * Akz, Ay = comp(A, rs.ky) - rs.Sy * Akz;
-    float Bx = comp(B, rs.kx) - rs.Sx * Bkz, By = comp(B, rs.ky) - rs.Sy * Bkz;
-    float Cx = comp(C, rs.kx) - rs.Sx * Ckz, Cy = comp(C, rs.ky) - rs.Sy * Ckz;
-    float U = Cx * By - Cy * Bx;
-    float V = Ax * Cy - Ay * Cx;
-    float W = Bx * Ay - By * Ax;
+    float Ax = ex_sub(comp(A, rs.kx), ex_mul(rs.Sx, Akz)), Ay = ex_sub(comp(A, rs.ky), ex_mul(rs.Sy, Akz));
+    float Bx = ex_sub(comp(B, rs.kx), ex_mul(rs.Sx, Bkz)), By = ex_sub(comp(B, rs.ky), ex_mul(rs.Sy, Bkz));
+    float Cx = ex_sub(comp(C, rs.kx), ex_mul(rs.Sx, Ckz)), Cy = ex_sub(comp(C, rs.ky), ex_mul(rs.Sy, Ckz));
+    float U = ex_sub(ex_mul(Cx, By), ex_mul(Cy, Bx));
+    float V = ex_sub(ex_mul(Ax, Cy), ex_mul(Ay, Cx));
+    float W = ex_sub(ex_mul(Bx, Ay), ex_mul(By, Ax));
     if (U == 0.0f || V == 0.0f || W == 0.0f) {
-        double CxBy = (double)Cx * (double)By, CyBx = (double)Cy * (double)Bx;
-        U = (float)(CxBy - CyBx);
-        double AxCy = (double)Ax * (double)Cy, AyCx = (double)Ay * (double)Cx;
-        V = (float)(AxCy - AyCx);
-        double BxAy = (double)Bx * (double)Ay, ByAx = (double)By * (double)Ax;
-        W = (float)(BxAy - ByAx);
+        double CxBy = __dmul_rn((double)Cx, (double)By), CyBx = __dmul_rn((double)Cy, (double)Bx);
+        U = (float)__dsub_rn(CxBy, CyBx);
+        double AxCy = __dmul_rn((double)Ax, (double)Cy), AyCx = __dmul_rn((double)Ay, (double)Cx);
+        V = (float)__dsub_rn(AxCy, AyCx);
+        double BxAy = __dmul_rn((double)Bx, (double)Ay), ByAx = __dmul_rn((double)By, (double)Ax);
+        W = (float)__dsub_rn(BxAy, ByAx);
     }
     if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
-    float det = U + V + W;
+    float det = ex_add(ex_add(U, V), W);
     if (det == 0.0f) return false;
-    float Az = rs.Sz * Akz, Bz = rs.Sz * Bkz, Cz = rs.Sz * Ckz;
-    float T = U * Az + V * Bz + W * Cz;
-    float rdet = 1.0f / det;
-    float t = T * rdet;
+    float Az = ex_mul(rs.Sz, Akz), Bz = ex_mul(rs.Sz, Bkz), Cz = ex_mul(rs.Sz, Ckz);
+    float T = ex_add(ex_add(ex_mul(U, Az), ex_mul(V, Bz)), ex_mul(W, Cz));
+    float rdet = ex_div(1.0f, det);
+    float t = ex_mul(T, rdet);
     if (!(t > tmin && t < tmax)) return false;
-    *t_out = t; *b1_out = V * rdet; *b2_out = W * rdet;
+    *t_out = t; *b1_out = ex_mul(V, rdet); *b2_out = ex_mul(W, rdet);
     return true;
 }
 
@@ -95,11 +99,11 @@ PTB_DEV void trav_prefetch4(const float4* __restrict__ nodes4, const float4* __r
 // triangles would pass ray_tri.  tminp = tmin * 0.999.
 PTB_DEV bool slab(float lox, float hix, float loy, float hiy, float loz, float hiz, float3 o, float3 id, float tminp,
                   float tbest, float* tnear) {
-    const float x0 = (lox - o.x) * id.x, x1 = (hix - o.x) * id.x;
-    const float y0 = (loy - o.y) * id.y, y1 = (hiy - o.y) * id.y;
-    const float z0 = (loz - o.z) * id.z, z1 = (hiz - o.z) * id.z;
+    const float x0 = ex_mul(ex_sub(lox, o.x), id.x), x1 = ex_mul(ex_sub(hix, o.x), id.x);
+    const float y0 = ex_mul(ex_sub(loy, o.y), id.y), y1 = ex_mul(ex_sub(hiy, o.y), id.y);
+    const float z0 = ex_mul(ex_sub(loz, o.z), id.z), z1 = ex_mul(ex_sub(hiz, o.z), id.z);
     const float lo = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), tminp));
-    const float hi = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1)) * 1.000001f;
+    const float hi = ex_mul(fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1)), 1.000001f);
     *tnear = lo;
     return lo <= hi && lo <= tbest;
 }
@@ -121,9 +125,9 @@ struct Trav {
 };
 
 PTB_DEV void trav_begin(Trav& t, int* stack, float3 o, float3 d, float tmin, float tmax) {
-    t.o = o; t.id = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    t.o = o; t.id = mk3(ex_div(1.0f, d.x), ex_div(1.0f, d.y), ex_div(1.0f, d.z));
     t.rs = ray_shear(d, t.id);
-    t.tmin = tmin; t.tminp = tmin * 0.999f; t.tmax = tmax;
+    t.tmin = tmin; t.tminp = ex_mul(tmin, 0.999f); t.tmax = tmax;
     t.best.t = tmax; t.best.b1 = 0.0f; t.best.b2 = 0.0f; t.best.prim = -1;
     stack[0] = PTB_TRAV_SENTINEL;
     t.sp = 1;
@@ -250,4 +254,4 @@ PTB_DEV HitRec bvh_closest_hit(const float4* __restrict__ nodes, const float4* _
     return t.best;
 }
 
-}  // namespace ptb
+}  // namespace PTB_NS

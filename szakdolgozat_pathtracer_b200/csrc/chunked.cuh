@@ -24,7 +24,7 @@
 #pragma once
 #include "kernels.cuh"
 
-namespace ptb {
+namespace PTB_NS {
 
 #ifndef PTB_CHUNK_THREADS
 #define PTB_CHUNK_THREADS 256    // 8 slots per thread in the compaction step (measured on C2: 256 > 512 > 128)
@@ -212,8 +212,8 @@ PTB_DEV void chunk_stage_miss(ChunkSharedT<SPT>& sh, const SceneView& s, const F
         const float4 d4 = ldp(&p.ray_d[slot]), as = ldp(&p.atten_seed[slot]);
         const uint4 mi = ldp(&p.misc[slot]);
         const float3 ray_dir = normalize(mk3(d4));
-        const float u = 0.5f + det_atan2f(ray_dir.z, ray_dir.x) / (2.0f * PTB_PI_F);
-        const float v = 0.5f - det_asinf(ray_dir.y) / PTB_PI_F;
+        const float u = 0.5f + AR_DIVC(det_atan2f(ray_dir.z, ray_dir.x), 2.0f * PTB_PI_F);
+        const float v = 0.5f - AR_DIVC(det_asinf(ray_dir.y), PTB_PI_F);
         const float4 hdr = sample_env(s.env, s.env_w, s.env_h, u, v);
         Bounce b;
         b.atten = mk3(as); b.seed = __float_as_uint(as.w);
@@ -245,8 +245,8 @@ PTB_DEV void chunk_stage_shade_miss(ChunkSharedT<SPT>& sh, const SceneView& s, c
             closest_hit(s, f, __float_as_int(h4.w), h4.y, h4.z, h4.x, mk3(o4), mk3(d4), (int)mi.y, b);
         } else {
             const float3 ray_dir = normalize(mk3(d4));
-            const float u = 0.5f + det_atan2f(ray_dir.z, ray_dir.x) / (2.0f * PTB_PI_F);
-            const float v = 0.5f - det_asinf(ray_dir.y) / PTB_PI_F;
+            const float u = 0.5f + AR_DIVC(det_atan2f(ray_dir.z, ray_dir.x), 2.0f * PTB_PI_F);
+            const float v = 0.5f - AR_DIVC(det_asinf(ray_dir.y), PTB_PI_F);
             const float4 hdr = sample_env(s.env, s.env_w, s.env_h, u, v);
             b.radiance = mk3(0.0f) + b.atten * mk3(hdr);
             b.origin = mk3(0.0f); b.direction = mk3(0.0f);
@@ -348,4 +348,39 @@ __global__ void __launch_bounds__(PTB_CHUNK_THREADS, (MINB * 128 + PTB_CHUNK_THR
     if (threadIdx.x == 0) atomicMax(max_iters_seen, iter);
 }
 
-}  // namespace ptb
+// ---- host-side launchers shared by both builds of the kernels (renderer.cu calls ptb::..., fast_kernels.cu wraps
+// ptb_fast::...) ---------------------------------------------------------------------------------------------------
+struct ChunkLaunch {
+    SceneView s; FrameView f; PathView p;
+    unsigned char* status; unsigned long long* totals; unsigned long long* trav_stats; unsigned int* max_iters;
+    uint32_t chunks;   // blocks of the fused kernel = ceil(slots / (PTB_CHUNK_THREADS * spt))
+    int spt;           // slots per thread: 8, 4, 2 or 1
+    int wide;          // 1: enough chunks to fill the chip -> the 64-register / 4-blocks-per-SM build
+    int count;         // 1: count nodes visited / triangles tested (2048-slot chunks only)
+};
+
+inline void launch_chunk_raygen(const ChunkLaunch& a, cudaStream_t st) {
+    k_chunk_raygen<<<(a.p.n_slots + 255u) / 256u, 256, 0, st>>>(a.f, a.p, a.status);
+}
+
+inline void launch_chunk_fused(const ChunkLaunch& a, cudaStream_t st) {
+#define PTB_CF_LAUNCH(COUNT, MINB, SPT) k_chunk_fused<COUNT, PTB_TRACE_QUANTUM, MINB, SPT><<<a.chunks, PTB_CHUNK_THREADS, 0, st>>>(a.s, a.f, a.p, a.status, a.totals, a.trav_stats, a.max_iters)
+#define PTB_CF_BY_SPT(COUNT, MINB) do { if (a.spt == 8) PTB_CF_LAUNCH(COUNT, MINB, 8); else if (a.spt == 4) PTB_CF_LAUNCH(COUNT, MINB, 4); \
+                                        else if (a.spt == 2) PTB_CF_LAUNCH(COUNT, MINB, 2); else PTB_CF_LAUNCH(COUNT, MINB, 1); } while (0)
+    if (a.count) PTB_CF_LAUNCH(true, 5, 8);
+    else if (a.wide) PTB_CF_BY_SPT(false, 8);
+    else PTB_CF_BY_SPT(false, 5);
+#undef PTB_CF_BY_SPT
+#undef PTB_CF_LAUNCH
+}
+
+// one wavefront iteration of the stage-kernel pipeline (pipeline 2): 0 = trace, 1 = shade, 2 = miss
+inline void launch_chunk_stage(const ChunkLaunch& a, int stage, int iter, cudaStream_t st) {
+    if (stage == 0) {
+        if (a.count) k_chunk_trace<true, PTB_TRACE_QUANTUM><<<a.chunks, PTB_CHUNK_THREADS, 0, st>>>(a.s, a.f, a.p, a.status, a.totals, a.trav_stats, iter);
+        else k_chunk_trace<false, PTB_TRACE_QUANTUM><<<a.chunks, PTB_CHUNK_THREADS, 0, st>>>(a.s, a.f, a.p, a.status, a.totals, a.trav_stats, iter);
+    } else if (stage == 1) k_chunk_shade<<<a.chunks, PTB_CHUNK_THREADS, 0, st>>>(a.s, a.f, a.p, a.status);
+    else k_chunk_miss<<<a.chunks, PTB_CHUNK_THREADS, 0, st>>>(a.s, a.f, a.p, a.status);
+}
+
+}  // namespace PTB_NS

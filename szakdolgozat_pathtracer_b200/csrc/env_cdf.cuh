@@ -12,7 +12,7 @@
 #pragma once
 #include "device_math.cuh"
 
-namespace ptb {
+namespace PTB_NS {
 
 struct EnvCdf {
     const float* marginal;     // [h + 1]
@@ -131,4 +131,4 @@ PTB_DEV float3 env_sample(const EnvCdf& e, float xi1, float xi2, float* pdf) {
     return env_uv_to_dir(u, v);
 }
 
-}  // namespace ptb
+}  // namespace PTB_NS

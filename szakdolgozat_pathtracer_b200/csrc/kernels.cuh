@@ -16,58 +16,13 @@
 // Queues are appended with one warp-aggregated atomic per warp (queue_push).
 #pragma once
 #include "bvh.cuh"
+#include "views.cuh"
 
-namespace ptb {
+namespace PTB_NS {
 
-struct DevTexture { const void* data; int w, h; int fmt; };  // fmt: 0 none, 1 RGBA8, 2 float4
-struct DevMaterial {
-    DevTexture tex[4];  // albedo, roughness, normal, metallic
-    float emission[3], diffuse[3], specular[3];
-    float roughness;
-    int metallic;
-    int _pad;
-};
-
-struct SceneView {
-    const float4* nodes; const float4* nodes4; const float4* tris;  // nodes4: 4-wide copy of the tree or nullptr
-    const float4* verts; const float4* normals; const float2* uvs; const uint32_t* mat_ids;
-    const DevMaterial* mats;
-    const float4* env; int env_w, env_h;
-};
-
-// Exact unsigned division by a launch constant d for x < 2^31: q = (x * m) >> sh with m = ceil(2^sh / d),
-// sh = 31 + ceil(log2 d) (the error m*d - 2^sh is < d <= 2^(sh-31), so it cannot carry into the quotient for x < 2^31).
-// One 64-bit multiply instead of the ~20-instruction software division; every sample start needs three of them.
-struct FastDiv { unsigned long long m; uint32_t sh, d; };
+using namespace ptbv;  // DevTexture, DevMaterial, SceneView, FastDiv, FrameView, PathView (views.cuh)
 PTB_DEV uint32_t fd_div(uint32_t x, const FastDiv& fd) { return (uint32_t)(((unsigned long long)x * fd.m) >> fd.sh); }
 PTB_DEV uint32_t fd_mod(uint32_t x, const FastDiv& fd) { return x - fd_div(x, fd) * fd.d; }
-
-struct FrameView {
-    uint32_t W, H;
-    FastDiv div_w, div_pixels;  // by W and by n_pixels
-    uint32_t row0;       // first image row rendered by this launch (row band; 0 for the whole frame)
-    uint32_t il_n, il_r, il_h;  // il_n > 1: interleaved strips of il_h rows, this launch renders strips il_r, il_r + il_n, ...
-    uint32_t n_pixels;   // W * rows of the band
-    int n_subframes;     // subframes rendered by this launch as ONE wavefront (slot = sub * n_pixels + pixel)
-    int subframe, dof;   // subframe = index of the first one
-    float3 eye, U, V, Wv;
-    int spp, max_depth;
-    float tmin, tmax, dof_blur, focus_dist, nmap_strength;
-    float exposure_scale, inv_gamma, contrast;
-    int accumulate_mode, write_frame;
-    float4* accum; uchar4* frame; int* aux_primary;
-};
-
-// Path pool, structure of arrays, one entry per pixel slot, 16-byte records.
-struct PathView {
-    float4* ray_o;       // origin.xyz, -
-    float4* ray_d;       // direction.xyz, -
-    float4* hit;         // t, b1, b2, prim (int bits)
-    float4* atten_seed;  // attenuation.xyz, payload.seed (uint bits)
-    uint4* misc;         // raygen seed, depth (int), sample index, -
-    float4* pixsum;      // sum of finished samples .xyz
-    uint32_t n_slots;
-};
 
 // Path state is streamed: every record is read once per stage and rewritten by the next one, by whichever thread
 // handles the slot.  ld.global.cs / st.global.cs (evict-first in L1 and L2) keep the caches for what IS reused across
@@ -95,6 +50,12 @@ struct QueueView {
 };
 
 #define PTB_PI_F 3.14159265358979323846f
+// division by a compile-time constant: IEEE division in the exact build, multiplication by the reciprocal in the fast one
+#if PTB_FAST
+#define AR_DIVC(x, c) ((x) * (1.0f / (c)))
+#else
+#define AR_DIVC(x, c) ((x) / (c))
+#endif
 
 // image row of the launch-local row lr (identity / row band / interleaved strips); may be >= H for the padded last strip
 PTB_DEV uint32_t image_row(const FrameView& f, uint32_t lr) {
@@ -103,29 +64,52 @@ PTB_DEV uint32_t image_row(const FrameView& f, uint32_t lr) {
 }
 
 // ---- camera ray of one sample (cu:326-347) ------------------------------------------
+// Camera rays decide the primary-hit IDs, so they are written with ex_* operations and are bit-identical in the exact and
+// the fast build (PTB_FAST_EXACT_CAMERA = 0 lets the fast build use MUFU sin/cos/sqrt in the depth-of-field branch).
+#ifndef PTB_FAST_EXACT_CAMERA
+#define PTB_FAST_EXACT_CAMERA 1
+#endif
+PTB_DEV float3 ex_camera_dir(float dx, float dy, float3 U, float3 V, float3 Wv) {  // (dx * U + dy * V) + W
+    return mk3(ex_add(ex_add(ex_mul(dx, U.x), ex_mul(dy, V.x)), Wv.x), ex_add(ex_add(ex_mul(dx, U.y), ex_mul(dy, V.y)), Wv.y),
+               ex_add(ex_add(ex_mul(dx, U.z), ex_mul(dy, V.z)), Wv.z));
+}
 PTB_DEV void start_sample(const FrameView& f, uint32_t ix, uint32_t iy, uint32_t& seed, float3& origin, float3& direction) {
     const float jx = myrnd(seed);
     const float jy = myrnd(seed);
-    const float dx = 2.0f * (((float)ix + jx) / (float)f.W) - 1.0f;
-    const float dy = 2.0f * (((float)iy + jy) / (float)f.H) - 1.0f;
+    const float dx = ex_sub(ex_mul(2.0f, ex_div(ex_add((float)ix, jx), (float)f.W)), 1.0f);
+    const float dy = ex_sub(ex_mul(2.0f, ex_div(ex_add((float)iy, jy), (float)f.H)), 1.0f);
     if (f.dof) {
         // defocus_disk_sample (cu:279-294): the seed is passed by value, the stream does not advance
         uint32_t s2 = seed;
-        const float r = sqrtf(myrnd(s2));
-        const float theta = (float)(2.0f * 3.14159265358979323846 * (double)myrnd(s2));
+        const float u1 = myrnd(s2);
+        const float theta = (float)__dmul_rn(2.0f * 3.14159265358979323846, (double)myrnd(s2));
+#if PTB_FAST && !PTB_FAST_EXACT_CAMERA
+        const float r = ar_sqrt(u1);
         float sn, cs; det_sincosf(theta, &sn, &cs);
-        const float x = f.dof_blur * sqrtf(r) * cs;
-        const float y = f.dof_blur * sqrtf(r) * sn;
+        const float x = f.dof_blur * ar_sqrt(r) * cs;
+        const float y = f.dof_blur * ar_sqrt(r) * sn;
         origin = x * f.U + y * f.V;
         const float3 target = f.focus_dist * (dx * f.U + dy * f.V + f.Wv);
         direction = normalize(target - origin);
         origin = origin + f.eye;
+#else
+        const float r = ex_sqrt(u1);
+        float sn, cs; det_sincosf_ex(theta, &sn, &cs);
+        const float rr = ex_mul(f.dof_blur, ex_sqrt(r));
+        const float x = ex_mul(rr, cs), y = ex_mul(rr, sn);
+        origin = mk3(ex_add(ex_mul(x, f.U.x), ex_mul(y, f.V.x)), ex_add(ex_mul(x, f.U.y), ex_mul(y, f.V.y)), ex_add(ex_mul(x, f.U.z), ex_mul(y, f.V.z)));
+        const float3 cd = ex_camera_dir(dx, dy, f.U, f.V, f.Wv);
+        const float3 target = mk3(ex_mul(f.focus_dist, cd.x), ex_mul(f.focus_dist, cd.y), ex_mul(f.focus_dist, cd.z));
+        direction = ex_normalize(mk3(ex_sub(target.x, origin.x), ex_sub(target.y, origin.y), ex_sub(target.z, origin.z)));
+        origin = mk3(ex_add(origin.x, f.eye.x), ex_add(origin.y, f.eye.y), ex_add(origin.z, f.eye.z));
+#endif
     } else {
         origin = f.eye;
-        direction = normalize(dx * f.U + dy * f.V + f.Wv);
+        direction = ex_normalize(ex_camera_dir(dx, dy, f.U, f.V, f.Wv));
     }
 }
 
+#if !PTB_FAST  // global-queue pipeline: exact build only
 __global__ void __launch_bounds__(256) k_raygen_init(FrameView f, PathView p, QueueView q) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) q.counters[0] = p.n_slots;
@@ -207,6 +191,7 @@ __global__ void __launch_bounds__(128) k_trace(SceneView s, FrameView f, PathVie
     }
 }
 
+#endif  // !PTB_FAST
 // ---- textures ---------------------------------------------------------------------------
 // Texel by the reference's linear index y*w + x (cu:518-521, 587-590); a negative
 // index (x0 or y0 == -1, an out-of-bounds read in the reference) wraps by +w*h (applied twice: one-row images).
@@ -216,7 +201,11 @@ __global__ void __launch_bounds__(128) k_trace(SceneView s, FrameView f, PathVie
 PTB_DEV float unit_from_u8(unsigned int b) {
     const float fb = (float)b, rc = 1.0f / 255.0f;
     const float q = fb * rc;
+#if PTB_FAST
+    return q;  // within 1 ulp of b / 255.0f
+#else
     return fmaf(fmaf(-q, 255.0f, fb), rc, q);
+#endif
 }
 PTB_DEV float4 fetch_texel(const void* data, int fmt, int w, int h, int x, int y) {
     int idx = y * w + x;
@@ -261,11 +250,11 @@ PTB_DEV float3 material_property(const DevTexture& tx, float3 fallback, float u,
 
 // ---- BSDF helpers (cu:244-263, 439-500) ---------------------------------------------------
 PTB_DEV float3 cosine_sample_hemisphere(float u1, float u2) {
-    const float r = sqrtf(u1);
+    const float r = ar_sqrt(u1);
     const float phi = 2.0f * PTB_PI_F * u2;
     float s, c; det_sincosf(phi, &s, &c);
     float3 p; p.x = r * c; p.z = r * s;
-    p.y = sqrtf(fmaxf(0.0f, 1.0f - p.x * p.x - p.z * p.z));
+    p.y = ar_sqrt(fmaxf(0.0f, 1.0f - p.x * p.x - p.z * p.z));
     return p;
 }
 PTB_DEV void burn_random_in_unit_sphere(uint32_t& seed) {
@@ -281,28 +270,28 @@ PTB_DEV float D_GGX(float3 n, float3 h, float a) {
     const float NdotH2 = NdotH * NdotH;
     float denom = (NdotH2 * (a2 - 1.0f) + 1.0f);
     denom = PTB_PI_F * denom * denom;
-    return a2 / denom;
+    return ar_div(a2, denom);
 }
 PTB_DEV float G_SchlickGGX(float alpha, float3 n, float3 x) {
     const float numerator = fabsf(dot(n, x));
     const float k = alpha / 2.0f;
     float denominator = fabsf(dot(n, x)) * (1.0f - k) + k;
     denominator = fmaxf(denominator, 1e-10f);
-    return numerator / denominator;
+    return ar_div(numerator, denominator);
 }
 PTB_DEV float3 Fresnel_Schlick(float cosTheta, float3 F0) {
     cosTheta = clampf(cosTheta, 0.0f, 1.0f);
     return F0 + (mk3(1.0f) - F0) * det_pow5(1.0f - cosTheta);
 }
 PTB_DEV float Fresnel_Schlick_float(float cosine, float refraction_index) {
-    float r0 = (1.0f - refraction_index) / (1.0f + refraction_index);
+    float r0 = ar_div(1.0f - refraction_index, 1.0f + refraction_index);
     r0 = r0 * r0;
     return r0 + (1.0f - r0) * det_pow5(1.0f - cosine);
 }
 PTB_DEV float3 GGX_importance_sample(float r1, float r2, float alpha) {
     const float phi = 2.0f * PTB_PI_F * r1;
-    const float cosTheta = sqrtf((1.0f - r2) / (1.0f + (alpha * alpha - 1.0f) * r2));
-    const float sinTheta = sqrtf(1.0f - cosTheta * cosTheta);
+    const float cosTheta = ar_sqrt(ar_div(1.0f - r2, 1.0f + (alpha * alpha - 1.0f) * r2));
+    const float sinTheta = ar_sqrt(1.0f - cosTheta * cosTheta);
     float s, c; det_sincosf(phi, &s, &c);
     return normalize(mk3(sinTheta * c, cosTheta, sinTheta * s));
 }
@@ -420,11 +409,16 @@ PTB_DEV void closest_hit(const SceneView& s, const FrameView& f, int prim_idx, f
     const float F_blend_factor = Fresnel_Schlick_float(NdotV, ior);
 
     const float specular_probability = metallicity + (1.0f - metallicity) * F_blend_factor;
-    const float spdf = D * NdotH / (4.0f * VdotH);
+    const float spdf = ar_div(D * NdotH, 4.0f * VdotH);
     const float dpdf = 1.0f / PTB_PI_F;
     if (myrnd(seed) < specular_probability) io.direction = light_dir_n;
     else io.direction = normalize(onb.inverse_transform(cosine_sample_hemisphere(r1, r2)));
+#if PTB_FAST
+    const float3 brdf = specular_probability * (brdf_specular / spdf) + (1.0f - specular_probability) * (diffuse_albedo * PTB_PI_F);
+    (void)dpdf;
+#else
     const float3 brdf = specular_probability * (brdf_specular / spdf) + (1.0f - specular_probability) * (diffuse_albedo / dpdf);
+#endif
 
     if (length(brdf) >= 1e-10f) io.atten = io.atten * (brdf * IdotN);
     io.origin = hit_pos;
@@ -463,6 +457,7 @@ PTB_DEV bool after_segment(const FrameView& f, const PathView& p, uint32_t slot,
     return true;
 }
 
+#if !PTB_FAST  // the global-queue pipeline, the display transform and the self tests exist in the exact build only
 __global__ void __launch_bounds__(128) k_shade(SceneView s, FrameView f, PathView p, QueueView q, int iter) {
     const uint32_t n = q.counters[iter * 4 + 1];
     const uint32_t stride = gridDim.x * blockDim.x;
@@ -499,8 +494,8 @@ __global__ void __launch_bounds__(128) k_miss(SceneView s, FrameView f, PathView
             const float4 d4 = ldp(&p.ray_d[slot]), as = ldp(&p.atten_seed[slot]);
             const uint4 mi = ldp(&p.misc[slot]);
             const float3 ray_dir = normalize(mk3(d4));
-            const float u = 0.5f + det_atan2f(ray_dir.z, ray_dir.x) / (2.0f * PTB_PI_F);
-            const float v = 0.5f - det_asinf(ray_dir.y) / PTB_PI_F;
+            const float u = 0.5f + AR_DIVC(det_atan2f(ray_dir.z, ray_dir.x), 2.0f * PTB_PI_F);
+            const float v = 0.5f - AR_DIVC(det_asinf(ray_dir.y), PTB_PI_F);
             const float4 hdr = sample_env(s.env, s.env_w, s.env_h, u, v);
             Bounce b;
             b.atten = mk3(as); b.seed = __float_as_uint(as.w);
@@ -654,4 +649,5 @@ __global__ void k_test_math(int op, const float* __restrict__ in, int in_stride,
     else if (op == 5) r[0] = det_powf(a[0], a[1]);
 }
 
-}  // namespace ptb
+#endif  // !PTB_FAST
+}  // namespace PTB_NS

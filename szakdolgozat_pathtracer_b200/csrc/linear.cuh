@@ -20,7 +20,7 @@
 #include "chunked.cuh"
 #include "env_cdf.cuh"
 
-namespace ptb {
+namespace PTB_NS {
 
 struct LinearView {
     EnvCdf cdf;
@@ -242,4 +242,4 @@ __global__ void k_env_sample_test(EnvCdf cdf, const float* __restrict__ xi, uint
     out[4 * (size_t)i] = d.x; out[4 * (size_t)i + 1] = d.y; out[4 * (size_t)i + 2] = d.z; out[4 * (size_t)i + 3] = pdf;
 }
 
-}  // namespace ptb
+}  // namespace PTB_NS

@@ -24,7 +24,7 @@
 #pragma once
 #include "chunked.cuh"
 
-namespace ptb {
+namespace PTB_NS {
 
 enum PoolStatus : unsigned char { ST_FREE = 5, ST_IDLE = 6 };  // FREE: wants a new slot; IDLE: the launch has no more slots
 
@@ -254,4 +254,4 @@ __global__ void __launch_bounds__(PTB_CHUNK_THREADS, (MINB * 128) / PTB_CHUNK_TH
     if (threadIdx.x == 0) atomicMax(max_iters_seen, iter);
 }
 
-}  // namespace ptb
+}  // namespace PTB_NS

@@ -27,6 +27,7 @@
 #include <vector>
 
 #include "bvh_build.h"
+#include "fast_api.h"
 #include "host.h"
 #include "linear.cuh"
 #include "pool.cuh"
@@ -385,6 +386,10 @@ int ptb_launch(ptb_context* ctx, const ptb_Params* P, const ptb_render_cfg* cfg_
     int pipeline = cfg.pipeline > 0 ? cfg.pipeline : (env_pipe > 0 ? env_pipe : PTB_PIPELINE_DEFAULT);
     if (pipeline < PTB_PIPELINE_QUEUES || pipeline > PTB_PIPELINE_POOL_FUSED) return fail(PTB_ERR_INVALID, "ptb_launch: unknown pipeline");
     if (cfg.env_importance_sampling) pipeline = PTB_PIPELINE_CHUNK_STAGES;  // the linear modes run as chunked stage kernels
+    if (cfg.arith_mode != PTB_ARITH_EXACT && cfg.arith_mode != PTB_ARITH_FAST) return fail(PTB_ERR_INVALID, "ptb_launch: arith_mode must be 0 (exact) or 1 (fast)");
+    const bool fast = cfg.arith_mode == PTB_ARITH_FAST;
+    if (fast && (cfg.env_importance_sampling || (pipeline != PTB_PIPELINE_CHUNK_FUSED && pipeline != PTB_PIPELINE_CHUNK_STAGES)))
+        return fail(PTB_ERR_UNSUPPORTED, "ptb_launch: arith_mode = 1 (fast) exists for the chunked pipelines (2, 3) of the reference estimator only");
     if (il_n > 1 && pipeline == PTB_PIPELINE_QUEUES) return fail(PTB_ERR_UNSUPPORTED, "ptb_launch: row interleave needs a chunked pipeline (2, 3 or 4)");
 
     // pool pipeline: persistent blocks own PTB_CHUNK positions each; path state is per position, not per slot
@@ -510,23 +515,14 @@ int ptb_launch(ptb_context* ctx, const ptb_Params* P, const ptb_render_cfg* cfg_
         }
         p.pixsum = ctx->out_pixsum;  // what k_resolve folds
     } else {
-        // block-local wavefront over chunks of the path pool (chunked.cuh)
-        if (pipeline == PTB_PIPELINE_CHUNK_STAGES) {
-            const uint32_t chunks = (slots + PTB_CHUNK - 1u) / PTB_CHUNK;
-            k_chunk_raygen<<<pix_blocks, 256, 0, st>>>(f, p, ctx->status);
-            if (prof) CU(cudaEventRecord(ctx->events[1], st));
-            launches = 1;
-            for (uint32_t it = 0; it < iters; ++it) {
-                if (cfg.count_traversal) k_chunk_trace<true, PTB_TRACE_QUANTUM><<<chunks, PTB_CHUNK_THREADS, 0, st>>>(s, f, p, ctx->status, ctx->launch_totals, ctx->trav_stats, (int)it);
-                else k_chunk_trace<false, PTB_TRACE_QUANTUM><<<chunks, PTB_CHUNK_THREADS, 0, st>>>(s, f, p, ctx->status, ctx->launch_totals, ctx->trav_stats, (int)it);
-                if (prof) CU(cudaEventRecord(ctx->events[2 + (size_t)it * 3 + 0], st));
-                k_chunk_shade<<<chunks, PTB_CHUNK_THREADS, 0, st>>>(s, f, p, ctx->status);
-                if (prof) CU(cudaEventRecord(ctx->events[2 + (size_t)it * 3 + 1], st));
-                k_chunk_miss<<<chunks, PTB_CHUNK_THREADS, 0, st>>>(s, f, p, ctx->status);
-                if (prof) CU(cudaEventRecord(ctx->events[2 + (size_t)it * 3 + 2], st));
-                launches += 3;
-            }
-        } else {
+        // block-local wavefront over chunks of the path pool (chunked.cuh), in the exact build of the kernels (namespace
+        // ptb) or in the fast-arithmetic one (fast_kernels.cu, cfg.arith_mode = 1)
+        ChunkLaunch cl;
+        cl.s = s; cl.f = f; cl.p = p; cl.status = ctx->status; cl.totals = ctx->launch_totals; cl.trav_stats = ctx->trav_stats;
+        cl.max_iters = (unsigned int*)(ctx->launch_totals + 3);
+        cl.count = cfg.count_traversal ? 1 : 0; cl.spt = PTB_CHUNK_SPT; cl.wide = 1;
+        cl.chunks = (slots + PTB_CHUNK - 1u) / PTB_CHUNK;
+        if (pipeline == PTB_PIPELINE_CHUNK_FUSED) {
             // Chunk size by launch size: 8 slots per thread (2048-slot chunks) when that still gives 8 waves of blocks,
             // otherwise fewer slots per thread so that a small frame (the reference's 600 x 400 / 1600 x 1200 launches of
             // one subframe) spreads over the whole chip instead of running its per-pixel sample chains on a few warps per
@@ -541,22 +537,29 @@ int ptb_launch(ptb_context* ctx, const ptb_Params* P, const ptb_render_cfg* cfg_
             if (spt != 8 && spt != 4 && spt != 2 && spt != 1) return fail(PTB_ERR_INVALID, "ptb_launch: chunk_slots_per_thread must be 0, 1, 2, 4 or 8");
             if (cfg.count_traversal) spt = 8;  // the counting variant is instantiated for 2048-slot chunks only: size the grid for it
             const uint32_t chunk = PTB_CHUNK_THREADS * (uint32_t)spt;
-            const uint32_t chunks = (slots + chunk - 1u) / chunk;
-            k_chunk_raygen<<<pix_blocks, 256, 0, st>>>(f, p, ctx->status);
-            if (prof) CU(cudaEventRecord(ctx->events[1], st));
-            launches = 1;
-            unsigned int* max_iters = (unsigned int*)(ctx->launch_totals + 3);
+            cl.spt = spt; cl.chunks = (slots + chunk - 1u) / chunk;
             // 64 registers / 4 blocks per SM once there are enough chunks to keep that many blocks busy, the
-            // unconstrained ~100-register build for launches that cannot fill the chip anyway
-            const bool wide = chunks >= full;
-#define PTB_CF_LAUNCH(COUNT, MINB, SPT) k_chunk_fused<COUNT, PTB_TRACE_QUANTUM, MINB, SPT><<<chunks, PTB_CHUNK_THREADS, 0, st>>>(s, f, p, ctx->status, ctx->launch_totals, ctx->trav_stats, max_iters)
-#define PTB_CF_BY_SPT(COUNT, MINB) do { if (spt == 8) PTB_CF_LAUNCH(COUNT, MINB, 8); else if (spt == 4) PTB_CF_LAUNCH(COUNT, MINB, 4); \
-                                        else if (spt == 2) PTB_CF_LAUNCH(COUNT, MINB, 2); else PTB_CF_LAUNCH(COUNT, MINB, 1); } while (0)
-            if (cfg.count_traversal) PTB_CF_LAUNCH(true, 5, 8);
-            else if (wide) PTB_CF_BY_SPT(false, 8);
-            else PTB_CF_BY_SPT(false, 5);
-#undef PTB_CF_BY_SPT
-#undef PTB_CF_LAUNCH
+            // unconstrained ~80-register build for launches that cannot fill the chip anyway
+            cl.wide = cl.chunks >= full ? 1 : 0;
+        }
+        ptb_fast_api::ChunkLaunchArgs fa;
+        if (fast) {
+            fa.s = s; fa.f = f; fa.p = p; fa.status = cl.status; fa.totals = cl.totals; fa.trav_stats = cl.trav_stats; fa.max_iters = cl.max_iters;
+            fa.chunks = cl.chunks; fa.spt = cl.spt; fa.wide = cl.wide; fa.count = cl.count;
+            ptb_fast_api::raygen(fa, st);
+        } else launch_chunk_raygen(cl, st);
+        if (prof) CU(cudaEventRecord(ctx->events[1], st));
+        launches = 1;
+        if (pipeline == PTB_PIPELINE_CHUNK_STAGES) {
+            for (uint32_t it = 0; it < iters; ++it) {
+                for (int stage = 0; stage < 3; ++stage) {
+                    if (fast) ptb_fast_api::stage(fa, stage, (int)it, st); else launch_chunk_stage(cl, stage, (int)it, st);
+                    if (prof) CU(cudaEventRecord(ctx->events[2 + (size_t)it * 3 + stage], st));
+                }
+                launches += 3;
+            }
+        } else {
+            if (fast) ptb_fast_api::fused(fa, st); else launch_chunk_fused(cl, st);
             launches += 1;
             prof_iters = 0;
             if (prof) {  // a single kernel: everything between raygen and resolve is reported as "trace"

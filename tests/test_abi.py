@@ -60,6 +60,28 @@ def test_header_structs_compile_to_reference_layout(tmp_path):
             assert int(v) == GOLD[k], (cc, k, v, GOLD[k])
 
 
+def test_ctypes_mirrors_match_header(ptb, tmp_path):
+    """Every configuration / statistics struct of include/ptb.h against its ctypes mirror: size and every field offset
+    (a field appended to the header but not to the binding would otherwise be read as garbage)."""
+    pairs = {"ptb_render_cfg": ptb.RenderCfg, "ptb_build_cfg": ptb.BuildCfg, "ptb_build_stats": ptb.BuildStats,
+             "ptb_launch_stats": ptb.LaunchStats, "ptb_material_info": ptb.MaterialInfo}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "ptb.h"', "int main(void){"]
+    for cname, cls in pairs.items():
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for f, _ in cls._fields_:
+            lines.append(f'printf("{cname}.{f} %zu\\n", offsetof({cname}, {f}));')
+    lines.append("return 0;}")
+    src = tmp_path / "cfg_probe.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "cfg_probe"
+    subprocess.run(["/usr/bin/gcc", "-std=c11", "-I", str(ROOT / "include"), "-o", str(exe), str(src)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, cls in pairs.items():
+        assert int(out[cname]) == C.sizeof(cls), cname
+        for f, _ in cls._fields_:
+            assert int(out[f"{cname}.{f}"]) == getattr(cls, f).offset, (cname, f)
+
+
 def test_golden_layout_matches_live_reference_probe(oh):
     if not oh.REF_PROBE.exists():
         pytest.skip("oracle/_ref/ref_probe not built (no /root/reference on this box)")

@@ -58,7 +58,7 @@ def test_c4_auto_wide_bvh_random_materials_parity(ptb, ctx, oh, assets):
     osc = oh.OracleScene.from_ptb(sc, guard=False)
     mids = sc.material_ids()
     # window 1: the emissive statue, the tower in front of it, the fish and the floor; window 2: a diffuse statue
-    h1 = _check_window(oh, osc, p, kw, (936, 560, 1064, 608), ga, gf, gh)
+    h1 = _check_window(oh, osc, p, kw, (936, 660, 1064, 708), ga, gf, gh)
     seen = set(np.unique(mids[h1[h1 >= 0]]).tolist())
     assert 4 in seen and len(seen) >= 3, seen
     h2 = _check_window(oh, osc, p, kw, (620, 650, 684, 690), ga, gf, gh)

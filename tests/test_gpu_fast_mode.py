@@ -1,0 +1,121 @@
+"""Gate of the fast-arithmetic build (ptb_render_cfg.arith_mode = PTB_ARITH_FAST, fast_kernels.cu).
+
+The fast build contracts multiply-add pairs into FMAs and uses the MUFU approximations for reciprocal, square root, sine and
+cosine in the SHADING code -- the reference's own build mode (--use_fast_math).  What decides a hit ID
+(camera rays, traversal set-up, the watertight ray-triangle test) is written with un-contractable IEEE intrinsics and is
+bit-identical to the exact build.  north_star's bar for floating point: primary-hit IDs bit-exact, converged images within
+a stated error bound.  Stated here and asserted below:
+
+  1. primary-hit IDs: bit-identical to the exact build / the oracle, depth of field on AND off (0 mismatches);
+  2. segment counts within 0.1 % of the exact build's (paths diverge only where a Russian-roulette or lobe decision sits
+     within rounding of its threshold);
+  3. converged images (1024 spp) against the CPU oracle: relative RMSE <= REL_RMSE_BOUND and |mean difference| <=
+     REL_BIAS_BOUND of the mean radiance, on the C1, C2 and C3 scenes -- far below the Monte-Carlo noise of the
+     estimator itself at that sample count (measured alongside with an independent set of samples).
+"""
+import numpy as np
+import pytest
+
+from scenes import CAMERAS, load_config
+
+pytestmark = pytest.mark.gpu
+
+REL_RMSE_BOUND = 5e-3   # sqrt(mean((fast - oracle)^2)) / mean(oracle), 1024 spp, accumulation buffer RGB
+REL_BIAS_BOUND = 5e-4   # |mean(fast) - mean(oracle)| / mean(oracle)
+
+
+def _render(ptb, ctx, handle, W, H, camera, dof, arith, spp, subframes, depth, first_subframe=0, want_hits=False, pipeline=3):
+    n = W * H
+    d_accum, d_frame, d_hits = ctx.alloc(n * 16), ctx.alloc(n * 4), ctx.alloc(n * 4)
+    try:
+        ctx.memset(d_accum, 0, n * 16)
+        ctx.memset(d_hits, 0xFF, n * 4)
+        p = ptb.make_params(W, H, subframe_index=first_subframe, dof=dof, **CAMERAS[camera])
+        p.accum_buffer, p.frame_buffer, p.handle = d_accum, d_frame, handle
+        cfg = ptb.default_render_cfg(spp_per_launch=spp, max_depth=depth, subframes_per_launch=subframes, arith_mode=arith,
+                                     pipeline=pipeline, aux_primary_hit=d_hits if want_hits else None)
+        ctx.launch(p, cfg)
+        st = ctx.launch_stats()
+        return (ctx.to_host(d_accum, (H, W, 4), np.float32), ctx.to_host(d_frame, (H, W, 4), np.uint8),
+                ctx.to_host(d_hits, (H, W), np.int32), st)
+    finally:
+        for b in (d_accum, d_frame, d_hits):
+            ctx.free(b)
+
+
+@pytest.mark.parametrize("dof", [False, True], ids=["dof-off", "dof-on"])
+def test_fast_mode_primary_hits_bit_exact_full_frame(ptb, ctx, oh, assets, dof):
+    """BASELINE config 2 at its full size: all 2 073 600 primary-hit IDs of the fast build equal the exact build's (which
+    tests/test_gpu_parity.py pins to the oracle); a crop is compared with the oracle directly."""
+    sc = load_config(ptb, assets, "c2")
+    handle, _ = ctx.accel_build(sc)
+    W, H = 1920, 1080
+    ea, ef, eh, est = _render(ptb, ctx, handle, W, H, "default", dof, ptb.PTB_ARITH_EXACT, 1, 1, 2, want_hits=True)
+    fa, ff, fh, fst = _render(ptb, ctx, handle, W, H, "default", dof, ptb.PTB_ARITH_FAST, 1, 1, 2, want_hits=True)
+    assert int((eh != fh).sum()) == 0
+    assert abs(int(fst.segments) - int(est.segments)) <= 1e-3 * est.segments
+    osc = oh.OracleScene.from_ptb(sc, guard=False)
+    win = (900, 380, 1020, 440)
+    p = ptb.make_params(W, H, subframe_index=0, dof=dof)
+    _, _, ch, _, rc = oh.render("oracle", osc, oh.params_from_ptb(p), oh.default_config("oracle", spp_per_launch=1, max_depth=2), window=win)
+    assert rc == 0 and np.array_equal(fh[380:440, 900:1020], ch[380:440, 900:1020])
+    assert (fh[380:440, 900:1020] < 15744).mean() > 0.2  # the mesh is in the window
+    # the images agree closely already at one sample per pixel: same random streams, same primary hits
+    rel = np.abs(fa[..., :3] - ea[..., :3]).mean() / ea[..., :3].mean()
+    assert rel < 5e-3, rel
+
+
+@pytest.mark.parametrize("name,camera,W,H", [("c1", "default", 96, 96), ("c2", "monkey_close", 128, 72), ("c3", "suitcase_close", 128, 72)])
+def test_fast_mode_converged_image_error_bound(ptb, ctx, oh, assets, name, camera, W, H):
+    sc = load_config(ptb, assets, name, small=(name == "c1"))
+    handle, _ = ctx.accel_build(sc)
+    spp, subframes, depth = 8, 128, 8   # 1024 samples per pixel
+    fa, _, _, fst = _render(ptb, ctx, handle, W, H, camera, True, ptb.PTB_ARITH_FAST, spp, subframes, depth)
+    ea, _, _, est = _render(ptb, ctx, handle, W, H, camera, True, ptb.PTB_ARITH_EXACT, spp, subframes, depth)
+    na, _, _, _ = _render(ptb, ctx, handle, W, H, camera, True, ptb.PTB_ARITH_EXACT, spp, subframes, depth, first_subframe=subframes)
+    # the oracle's 1024-spp image (running average over 128 launches, optixSphere.cu:403-409)
+    osc = oh.OracleScene.from_ptb(sc, guard=False)
+    ca = np.zeros((H, W, 4), np.float32)
+    for sf in range(subframes):
+        p = ptb.make_params(W, H, subframe_index=sf, dof=True, **CAMERAS[camera])
+        ca, _, _, _, rc = oh.render("oracle", osc, oh.params_from_ptb(p), oh.default_config("oracle", spp_per_launch=spp, max_depth=depth), accum=ca, want_hits=False)
+        assert rc == 0
+    assert np.array_equal(ea.view(np.uint32), ca.view(np.uint32)), "the exact build must equal the oracle bit for bit"
+    ref = ca[..., :3].astype(np.float64)
+    mean = ref.mean()
+    rmse = np.sqrt(((fa[..., :3] - ref) ** 2).mean()) / mean
+    bias = abs(fa[..., :3].astype(np.float64).mean() - mean) / mean
+    noise = np.sqrt(((na[..., :3] - ref) ** 2).mean()) / mean   # two independent 1024-spp images of the exact estimator
+    frac_px = float((np.abs(fa[..., :3] - ref).max(axis=2) > 1e-4 * (ref.max(axis=2) + 1e-6)).mean())
+    print(f"\n[fast-mode gate] {name}/{camera} {W}x{H} 1024 spp: rel RMSE {rmse:.3e}, rel bias {bias:.3e}, MC noise between independent "
+          f"1024-spp images {noise:.3e}, pixels differing by > 1e-4 relative {frac_px:.3f}, segments fast/exact {fst.segments}/{est.segments}")
+    assert rmse <= REL_RMSE_BOUND, rmse
+    assert bias <= REL_BIAS_BOUND, bias
+    assert rmse < 0.25 * noise, (rmse, noise)
+    assert abs(int(fst.segments) - int(est.segments)) <= 1e-3 * est.segments
+
+
+def test_fast_mode_stage_kernels_equal_fused(ptb, ctx, assets):
+    """The fast build of pipeline 2 (one kernel per stage) and of pipeline 3 (fused) run the same arithmetic: bit-identical."""
+    sc = load_config(ptb, assets, "c2")
+    handle, _ = ctx.accel_build(sc)
+    a3, f3, h3, s3 = _render(ptb, ctx, handle, 160, 90, "monkey_close", True, ptb.PTB_ARITH_FAST, 4, 2, 6, want_hits=True, pipeline=3)
+    a2, f2, h2, s2 = _render(ptb, ctx, handle, 160, 90, "monkey_close", True, ptb.PTB_ARITH_FAST, 4, 2, 6, want_hits=True, pipeline=2)
+    assert s2.segments == s3.segments and np.array_equal(h2, h3) and np.array_equal(f2, f3)
+    assert np.array_equal(a2.view(np.uint32), a3.view(np.uint32))
+
+
+def test_fast_mode_refused_where_it_does_not_exist(ptb, ctx, assets):
+    sc = load_config(ptb, assets, "c1", small=True)
+    handle, _ = ctx.accel_build(sc)
+    d = ctx.alloc(32 * 32 * 16)
+    try:
+        p = ptb.make_params(32, 32)
+        p.accum_buffer, p.handle = d, handle
+        for bad in (dict(pipeline=1), dict(pipeline=4), dict(env_importance_sampling=1), dict(arith_mode=2)):
+            kw = dict(write_frame=0, spp_per_launch=1, max_depth=1, arith_mode=ptb.PTB_ARITH_FAST)
+            kw.update(bad)
+            with pytest.raises(ptb.PtbError):
+                ctx.launch(p, ptb.default_render_cfg(**kw))
+    finally:
+        ctx.free(d)

@@ -30,6 +30,7 @@ ap.add_argument("--refine", type=int, default=1)
 ap.add_argument("--morton", type=int, default=30)
 ap.add_argument("--treelet", type=int, default=256)
 ap.add_argument("--bvh-width", type=int, default=0)
+ap.add_argument("--arith", type=int, default=0, help="0 exact, 1 fast")
 a = ap.parse_args()
 
 ctx = ptb.Context(0)
@@ -43,7 +44,7 @@ n = W * H
 d_accum, d_frame = ctx.alloc(n * 16), ctx.alloc(n * 4)
 ctx.memset(d_accum, 0, n * 16)
 cfg = ptb.default_render_cfg(spp_per_launch=a.spp, max_depth=a.depth, count_traversal=a.count, subframes_per_launch=a.batch,
-                             profile_stages=a.stages, pipeline=a.pipeline)
+                             profile_stages=a.stages, pipeline=a.pipeline, arith_mode=a.arith)
 for rep in range(2):
     seg = 0
     ctx.synchronize()
@@ -56,7 +57,7 @@ for rep in range(2):
     dt = time.time() - t0
 st = ctx.launch_stats()
 seg = st.segments * a.launches
-print(f"{a.config}/{a.camera} {W}x{H} spp {a.spp} depth {a.depth}: {dt / a.launches * 1e3:.2f} ms/launch, "
+print(f"{a.config}/{a.camera} arith {a.arith} {W}x{H} spp {a.spp} depth {a.depth}: {dt / a.launches * 1e3:.2f} ms/launch, "
       f"~{seg / dt / 1e6:.1f} Msegments/s (last-launch segments {st.segments}, iterations {st.iterations}, "
       f"hits {st.hits}, misses {st.misses}), {a.spp * a.launches * a.batch / dt * (n / (1920 * 1080)):.1f} 1080p-spp/s")
 if a.stages:
