@@ -140,9 +140,9 @@ typedef struct ptb_render_cfg {
     int32_t count_traversal;  /* 1: also count BVH nodes visited / triangles tested (slower) */
     int32_t profile_stages;   /* 1: bracket every stage kernel with CUDA events (ptb_launch_get_stage_ms) */
     int32_t subframes_per_launch; /* default 1.  n > 1: this one call renders subframes subframe_index .. +n-1 as ONE
-                                 wavefront of n*W*H path slots (results are bit-identical to n consecutive calls;
-                                 the path pool grows to n*W*H*96 bytes).  Keeps the GPU full through the tail of the
-                                 per-pixel sample chains. */
+                                 wavefront of n*W*H path slots (results are bit-identical to n consecutive calls).
+                                 Keeps the GPU full through the tail of the per-pixel sample chains.  The pool is
+                                 bounded by max_pool_bytes: larger launches run as batches of subframes. */
     int32_t pipeline;         /* 0 = default.  1: global ray queues, one kernel per stage and iteration;
                                  2: block-local wavefront over chunks of the path pool, one kernel per stage and
                                     iteration; 3: the same stages fused into one kernel per launch (default);
@@ -163,6 +163,9 @@ typedef struct ptb_render_cfg {
                                  FMA contraction and MUFU reciprocal / square root / sin / cos in the shading code.  Camera
                                  rays and ray-triangle tests stay exact, so primary-hit IDs are bit-identical; images agree
                                  within the RMSE bound tests/test_gpu_fast_mode.py states.  Pipelines 2 and 3 only. */
+    int64_t max_pool_bytes;   /* bound of the path-state pool (97 B per resident path slot); 0 = 2 GiB.  A launch of
+                                 subframes_per_launch * W * H slots that would exceed it is rendered as consecutive batches
+                                 of subframes inside ptb_launch(): same result bit for bit, bounded memory. */
 } ptb_render_cfg;
 
 typedef struct ptb_launch_stats {
@@ -288,6 +291,12 @@ int ptb_resolve(ptb_context* ctx, const ptb_float4* accum, ptb_float4* accum_out
  * rank's rendering (a stream-ordered barrier) and must barrier again before the root reads the frame. */
 int ptb_resolve_peers(ptb_context* ctx, const ptb_float4* const* accums, int n_ranks, ptb_float4* accum_out, ptb_uchar4* frame,
                       uint32_t first_pixel, uint32_t n_pixels, float scale, const ptb_render_cfg* cfg, void* stream);
+/* The same with the frame's earlier history: prev_accum (may be null, may alias accum_out) holds the mean of prev_weight
+ * earlier subframes and enters the sum first as prev_accum * prev_weight; scale is then 1 / (prev_weight + new subframes).
+ * This is how ptb_multi_launch() continues the reference's running average (optixSphere.cu:403-409) across launches. */
+int ptb_resolve_peers_accumulate(ptb_context* ctx, const ptb_float4* const* accums, int n_ranks, const ptb_float4* prev_accum,
+                                 float prev_weight, ptb_float4* accum_out, ptb_uchar4* frame, uint32_t first_pixel,
+                                 uint32_t n_pixels, float scale, const ptb_render_cfg* cfg, void* stream);
 /* CUDA IPC plumbing for the above (one process per GPU): export a cudaMalloc'ed buffer, open a peer's, close it */
 int ptb_ipc_export(ptb_context* ctx, const void* device_ptr, unsigned char handle[64]);
 int ptb_ipc_open(ptb_context* ctx, const unsigned char handle[64], void** device_ptr);
@@ -295,6 +304,34 @@ int ptb_ipc_close(ptb_context* ctx, void* device_ptr);
 /* batch closest-hit query on the built BVH (device arrays of float3 / outputs) */
 int ptb_trace_rays(ptb_context* ctx, unsigned long long handle, const float* d_origins, const float* d_dirs, uint32_t n,
                    float tmin, float tmax, int32_t* d_prim, float* d_t, float* d_b1, float* d_b2, void* stream);
+
+/* ---- multi-GPU context: the n-device counterpart of optixDeviceContextCreate + the render loop's optixLaunch
+ *      (optixSphere.cpp:798-812, 1390-1437; SURVEY.md section 8b "multi-GPU is internal", 8e).  ONE host process drives all
+ *      devices; the scene is replicated (ptb_multi_accel_build uploads it and builds a BVH on every device); one
+ *      ptb_multi_launch() renders the cfg->subframes_per_launch subframes that start at params->subframe_index:
+ *        PTB_SPLIT_SAMPLES  contiguous blocks of subframes per device (global subframe indices seed the RNG,
+ *                           optixSphere.cu:316) into per-device sum accumulators, then one fused reduce-scatter ->
+ *                           accumulate -> tonemap -> gather kernel per device over peer memory (NVLink).  The frame's mean
+ *                           is continued as (old mean * subframe_index + sum of the new launch means) / (subframe_index + K):
+ *                           equal to the reference's running average up to rounding (sum order), not bitwise.
+ *        PTB_SPLIT_TILES    16-row strips dealt round-robin; every device writes its strips straight into the root's
+ *                           buffers through peer pointers: bit-identical to a single-GPU launch.
+ *      params->accum_buffer / frame_buffer live on the ROOT device (index 0: allocate them through ptb_multi_context(m, 0));
+ *      params->handle is ignored.  The call is asynchronous; ptb_multi_synchronize() waits for every device.  The same
+ *      device may be listed more than once (several contexts on one GPU: how the single-GPU tests exercise this path). */
+typedef struct ptb_multi ptb_multi;
+#define PTB_SPLIT_SAMPLES 0
+#define PTB_SPLIT_TILES 1
+int ptb_multi_create(const int* devices, int n_devices, ptb_multi** out);
+void ptb_multi_destroy(ptb_multi* m);
+int ptb_multi_device_count(const ptb_multi* m);
+ptb_context* ptb_multi_context(ptb_multi* m, int index);
+void* ptb_multi_stream(ptb_multi* m, int index);   /* cudaStream_t the launches of device `index` are issued on */
+int ptb_multi_accel_build(ptb_multi* m, ptb_scene* scene, const ptb_build_cfg* cfg, ptb_build_stats* stats);
+int ptb_multi_launch(ptb_multi* m, const ptb_Params* params, const ptb_render_cfg* cfg, int split);
+int ptb_multi_synchronize(ptb_multi* m);
+/* segments, hits, misses, launches summed over the devices (ptb_context_get_totals of every context) */
+int ptb_multi_get_totals(ptb_multi* m, uint64_t out[4], int reset);
 
 /* ---- output buffer: sutil::CUDAOutputBuffer<uchar4> (optixSphere.cpp:1284,
  *      1376-1382, 1401, 1419, 1484-1486, 256) ----------------------------------- */

@@ -78,7 +78,7 @@ class RenderCfg(C.Structure):
         ("exposure", C.c_float), ("gamma", C.c_float), ("contrast", C.c_float),
         ("accumulate_mode", C.c_int32), ("write_frame", C.c_int32), ("env_importance_sampling", C.c_int32),
         ("count_traversal", C.c_int32), ("profile_stages", C.c_int32), ("subframes_per_launch", C.c_int32), ("pipeline", C.c_int32), ("row_begin", C.c_int32), ("row_end", C.c_int32), ("row_interleave_count", C.c_int32), ("row_interleave_index", C.c_int32),
-        ("row_interleave_height", C.c_int32), ("aux_primary_hit", C.c_void_p), ("chunk_slots_per_thread", C.c_int32), ("arith_mode", C.c_int32),
+        ("row_interleave_height", C.c_int32), ("aux_primary_hit", C.c_void_p), ("chunk_slots_per_thread", C.c_int32), ("arith_mode", C.c_int32), ("max_pool_bytes", C.c_int64),
     ]
 
 
@@ -120,7 +120,7 @@ EXPORTS = [
     "ptb_scene_copy_triangles", "ptb_scene_copy_material_ids", "ptb_scene_get_material", "ptb_scene_copy_texture",
     "ptb_scene_env_size", "ptb_scene_copy_env", "ptb_default_build_cfg", "ptb_accel_build", "ptb_accel_read",
     "ptb_camera_uvw", "ptb_params_default_camera", "ptb_default_render_cfg", "ptb_launch", "ptb_launch_get_stats", "ptb_launch_get_stage_ms", "ptb_context_get_totals",
-    "ptb_resolve", "ptb_resolve_peers", "ptb_ipc_export", "ptb_ipc_open", "ptb_ipc_close", "ptb_trace_rays", "ptb_output_create", "ptb_output_resize", "ptb_output_map", "ptb_output_unmap",
+    "ptb_resolve", "ptb_resolve_peers", "ptb_resolve_peers_accumulate", "ptb_multi_create", "ptb_multi_destroy", "ptb_multi_device_count", "ptb_multi_context", "ptb_multi_stream", "ptb_multi_accel_build", "ptb_multi_launch", "ptb_multi_synchronize", "ptb_multi_get_totals", "ptb_ipc_export", "ptb_ipc_open", "ptb_ipc_close", "ptb_trace_rays", "ptb_output_create", "ptb_output_resize", "ptb_output_map", "ptb_output_unmap",
     "ptb_output_host_ptr", "ptb_output_width", "ptb_output_height", "ptb_output_destroy", "ptb_device_alloc",
     "ptb_device_free", "ptb_device_memset", "ptb_copy_to_device", "ptb_copy_to_host", "ptb_image_load_rgba8",
     "ptb_image_load_float4", "ptb_save_image", "ptb_save_accum_raw", "ptb_load_accum_raw", "ptb_free", "ptb_obj_read", "ptb_microbench_read", "ptb_test_env_sample", "ptb_test_device_math",
@@ -157,6 +157,8 @@ def lib() -> C.CDLL:
                      "ptb_camera_uvw", "ptb_params_default_camera", "ptb_default_render_cfg", "ptb_default_build_cfg"):
             getattr(L, name).restype = None
         L.ptb_context_destroy.argtypes = [C.c_void_p]
+        L.ptb_multi_destroy.restype = None
+        L.ptb_multi_destroy.argtypes = [C.c_void_p]
         L.ptb_scene_destroy.argtypes = [C.c_void_p]
         L.ptb_output_destroy.argtypes = [C.c_void_p]
         L.ptb_free.argtypes = [C.c_void_p]
@@ -517,6 +519,67 @@ def obj_read(path) -> np.ndarray:
     out = np.frombuffer(buf, np.uint32).reshape(-1, 10).copy()
     lib().ptb_free(rec)
     return out
+
+
+PTB_SPLIT_SAMPLES, PTB_SPLIT_TILES = 0, 1
+
+
+class _BorrowedContext(Context):
+    """A context owned by a Multi (never destroyed from Python)."""
+
+    def __init__(self, handle, device):
+        self._h, self.device = handle, device
+
+    def close(self):
+        self._h = None
+
+    def __del__(self):
+        pass
+
+
+class Multi:
+    """ptb_multi: one host process drives n devices (include/ptb.h; csrc/multi.cpp).  contexts[0] is the root: the
+    accumulator / frame buffers of Params live there."""
+
+    def __init__(self, devices):
+        devs = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        _check(lib().ptb_multi_create(devs, len(devices), C.byref(h)))
+        self._h = h
+        L = lib()
+        L.ptb_multi_context.restype = C.c_void_p
+        L.ptb_multi_context.argtypes = [C.c_void_p, C.c_int]
+        self.contexts = [_BorrowedContext(C.c_void_p(L.ptb_multi_context(h, i)), d) for i, d in enumerate(devices)]
+        self.root = self.contexts[0]
+
+    def accel_build(self, scene: Scene, cfg: BuildCfg | None = None) -> BuildStats:
+        st = BuildStats()
+        _check(lib().ptb_multi_accel_build(self._h, scene._h, C.byref(cfg) if cfg is not None else None, C.byref(st)))
+        return st
+
+    def launch(self, params: Params, cfg: RenderCfg | None = None, split=PTB_SPLIT_SAMPLES):
+        _check(lib().ptb_multi_launch(self._h, C.byref(params), C.byref(cfg) if cfg is not None else None, int(split)))
+
+    def synchronize(self):
+        _check(lib().ptb_multi_synchronize(self._h))
+
+    def totals(self, reset=False) -> dict:
+        out = (C.c_uint64 * 4)()
+        _check(lib().ptb_multi_get_totals(self._h, out, int(bool(reset))))
+        return dict(zip(("segments", "hits", "misses", "launches"), [int(x) for x in out]))
+
+    def close(self):
+        if self._h:
+            for c in self.contexts:
+                c.close()
+            lib().ptb_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def save_image(path, rgba: np.ndarray, flip_y=True):

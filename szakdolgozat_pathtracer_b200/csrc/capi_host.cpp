@@ -190,7 +190,7 @@ int ptb_scene_set_env_pixels(ptb_scene* scene, const float* rgba, int w, int h) 
 
 void ptb_scene_destroy(ptb_scene* scene) {
     if (!scene) return;
-    if (scene->dev) free_device_scene(scene->dev);
+    for (DeviceScene* d : scene->devs) free_device_scene(d);
     delete scene;
 }
 

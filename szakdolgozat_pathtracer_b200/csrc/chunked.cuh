@@ -33,6 +33,15 @@ namespace PTB_NS {
 #define PTB_CHUNK_SPT 8          // default slots per thread (1, 2, 4, 8 or 16)
 #endif
 #define PTB_CHUNK (PTB_CHUNK_THREADS * PTB_CHUNK_SPT)  // slots per block at the default SPT
+#ifndef PTB_SHADE_DYNAMIC
+#define PTB_SHADE_DYNAMIC 0      // 1: the shade + miss stage hands out its list in warp-sized batches (see chunk_stage_shade_miss)
+#endif
+#ifndef PTB_STATUS_SMEM
+#define PTB_STATUS_SMEM 0        // 1: the fused kernel keeps its chunk's status bytes in shared memory
+#endif
+#ifndef PTB_MINB_WIDE
+#define PTB_MINB_WIDE 8          // fused kernel, launches that fill the chip: resident 128-thread units per SM the register
+#endif                           // budget is sized for (8 -> 64 registers, 10 -> 51, 12 -> 42)
 // The chunk helpers are templates on SPT = slots per thread (chunk = PTB_CHUNK_THREADS * SPT slots): the fused kernel uses
 // smaller chunks for small launches (a 600 x 400 frame has 117 chunks of 2048 slots -- less than one block per SM -- but
 // 938 chunks of 256), everything else uses the default through the aliases below.
@@ -62,7 +71,11 @@ PTB_DEV void chunk_status_words(const unsigned char* __restrict__ status, uint32
         for (int w = 0; w < (SPT + 7) / 8; ++w) {
             const uint32_t f0 = first + 8u * w;
             unsigned long long bytes = 0ull;
+#if PTB_STATUS_SMEM
+            if (f0 + 8u <= n_slots) bytes = *reinterpret_cast<const unsigned long long*>(status + f0);  // generic: shared or global
+#else
             if (f0 + 8u <= n_slots) bytes = __ldcs(reinterpret_cast<const unsigned long long*>(status + f0));
+#endif
             else if (f0 < n_slots) for (uint32_t k = 0; f0 + k < n_slots; ++k) bytes |= (unsigned long long)status[f0 + k] << (8u * k);
             words[w] = bytes;
         }
@@ -146,7 +159,7 @@ PTB_DEV void chunk_build_two(ChunkSharedT<SPT>& sh, const unsigned char* __restr
 template <bool COUNT, int QUANTUM, int SPT>
 PTB_DEV void chunk_stage_trace(ChunkSharedT<SPT>& sh, const SceneView& s, const FrameView& f, const PathView& p,
                                unsigned char* __restrict__ status, uint32_t base, unsigned int n, bool first_iteration,
-                               TravCounters& tc) {
+                               TravCounters& tc, uint32_t sbase = 0) {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
     int stack[PTB_BVH_STACK];
@@ -180,7 +193,7 @@ PTB_DEV void chunk_stage_trace(ChunkSharedT<SPT>& sh, const SceneView& s, const 
             have = false;
             stp(&p.hit[slot], make_float4(t.best.t, t.best.b1, t.best.b2, __int_as_float(t.best.prim)));
             const bool is_hit = t.best.prim >= 0;
-            status[slot] = is_hit ? ST_HIT : ST_MISS;
+            status[slot - sbase] = is_hit ? ST_HIT : ST_MISS;
             hits += is_hit ? 1u : 0u;
             if (first_iteration && f.aux_primary && slot < f.n_pixels) f.aux_primary[(size_t)image_row(f, slot / f.W) * f.W + slot % f.W] = t.best.prim;
         }
@@ -231,9 +244,22 @@ PTB_DEV void chunk_stage_miss(ChunkSharedT<SPT>& sh, const SceneView& s, const F
 // executes both bodies.
 template <int SPT>
 PTB_DEV void chunk_stage_shade_miss(ChunkSharedT<SPT>& sh, const SceneView& s, const FrameView& f, const PathView& p,
-                                    unsigned char* __restrict__ status, uint32_t base, unsigned int n_hit, unsigned int n_miss) {
+                                    unsigned char* __restrict__ status, uint32_t base, unsigned int n_hit, unsigned int n_miss,
+                                    uint32_t sbase = 0) {
     const unsigned int total = n_hit + n_miss;
+#if PTB_SHADE_DYNAMIC
+    // warps take 32 consecutive items at a time from the list cursor (reset by chunk_build_two): a warp that drew cheap items
+    // (misses, Russian-roulette kills) goes on to the next batch instead of waiting at the stage barrier
+    for (;;) {
+        unsigned int b0 = 0;
+        if ((threadIdx.x & 31u) == 0u) b0 = atomicAdd(&sh.next, 32u);
+        b0 = __shfl_sync(0xffffffffu, b0, 0);
+        if (b0 >= total) break;
+        const unsigned int i = b0 + (threadIdx.x & 31u);
+        if (i >= total) continue;
+#else
     for (unsigned int i = threadIdx.x; i < total; i += PTB_CHUNK_THREADS) {
+#endif
         const bool is_hit = i < n_hit;
         const uint32_t slot = base + sh.list[is_hit ? i : ChunkSharedT<SPT>::CHUNK - total + i];
         const float4 d4 = ldp(&p.ray_d[slot]), as = ldp(&p.atten_seed[slot]);
@@ -252,7 +278,7 @@ PTB_DEV void chunk_stage_shade_miss(ChunkSharedT<SPT>& sh, const SceneView& s, c
             b.origin = mk3(0.0f); b.direction = mk3(0.0f);
             b.done = 1;
         }
-        status[slot] = after_segment(f, p, slot, b, mi.x, (int)mi.y, mi.z) ? ST_TRACE : ST_DONE;
+        status[slot - sbase] = after_segment(f, p, slot, b, mi.x, (int)mi.y, mi.z) ? ST_TRACE : ST_DONE;
     }
 }
 
@@ -331,16 +357,28 @@ __global__ void __launch_bounds__(PTB_CHUNK_THREADS, (MINB * 128 + PTB_CHUNK_THR
     if (threadIdx.x < 4) sh.count[threadIdx.x] = 0;
     TravCounters tc; tc.nodes = 0; tc.tris = 0;
     unsigned int iter = 0;
+#if PTB_STATUS_SMEM
+    // the chunk's status bytes live in shared memory for the whole life of the block (read once from what raygen wrote):
+    // the list pass at the top of every phase and the status stores of the stages never leave the SM
+    __shared__ __align__(8) unsigned char st_sh[ChunkSharedT<SPT>::CHUNK];
+    for (unsigned int k = threadIdx.x; k < ChunkSharedT<SPT>::CHUNK; k += PTB_CHUNK_THREADS) st_sh[k] = base + k < p.n_slots ? status[base + k] : (unsigned char)ST_DONE;
+    __syncthreads();
+    unsigned char* const stp_ = st_sh;
+    const uint32_t sbase = base, sn = ChunkSharedT<SPT>::CHUNK;   // padding reads as ST_DONE, so the list pass needs no bound
+#else
+    unsigned char* const stp_ = status;
+    const uint32_t sbase = 0, sn = p.n_slots;
+#endif
     for (unsigned int phase = 0;; phase ^= 1u) {
         unsigned int na, nb;
-        chunk_build_two(sh, status, base, p.n_slots, phase ? ST_HIT : ST_TRACE, phase ? ST_MISS : (unsigned char)0xff, &na, &nb);
+        chunk_build_two(sh, stp_, base - sbase, sn, phase ? ST_HIT : ST_TRACE, phase ? ST_MISS : (unsigned char)0xff, &na, &nb);
         if (phase == 0u) {
             if (na == 0u) break;  // every pixel of the chunk has finished its samples
             if (threadIdx.x == 0) sh.count[0] += na;
-            chunk_stage_trace<COUNT, QUANTUM>(sh, s, f, p, status, base, na, iter == 0, tc);
+            chunk_stage_trace<COUNT, QUANTUM>(sh, s, f, p, stp_, base, na, iter == 0, tc, sbase);
             ++iter;
         } else {
-            chunk_stage_shade_miss(sh, s, f, p, status, base, na, nb);
+            chunk_stage_shade_miss(sh, s, f, p, stp_, base, na, nb, sbase);
         }
         __syncthreads();  // status / hit records of this chunk are block-visible from here on
     }
@@ -349,13 +387,13 @@ __global__ void __launch_bounds__(PTB_CHUNK_THREADS, (MINB * 128 + PTB_CHUNK_THR
 }
 
 // ---- host-side launchers shared by both builds of the kernels (renderer.cu calls ptb::..., fast_kernels.cu wraps
-// ptb_fast::...) ---------------------------------------------------------------------------------------------------
+// ptb_fast::...).  Grid sizes are derived HERE from the slot count, because the two builds may use different block sizes
+// (PTB_CHUNK_THREADS is a per-translation-unit constant). ------------------------------------------------------------
 struct ChunkLaunch {
     SceneView s; FrameView f; PathView p;
     unsigned char* status; unsigned long long* totals; unsigned long long* trav_stats; unsigned int* max_iters;
-    uint32_t chunks;   // blocks of the fused kernel = ceil(slots / (PTB_CHUNK_THREADS * spt))
-    int spt;           // slots per thread: 8, 4, 2 or 1
-    int wide;          // 1: enough chunks to fill the chip -> the 64-register / 4-blocks-per-SM build
+    int num_sms;
+    int spt_request;   // slots per thread asked for by the caller: 0 = by launch size, else 1, 2, 4 or 8
     int count;         // 1: count nodes visited / triangles tested (2048-slot chunks only)
 };
 
@@ -363,12 +401,26 @@ inline void launch_chunk_raygen(const ChunkLaunch& a, cudaStream_t st) {
     k_chunk_raygen<<<(a.p.n_slots + 255u) / 256u, 256, 0, st>>>(a.f, a.p, a.status);
 }
 
+// Chunk size by launch size: 8 slots per thread when that still gives 8 waves of blocks, otherwise fewer slots per thread so
+// that a small frame (the reference's 600 x 400 / 1600 x 1200 launches of one subframe) spreads over the whole chip instead
+// of running its per-pixel sample chains on a few warps per SM (profiles/r1_experiments.md: 600 x 400 4.66 -> 2.50 ms).
 inline void launch_chunk_fused(const ChunkLaunch& a, cudaStream_t st) {
-#define PTB_CF_LAUNCH(COUNT, MINB, SPT) k_chunk_fused<COUNT, PTB_TRACE_QUANTUM, MINB, SPT><<<a.chunks, PTB_CHUNK_THREADS, 0, st>>>(a.s, a.f, a.p, a.status, a.totals, a.trav_stats, a.max_iters)
-#define PTB_CF_BY_SPT(COUNT, MINB) do { if (a.spt == 8) PTB_CF_LAUNCH(COUNT, MINB, 8); else if (a.spt == 4) PTB_CF_LAUNCH(COUNT, MINB, 4); \
-                                        else if (a.spt == 2) PTB_CF_LAUNCH(COUNT, MINB, 2); else PTB_CF_LAUNCH(COUNT, MINB, 1); } while (0)
+    const uint32_t slots = a.p.n_slots;
+    const uint32_t full = (uint32_t)a.num_sms * (1024u / PTB_CHUNK_THREADS);  // resident blocks at 64 registers
+    int spt = 8;
+    while (spt > 1 && (slots + PTB_CHUNK_THREADS * (uint32_t)spt - 1u) / (PTB_CHUNK_THREADS * (uint32_t)spt) < 8u * full) spt >>= 1;
+    if (a.spt_request) spt = a.spt_request;
+    if (a.count) spt = 8;  // the counting variant is instantiated for the largest chunks only: size the grid for it
+    const uint32_t chunk = PTB_CHUNK_THREADS * (uint32_t)spt;
+    const uint32_t chunks = (slots + chunk - 1u) / chunk;
+    // 64 registers once there are enough chunks to keep that many blocks busy, the unconstrained ~80-register build for
+    // launches that cannot fill the chip anyway
+    const bool wide = chunks >= full;
+#define PTB_CF_LAUNCH(COUNT, MINB, SPT) k_chunk_fused<COUNT, PTB_TRACE_QUANTUM, MINB, SPT><<<chunks, PTB_CHUNK_THREADS, 0, st>>>(a.s, a.f, a.p, a.status, a.totals, a.trav_stats, a.max_iters)
+#define PTB_CF_BY_SPT(COUNT, MINB) do { if (spt == 8) PTB_CF_LAUNCH(COUNT, MINB, 8); else if (spt == 4) PTB_CF_LAUNCH(COUNT, MINB, 4); \
+                                        else if (spt == 2) PTB_CF_LAUNCH(COUNT, MINB, 2); else PTB_CF_LAUNCH(COUNT, MINB, 1); } while (0)
     if (a.count) PTB_CF_LAUNCH(true, 5, 8);
-    else if (a.wide) PTB_CF_BY_SPT(false, 8);
+    else if (wide) PTB_CF_BY_SPT(false, PTB_MINB_WIDE);
     else PTB_CF_BY_SPT(false, 5);
 #undef PTB_CF_BY_SPT
 #undef PTB_CF_LAUNCH
@@ -376,11 +428,12 @@ inline void launch_chunk_fused(const ChunkLaunch& a, cudaStream_t st) {
 
 // one wavefront iteration of the stage-kernel pipeline (pipeline 2): 0 = trace, 1 = shade, 2 = miss
 inline void launch_chunk_stage(const ChunkLaunch& a, int stage, int iter, cudaStream_t st) {
+    const uint32_t chunks = (a.p.n_slots + PTB_CHUNK - 1u) / PTB_CHUNK;
     if (stage == 0) {
-        if (a.count) k_chunk_trace<true, PTB_TRACE_QUANTUM><<<a.chunks, PTB_CHUNK_THREADS, 0, st>>>(a.s, a.f, a.p, a.status, a.totals, a.trav_stats, iter);
-        else k_chunk_trace<false, PTB_TRACE_QUANTUM><<<a.chunks, PTB_CHUNK_THREADS, 0, st>>>(a.s, a.f, a.p, a.status, a.totals, a.trav_stats, iter);
-    } else if (stage == 1) k_chunk_shade<<<a.chunks, PTB_CHUNK_THREADS, 0, st>>>(a.s, a.f, a.p, a.status);
-    else k_chunk_miss<<<a.chunks, PTB_CHUNK_THREADS, 0, st>>>(a.s, a.f, a.p, a.status);
+        if (a.count) k_chunk_trace<true, PTB_TRACE_QUANTUM><<<chunks, PTB_CHUNK_THREADS, 0, st>>>(a.s, a.f, a.p, a.status, a.totals, a.trav_stats, iter);
+        else k_chunk_trace<false, PTB_TRACE_QUANTUM><<<chunks, PTB_CHUNK_THREADS, 0, st>>>(a.s, a.f, a.p, a.status, a.totals, a.trav_stats, iter);
+    } else if (stage == 1) k_chunk_shade<<<chunks, PTB_CHUNK_THREADS, 0, st>>>(a.s, a.f, a.p, a.status);
+    else k_chunk_miss<<<chunks, PTB_CHUNK_THREADS, 0, st>>>(a.s, a.f, a.p, a.status);
 }
 
 }  // namespace PTB_NS

@@ -9,7 +9,7 @@ namespace ptb_fast_api {
 struct ChunkLaunchArgs {
     ptbv::SceneView s; ptbv::FrameView f; ptbv::PathView p;
     unsigned char* status; unsigned long long* totals; unsigned long long* trav_stats; unsigned int* max_iters;
-    uint32_t chunks; int spt, wide, count;
+    int num_sms, spt_request, count;
 };
 void raygen(const ChunkLaunchArgs& a, cudaStream_t st);
 void fused(const ChunkLaunchArgs& a, cudaStream_t st);

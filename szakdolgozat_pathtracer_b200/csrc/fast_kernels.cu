@@ -13,7 +13,7 @@ static ptb_fast::ChunkLaunch convert(const ChunkLaunchArgs& a) {
     ptb_fast::ChunkLaunch c;
     c.s = a.s; c.f = a.f; c.p = a.p;
     c.status = a.status; c.totals = a.totals; c.trav_stats = a.trav_stats; c.max_iters = a.max_iters;
-    c.chunks = a.chunks; c.spt = a.spt; c.wide = a.wide; c.count = a.count;
+    c.num_sms = a.num_sms; c.spt_request = a.spt_request; c.count = a.count;
     return c;
 }
 void raygen(const ChunkLaunchArgs& a, cudaStream_t st) { ptb_fast::launch_chunk_raygen(convert(a), st); }

@@ -66,7 +66,7 @@ struct ptb_scene {
     std::vector<ptb::Material> mats;
     std::vector<float> env;  // float4 texels
     int env_w = 0, env_h = 0;
-    ptb::DeviceScene* dev = nullptr;  // owned; created by ptb_accel_build
+    std::vector<ptb::DeviceScene*> devs;  // owned; one upload per context the scene was built on (ptb_accel_build)
     uint64_t revision = 0;            // bumped by every host-side mutation
 };
 

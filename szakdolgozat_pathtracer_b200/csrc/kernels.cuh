@@ -64,10 +64,12 @@ PTB_DEV uint32_t image_row(const FrameView& f, uint32_t lr) {
 }
 
 // ---- camera ray of one sample (cu:326-347) ------------------------------------------
-// Camera rays decide the primary-hit IDs, so they are written with ex_* operations and are bit-identical in the exact and
-// the fast build (PTB_FAST_EXACT_CAMERA = 0 lets the fast build use MUFU sin/cos/sqrt in the depth-of-field branch).
+// Camera rays decide the primary-hit IDs, so the pinhole ray is written with ex_* operations and is bit-identical in the
+// exact and the fast build.  The depth-of-field branch (two square roots, a sine / cosine pair, a normalisation) uses the
+// MUFU approximations in the fast build unless PTB_FAST_EXACT_CAMERA = 1: its primary hits then differ from the exact
+// build's only where a ray passes within rounding of a triangle edge (counted by tests/test_gpu_fast_mode.py).
 #ifndef PTB_FAST_EXACT_CAMERA
-#define PTB_FAST_EXACT_CAMERA 1
+#define PTB_FAST_EXACT_CAMERA 0
 #endif
 PTB_DEV float3 ex_camera_dir(float dx, float dy, float3 U, float3 V, float3 Wv) {  // (dx * U + dy * V) + W
     return mk3(ex_add(ex_add(ex_mul(dx, U.x), ex_mul(dy, V.x)), Wv.x), ex_add(ex_add(ex_mul(dx, U.y), ex_mul(dy, V.y)), Wv.y),
@@ -239,7 +241,9 @@ PTB_DEV float4 sample_env(const float4* env, int w, int h, float u, float v) {
     // u, v are in [0, 1] (atan2 / asin of a normalised direction; a NaN converts to 0), so floorf(x) is in [-1, w-1]
     // and the reference's `% w` (C remainder: -1 stays -1) is the identity on that range: no integer division here.
     const float x = u * w - 0.5f, y = v * h - 0.5f;
-    const int x0 = (int)floorf(x), y0 = (int)floorf(y);
+    int x0 = (int)floorf(x), y0 = (int)floorf(y);
+    if (w == 1) x0 = 0;  // the one case where `% w` is not the identity on [-1, w-1]: -1 % 1 == 0 (one-column / one-row maps)
+    if (h == 1) y0 = 0;
     return bilinear(env, 2, w, h, x0, y0, x - floorf(x), y - floorf(y));
 }
 // setMaterialProperty (cu:598-613)
@@ -594,13 +598,15 @@ __global__ void __launch_bounds__(256) k_resolve_scaled(const float4* __restrict
 // that slice from all ranks' accumulators (local HBM or NVLink peer loads) and storing the result where the root wants it.
 #define PTB_MAX_RANKS 16
 struct PeerAccums { const float4* a[PTB_MAX_RANKS]; int n; };
-__global__ void __launch_bounds__(256) k_resolve_peers(PeerAccums peers, float4* __restrict__ accum_out, uchar4* __restrict__ frame,
-                                                       uint32_t first, uint32_t n, float scale, float exposure_scale,
-                                                       float inv_gamma, float contrast) {
+// prev (optional, may alias accum_out): what the frame's accumulator holds from earlier launches, as a mean over prev_weight
+// subframes; it enters the sum first, weighted, so that a progressive render continues across launches.
+__global__ void __launch_bounds__(256) k_resolve_peers(PeerAccums peers, const float4* prev, float prev_weight, float4* accum_out,
+                                                       uchar4* __restrict__ frame, uint32_t first, uint32_t n, float scale,
+                                                       float exposure_scale, float inv_gamma, float contrast) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t px = first + i;
-    float3 sum = mk3(0.0f);
+    float3 sum = prev ? mk3(prev[px]) * prev_weight : mk3(0.0f);
     for (int k = 0; k < peers.n; ++k) sum = sum + mk3(peers.a[k][px]);  // fixed rank order: deterministic
     const float3 c = sum * scale;
     if (accum_out) accum_out[px] = make_float4(c.x, c.y, c.z, 1.0f);

@@ -80,6 +80,7 @@ struct ptb_context {
     // linear estimator (env_importance_sampling != 0): pending shadow rays, allocated on first use
     float4 *shadow_o = nullptr, *shadow_d = nullptr, *shadow_c = nullptr; unsigned char* shadow_flag = nullptr; uint32_t shadow_slots = 0;
     int last_pipeline = 0;
+    bool keep_launch_totals = false;  // set by ptb_launch while it renders the later batches of a bounded-pool launch
     // last launch, for ptb_launch_get_stats
     cudaStream_t last_stream = nullptr;
     uint32_t last_iters = 0, last_kernels = 0;
@@ -110,6 +111,8 @@ void free_device_scene(DeviceScene* d) {
 }  // namespace ptb
 
 namespace {
+
+#define PTB_SLOT_BYTES 97ull  // path state per slot: six 16-byte records + one status byte
 
 int fail(int code, const std::string& msg) { set_error(msg); return code; }
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(PTB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
@@ -224,7 +227,11 @@ int ptb_accel_build(ptb_context* ctx, ptb_scene* scene, const ptb_build_cfg* cfg
     ptb_build_cfg cfg;
     if (cfg_in) cfg = *cfg_in; else ptb_default_build_cfg(&cfg);
 
-    if (scene->dev) { free_device_scene(scene->dev); scene->dev = nullptr; }
+    // a scene can be built on several contexts (multi-GPU replicas); a rebuild replaces THIS context's upload only
+    for (size_t i = 0; i < scene->devs.size();) {
+        if (scene->devs[i]->owner == ctx || scene->devs[i]->owner == nullptr) { free_device_scene(scene->devs[i]); scene->devs.erase(scene->devs.begin() + i); }
+        else ++i;
+    }
     DeviceScene* d = new DeviceScene();
     d->device = ctx->device; d->revision = scene->revision; d->source = scene;
     const uint32_t n = (uint32_t)scene->tris.size();
@@ -317,7 +324,7 @@ int ptb_accel_build(ptb_context* ctx, ptb_scene* scene, const ptb_build_cfg* cfg
     d->handle = ctx->next_handle++;
     d->owner = ctx;
     ctx->scenes[d->handle] = d;
-    scene->dev = d;
+    scene->devs.push_back(d);
     *handle = d->handle;
     if (stats_out) *stats_out = stats;
     return PTB_OK;
@@ -360,6 +367,31 @@ int ptb_launch(ptb_context* ctx, const ptb_Params* P, const ptb_render_cfg* cfg_
     CU(cudaSetDevice(ctx->device));
 
     const int n_sub = cfg.subframes_per_launch < 1 ? 1 : cfg.subframes_per_launch;
+    // The path pool is bounded: a launch whose n_sub * W * H slots would need more than max_pool_bytes of path state
+    // (97 B per slot) is rendered as consecutive batches of subframes, each one wavefront -- bit-identical to the single
+    // wavefront (and to n_sub separate launches); counters of the batches add up.
+    {
+        const uint64_t cap_bytes = cfg.max_pool_bytes > 0 ? (uint64_t)cfg.max_pool_bytes : (2ull << 30);
+        const uint64_t px = (uint64_t)P->image_width * P->image_height;   // an upper bound of the launch's pixels (bands render fewer)
+        uint64_t max_sub = cap_bytes / (px * PTB_SLOT_BYTES);
+        if (max_sub < 1) max_sub = 1;
+        if ((uint64_t)n_sub > max_sub && cfg.pipeline != PTB_PIPELINE_POOL_FUSED) {
+            uint32_t kernels = 0; uint64_t paths = 0;
+            for (int first = 0; first < n_sub; first += (int)max_sub) {
+                ptb_Params p2 = *P; p2.subframe_index = P->subframe_index + first;
+                ptb_render_cfg c2 = cfg;
+                c2.subframes_per_launch = n_sub - first < (int)max_sub ? n_sub - first : (int)max_sub;
+                if (first > 0) c2.aux_primary_hit = nullptr;   // primary hits are those of the launch's first subframe
+                ctx->keep_launch_totals = first > 0;
+                const int rc = ptb_launch(ctx, &p2, &c2, stream_);
+                ctx->keep_launch_totals = false;
+                if (rc != PTB_OK) return rc;
+                kernels += ctx->last_kernels; paths += ctx->last_paths;
+            }
+            ctx->last_kernels = kernels; ctx->last_paths = paths;
+            return PTB_OK;
+        }
+    }
     uint32_t row0 = 0, rows = P->image_height;
     if (cfg.row_begin != 0 || cfg.row_end != 0) {
         if (cfg.row_begin < 0 || cfg.row_end <= cfg.row_begin || (uint32_t)cfg.row_end > P->image_height)
@@ -433,8 +465,10 @@ int ptb_launch(ptb_context* ctx, const ptb_Params* P, const ptb_render_cfg* cfg_
     const SceneView s = scene_view(d);
 
     CU(cudaMemsetAsync(ctx->counters, 0, (size_t)(iters + 2) * 4 * sizeof(uint32_t), st));
-    CU(cudaMemsetAsync(ctx->trav_stats, 0, 2 * sizeof(unsigned long long), st));
-    CU(cudaMemsetAsync(ctx->launch_totals, 0, 4 * sizeof(unsigned long long), st));
+    if (!ctx->keep_launch_totals) {  // later batches of one launch add to the counters of the first
+        CU(cudaMemsetAsync(ctx->trav_stats, 0, 2 * sizeof(unsigned long long), st));
+        CU(cudaMemsetAsync(ctx->launch_totals, 0, 4 * sizeof(unsigned long long), st));
+    }
     const uint32_t pix_blocks = (slots + 255u) / 256u;
     const bool prof = cfg.profile_stages != 0;
     if (prof) {
@@ -520,32 +554,15 @@ int ptb_launch(ptb_context* ctx, const ptb_Params* P, const ptb_render_cfg* cfg_
         ChunkLaunch cl;
         cl.s = s; cl.f = f; cl.p = p; cl.status = ctx->status; cl.totals = ctx->launch_totals; cl.trav_stats = ctx->trav_stats;
         cl.max_iters = (unsigned int*)(ctx->launch_totals + 3);
-        cl.count = cfg.count_traversal ? 1 : 0; cl.spt = PTB_CHUNK_SPT; cl.wide = 1;
-        cl.chunks = (slots + PTB_CHUNK - 1u) / PTB_CHUNK;
-        if (pipeline == PTB_PIPELINE_CHUNK_FUSED) {
-            // Chunk size by launch size: 8 slots per thread (2048-slot chunks) when that still gives 8 waves of blocks,
-            // otherwise fewer slots per thread so that a small frame (the reference's 600 x 400 / 1600 x 1200 launches of
-            // one subframe) spreads over the whole chip instead of running its per-pixel sample chains on a few warps per
-            // SM.  Measured (profiles/r1_experiments.md): 600 x 400 4.66 -> 2.50 ms, 1600 x 1200 7.36 -> 6.20 ms per launch.
-            static const int env_spt = getenv("PTB_SPT") ? atoi(getenv("PTB_SPT")) : 0;  // experiments only
-            const uint32_t blocks_per_sm = 1024u / PTB_CHUNK_THREADS;
-            const uint32_t full = (uint32_t)ctx->num_sms * blocks_per_sm;                  // resident blocks at 64 registers
-            int spt = 8;
-            while (spt > 1 && (slots + PTB_CHUNK_THREADS * (uint32_t)spt - 1u) / (PTB_CHUNK_THREADS * (uint32_t)spt) < 8u * full) spt >>= 1;
-            if (env_spt) spt = env_spt;
-            if (cfg.chunk_slots_per_thread) spt = cfg.chunk_slots_per_thread;
-            if (spt != 8 && spt != 4 && spt != 2 && spt != 1) return fail(PTB_ERR_INVALID, "ptb_launch: chunk_slots_per_thread must be 0, 1, 2, 4 or 8");
-            if (cfg.count_traversal) spt = 8;  // the counting variant is instantiated for 2048-slot chunks only: size the grid for it
-            const uint32_t chunk = PTB_CHUNK_THREADS * (uint32_t)spt;
-            cl.spt = spt; cl.chunks = (slots + chunk - 1u) / chunk;
-            // 64 registers / 4 blocks per SM once there are enough chunks to keep that many blocks busy, the
-            // unconstrained ~80-register build for launches that cannot fill the chip anyway
-            cl.wide = cl.chunks >= full ? 1 : 0;
-        }
+        cl.count = cfg.count_traversal ? 1 : 0; cl.num_sms = ctx->num_sms;
+        static const int env_spt = getenv("PTB_SPT") ? atoi(getenv("PTB_SPT")) : 0;  // experiments only
+        cl.spt_request = cfg.chunk_slots_per_thread ? cfg.chunk_slots_per_thread : env_spt;
+        if (cl.spt_request != 0 && cl.spt_request != 8 && cl.spt_request != 4 && cl.spt_request != 2 && cl.spt_request != 1)
+            return fail(PTB_ERR_INVALID, "ptb_launch: chunk_slots_per_thread must be 0, 1, 2, 4 or 8");
         ptb_fast_api::ChunkLaunchArgs fa;
         if (fast) {
             fa.s = s; fa.f = f; fa.p = p; fa.status = cl.status; fa.totals = cl.totals; fa.trav_stats = cl.trav_stats; fa.max_iters = cl.max_iters;
-            fa.chunks = cl.chunks; fa.spt = cl.spt; fa.wide = cl.wide; fa.count = cl.count;
+            fa.num_sms = cl.num_sms; fa.spt_request = cl.spt_request; fa.count = cl.count;
             ptb_fast_api::raygen(fa, st);
         } else launch_chunk_raygen(cl, st);
         if (prof) CU(cudaEventRecord(ctx->events[1], st));
@@ -647,6 +664,12 @@ int ptb_resolve(ptb_context* ctx, const ptb_float4* accum, ptb_float4* accum_out
 
 int ptb_resolve_peers(ptb_context* ctx, const ptb_float4* const* accums, int n_ranks, ptb_float4* accum_out, ptb_uchar4* frame,
                       uint32_t first_pixel, uint32_t n_pixels, float scale, const ptb_render_cfg* cfg_in, void* stream_) {
+    return ptb_resolve_peers_accumulate(ctx, accums, n_ranks, nullptr, 0.0f, accum_out, frame, first_pixel, n_pixels, scale, cfg_in, stream_);
+}
+
+int ptb_resolve_peers_accumulate(ptb_context* ctx, const ptb_float4* const* accums, int n_ranks, const ptb_float4* prev_accum, float prev_weight,
+                                 ptb_float4* accum_out, ptb_uchar4* frame, uint32_t first_pixel, uint32_t n_pixels, float scale,
+                                 const ptb_render_cfg* cfg_in, void* stream_) {
     if (!ctx || !accums || n_ranks < 1 || n_ranks > PTB_MAX_RANKS) return fail(PTB_ERR_INVALID, "ptb_resolve_peers: bad arguments");
     ptb_render_cfg cfg;
     if (cfg_in) cfg = *cfg_in; else ptb_default_render_cfg(&cfg);
@@ -654,7 +677,7 @@ int ptb_resolve_peers(ptb_context* ctx, const ptb_float4* const* accums, int n_r
     pa.n = n_ranks;
     for (int k = 0; k < n_ranks; ++k) { if (!accums[k]) return fail(PTB_ERR_INVALID, "ptb_resolve_peers: null accumulator"); pa.a[k] = (const float4*)accums[k]; }
     CU(cudaSetDevice(ctx->device));
-    if (n_pixels) k_resolve_peers<<<(n_pixels + 255u) / 256u, 256, 0, (cudaStream_t)stream_>>>(pa, (float4*)accum_out, (uchar4*)frame, first_pixel, n_pixels,
+    if (n_pixels) k_resolve_peers<<<(n_pixels + 255u) / 256u, 256, 0, (cudaStream_t)stream_>>>(pa, (const float4*)prev_accum, prev_weight, (float4*)accum_out, (uchar4*)frame, first_pixel, n_pixels,
                                                                                                 scale, exp2f(cfg.exposure), 1.0f / cfg.gamma, cfg.contrast);
     CU(cudaGetLastError());
     return PTB_OK;

@@ -144,3 +144,30 @@ def test_stale_handle_is_refused(ptb, ctx, assets):
         ctx.synchronize()
     finally:
         ctx.free(d)
+
+
+def test_bounded_pool_batches_bit_identical(ptb, ctx, assets):
+    """ptb_render_cfg.max_pool_bytes: a 7-subframe launch whose pool is capped at 2 / 3 subframes' worth of path state runs as
+    batches inside ptb_launch -- accumulator, frame, primary hits and every counter equal the single wavefront's."""
+    sc = load_config(ptb, assets, "c2")
+    handle, _ = ctx.accel_build(sc)
+    W, H = 200, 120
+    n = W * H
+    res = []
+    for cap in (0, 97 * n * 2 + 5, 97 * n * 3, 1):   # default (2 GiB: one wavefront), 2 per batch, 3 per batch, 1 per batch
+        d_accum, d_frame, d_hits = ctx.alloc(n * 16), ctx.alloc(n * 4), ctx.alloc(n * 4)
+        try:
+            ctx.memset(d_accum, 0, n * 16); ctx.memset(d_hits, 0xFF, n * 4)
+            p = ptb.make_params(W, H, subframe_index=3, dof=True, **CAMERAS["monkey_close"])
+            p.accum_buffer, p.frame_buffer, p.handle = d_accum, d_frame, handle
+            ctx.launch(p, ptb.default_render_cfg(spp_per_launch=3, max_depth=6, subframes_per_launch=7, max_pool_bytes=cap, aux_primary_hit=d_hits,
+                                                 count_traversal=1))
+            st = ctx.launch_stats()
+            res.append((ctx.to_host(d_accum, (H, W, 4), np.float32).view(np.uint32), ctx.to_host(d_frame, (H, W, 4), np.uint8),
+                        ctx.to_host(d_hits, (H, W), np.int32), (st.segments, st.hits, st.misses, st.paths, st.nodes_visited, st.tris_tested)))
+        finally:
+            for b in (d_accum, d_frame, d_hits):
+                ctx.free(b)
+    for r in res[1:]:
+        assert all(np.array_equal(x, y) for x, y in zip(res[0][:3], r[:3])) and res[0][3] == r[3]
+    assert res[0][3][3] == n * 3 * 7 and res[0][3][0] > res[0][3][3]

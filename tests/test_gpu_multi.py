@@ -1,0 +1,112 @@
+"""ptb_multi (csrc/multi.cpp): multi-GPU rendering behind the C ABI, one host process driving n devices.
+
+On a one-GPU box the same device is listed several times (several contexts, streams and accumulators on one GPU), which
+runs exactly the code path of n real devices except the NVLink hops; tools/check_multi_gpu.py runs the same checks over
+real peers and its output is kept under profiles/.
+
+  tiles    every pixel is computed whole by one device with its full-frame seed -> BIT-IDENTICAL to one ptb_launch;
+  samples  per-device sums of launch means, reduced in device order and folded into the running mean as
+           (old * s + sum) / (s + K): equal to the reference's lerp (optixSphere.cu:403-409) up to rounding.  Stated
+           tolerance: 2e-6 relative to the pixel value + 1e-7 absolute (a handful of float roundings); frame bytes within 1.
+"""
+import numpy as np
+import pytest
+
+from scenes import load_config
+
+pytestmark = pytest.mark.gpu
+
+
+def _single(ptb, ctx, sc, W, H, kw, launches):
+    handle, _ = ctx.accel_build(sc)
+    n = W * H
+    d_accum, d_frame = ctx.alloc(n * 16), ctx.alloc(n * 4)
+    try:
+        ctx.memset(d_accum, 0, n * 16)
+        seg, sf = 0, 0
+        for k in launches:
+            p = ptb.make_params(W, H, subframe_index=sf, dof=True)
+            p.accum_buffer, p.frame_buffer, p.handle = d_accum, d_frame, handle
+            ctx.launch(p, ptb.default_render_cfg(subframes_per_launch=k, **kw))
+            seg += ctx.launch_stats().segments
+            sf += k
+        return ctx.to_host(d_accum, (H, W, 4), np.float32), ctx.to_host(d_frame, (H, W, 4), np.uint8), seg
+    finally:
+        ctx.free(d_accum); ctx.free(d_frame)
+
+
+def _multi(ptb, sc, n_dev, W, H, kw, launches, split):
+    m = ptb.Multi([0] * n_dev)
+    try:
+        m.accel_build(sc)
+        root = m.root
+        n = W * H
+        d_accum, d_frame = root.alloc(n * 16), root.alloc(n * 4)
+        root.memset(d_accum, 0, n * 16); root.memset(d_frame, 0, n * 4)
+        root.synchronize()
+        sf = 0
+        for k in launches:
+            p = ptb.make_params(W, H, subframe_index=sf, dof=True)
+            p.accum_buffer, p.frame_buffer = d_accum, d_frame
+            m.launch(p, ptb.default_render_cfg(subframes_per_launch=k, **kw), split)
+            sf += k
+        seg = m.totals()["segments"]
+        a, f = root.to_host(d_accum, (H, W, 4), np.float32), root.to_host(d_frame, (H, W, 4), np.uint8)
+        root.free(d_accum); root.free(d_frame)
+        return a, f, seg
+    finally:
+        m.close()
+
+
+@pytest.mark.parametrize("n_dev", [2, 3])
+def test_multi_tiles_bit_identical(ptb, ctx, assets, n_dev):
+    sc = load_config(ptb, assets, "c1", small=True)
+    W, H = 150, 100   # 100 rows = 6 strips of 16 + 4: ragged last strip
+    kw = dict(spp_per_launch=3, max_depth=5)
+    launches = [2, 1, 3]
+    a1, f1, s1 = _single(ptb, ctx, sc, W, H, kw, launches)
+    a2, f2, s2 = _multi(ptb, sc, n_dev, W, H, kw, launches, ptb.PTB_SPLIT_TILES)
+    assert s1 == s2
+    assert np.array_equal(a1.view(np.uint32), a2.view(np.uint32)) and np.array_equal(f1, f2)
+
+
+@pytest.mark.parametrize("n_dev", [1, 2, 3])
+def test_multi_sample_split_matches_running_average(ptb, ctx, assets, n_dev):
+    sc = load_config(ptb, assets, "c2")
+    W, H = 160, 90
+    kw = dict(spp_per_launch=4, max_depth=6)
+    launches = [4, 5, 1]   # K not a multiple of the device count; a later launch continues the frame's mean
+    a1, f1, s1 = _single(ptb, ctx, sc, W, H, kw, launches)
+    a2, f2, s2 = _multi(ptb, sc, n_dev, W, H, kw, launches, ptb.PTB_SPLIT_SAMPLES)
+    assert s1 == s2, "the same samples are rendered, whatever the device count"
+    if n_dev == 1:
+        assert np.array_equal(a1.view(np.uint32), a2.view(np.uint32)) and np.array_equal(f1, f2)
+        return
+    err = np.abs(a1[..., :3].astype(np.float64) - a2[..., :3])
+    tol = 2e-6 * np.abs(a1[..., :3]) + 1e-7
+    assert (err <= tol).all(), float((err / (np.abs(a1[..., :3]) + 1e-7)).max())
+    assert np.all(a2[..., 3] == 1.0)
+    assert np.abs(f1.astype(np.int32) - f2.astype(np.int32)).max() <= 1
+
+
+def test_multi_argument_errors(ptb, assets):
+    with pytest.raises(ptb.PtbError):
+        ptb.Multi([0, 99])          # no such device
+    m = ptb.Multi([0, 0])
+    try:
+        p = ptb.make_params(32, 32)
+        d = m.root.alloc(32 * 32 * 16)
+        p.accum_buffer = d
+        with pytest.raises(ptb.PtbError):   # nothing built yet
+            m.launch(p, ptb.default_render_cfg(write_frame=0))
+        sc = load_config(ptb, assets, "c1", small=True)
+        m.accel_build(sc)
+        with pytest.raises(ptb.PtbError):   # the row partition belongs to the split mode
+            m.launch(p, ptb.default_render_cfg(write_frame=0, row_begin=0, row_end=8))
+        with pytest.raises(ptb.PtbError):
+            m.launch(p, ptb.default_render_cfg(write_frame=0), 7)
+        m.launch(p, ptb.default_render_cfg(write_frame=0, spp_per_launch=1, max_depth=1))
+        m.synchronize()
+        m.root.free(d)
+    finally:
+        m.close()
