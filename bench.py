@@ -7,13 +7,18 @@ One STEP = one full 64-spp frame = 8 subframes of 8 samples per pixel, rendered 
 ptb_launch() with subframes_per_launch = 8 (bit-identical to 8 consecutive calls, i.e. to 8 optixLaunch
 iterations of the reference's render loop, optixSphere.cpp:1390-1437; tests/test_gpu_parity.py checks it).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W]            our CUDA path
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our CUDA path; --arith fast (default, the headline: the
+                                                                 reference's own build mode, gated by tests/test_gpu_fast_mode.py)
+                                                                 or --arith exact (bit-identical to the CPU oracle); the other
+                                                                 mode is timed alongside and reported under "other_arith"
   python bench.py --impl reference [--gpus N] [--steps K] ...    the reference's own device file compiled for the
                                                                  host (oracle/_ref), timed on the box's CPU cores
 
 N > 1 (one process per GPU under torchrun): the scene is replicated, rank r renders
-subframes r, r+N, ... of a 64*N-spp frame (weak scaling) into a sum-mode accumulator,
-one NCCL reduce of the float4 accumulator follows, rank 0 resolves/tonemaps.
+a contiguous block of subframes of a 64*N-spp frame (weak scaling) into a sum-mode accumulator; the exchange is ONE
+fused kernel per rank over peer memory (reduce-scatter -> tonemap -> gather, NVLink), ordered by epoch flags in
+peer-mapped memory -- no NCCL on the data path or for ordering (`--exchange nccl` keeps the ncclReduce variant).
+Strong scaling (the fixed 64-spp frame split by samples and by tiles) is timed too and reported under "strong".
 
 Prints ONE JSON line (rank 0).  `value` = segments of all ranks / max-over-ranks device time.
 """
@@ -174,6 +179,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pipeline", type=int, default=3, help="1 global queues, 2 chunked stage kernels, 3 chunked fused (default), 4 persistent pool")
     ap.add_argument("--config", default="c2", choices=list(CONFIGS))
+    ap.add_argument("--arith", default="fast", choices=["fast", "exact"], help="arithmetic mode of the headline number (ptb_render_cfg.arith_mode)")
+    ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the strong-scaling legs")
     ap.add_argument("--split", default="samples", choices=["samples", "tiles"],
                     help="N > 1: split the frame's subframes across ranks (weak scaling, default) or its rows (tile partitioning, strong scaling)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="N > 1: fused peer-memory exchange (default) or NCCL reduce")
@@ -202,6 +209,10 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
+    ARITH = {"exact": ptb.PTB_ARITH_EXACT, "fast": ptb.PTB_ARITH_FAST}
+    arith, other = args.arith, ("exact" if args.arith == "fast" else "fast")
+    if args.pipeline not in (2, 3):   # the fast build exists for the chunked pipelines only
+        arith, other = "exact", None
 
     ctx = ptb.Context(local_rank)
     if rank == 0:
@@ -216,30 +227,26 @@ def main():
     accum = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
     frame = torch.zeros((H, W, 4), dtype=torch.uint8, device=dev)
     multi = world > 1
-    # the whole 64-spp frame of this rank is ONE wavefront: 8 subframes x 1920 x 1080 path slots
     tiles = multi and args.split == "tiles"
-    band = (0, 0)
-    il = dict(row_interleave_count=world, row_interleave_index=rank, row_interleave_height=16) if tiles else {}
-    total_subframes = LAUNCHES_PER_STEP * (1 if (tiles or not multi) else world)   # subframes in the frame all ranks produce together
-    cfg = ptb.default_render_cfg(spp_per_launch=SPP_PER_LAUNCH, max_depth=DEPTH, subframes_per_launch=LAUNCHES_PER_STEP,
-                                 pipeline=args.pipeline, accumulate_mode=1 if multi else 0, write_frame=0 if multi else 1,
-                                 row_begin=band[0], row_end=band[1], **il)
+
+    def make_cfg(mode, subframes=LAUNCHES_PER_STEP, tiled=False, **kw):
+        il = dict(row_interleave_count=world, row_interleave_index=rank, row_interleave_height=16) if tiled else {}
+        base = dict(spp_per_launch=SPP_PER_LAUNCH, max_depth=DEPTH, subframes_per_launch=subframes, pipeline=args.pipeline,
+                    accumulate_mode=1 if multi else 0, write_frame=0 if multi else 1, arith_mode=ARITH[mode])
+        base.update(il); base.update(kw)
+        return ptb.default_render_cfg(**base)
 
     # N > 1 exchange.  "p2p": every rank reduces + tonemaps its slice of the frame straight out of the peers' accumulators
-    # (CUDA IPC mappings over NVLink) and stores it into rank 0's buffers: ONE kernel per rank (ptb_resolve_peers), NCCL only
-    # for two stream-ordered barriers.  "nccl": ncclReduce of the float4 accumulator, then ptb_resolve on rank 0.
-    acc_ptr, frame_ptr = accum.data_ptr(), frame.data_ptr()
-    exchange, exchange_note, tiny = None, "none (single GPU)", None
+    # (CUDA IPC mappings over NVLink) and stores it into rank 0's buffers: ONE kernel per rank, ordered by epoch flags in
+    # peer memory (parallel.PeerExchange).  "nccl": ncclReduce of the float4 accumulator, then ptb_resolve on rank 0.
+    exchange, exchange_note = None, "none (single GPU)"
     if multi:
         exchange_note = "nccl reduce + ptb_resolve on rank 0"
         if args.exchange == "p2p":
             try:
-                raw_accum, raw_out = ctx.alloc(n * 16), ctx.alloc(n * 16)   # plain cudaMalloc: exportable through CUDA IPC
-                raw_frame = ctx.alloc(n * 4)
-                exchange = parallel.PeerExchange(ctx, rank, world, raw_accum, raw_out, raw_frame)
-                acc_ptr, frame_ptr = raw_accum, raw_frame
-                tiny = torch.zeros(1, device=dev)
-                exchange_note = "fused peer-memory reduce-scatter -> tonemap -> gather (ptb_resolve_peers over CUDA IPC / NVLink), 2 NCCL barriers"
+                exchange = parallel.PeerExchange(ctx, rank, world, n)   # plain cudaMalloc buffers: exportable through CUDA IPC
+                exchange_note = ("fused peer-memory reduce-scatter -> tonemap -> gather (ptb_resolve_peers_sync over CUDA IPC / NVLink), ordered by epoch "
+                                 "flags in peer memory (no NCCL call per step), double-buffered accumulators")
             except Exception as e:  # capability probe at set-up time, outside every timed region
                 print(f"[rank {rank}] peer-memory exchange unavailable ({e}); using the NCCL reduce", file=sys.stderr)
                 exchange = None
@@ -247,32 +254,30 @@ def main():
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if int(flag.item()) == 0 and exchange is not None:
             exchange.close(); exchange = None
-            acc_ptr, frame_ptr = accum.data_ptr(), frame.data_ptr()
             exchange_note = "nccl reduce + ptb_resolve on rank 0 (a peer could not map the IPC handles)"
+    frame_ptr = exchange.out_frame if (exchange is not None and rank == 0) else frame.data_ptr()
+    result_accum_ptr = exchange.out_accum if (exchange is not None and rank == 0) else accum.data_ptr()
 
-    def zero_accum():
-        ctx.memset(acc_ptr, 0, n * 16, stream=stream)
-
-    def stream_barrier():
-        dist.all_reduce(tiny)
-
-    def one_step(step_index, cfg_used):
-        # a fresh 64-spp frame: the accumulator restarts (the reference resets subframe_index on camera change, cpp:267-278)
+    def one_step(cfg_used, frame_subframes, tiled=False):
+        """One frame of `frame_subframes` subframes over all ranks.  samples: rank r renders a contiguous block of them;
+        tiles: every rank renders all of them for ITS strips (the rest of its accumulator stays zero, so the same
+        sum-exchange doubles as the gather)."""
         if multi:
-            zero_accum()
-        # samples: rank r renders the contiguous block of subframes [r*8, r*8+8) of the 64*N-spp frame;
-        # tiles:   every rank renders subframes [0, 8) of ITS row band (the rest of its accumulator stays zero, so the
-        #          same sum-exchange doubles as the gather)
-        first = 0 if tiles else parallel.subframe_block_for_rank(rank, world, LAUNCHES_PER_STEP * world)[0]
+            acc_ptr = exchange.begin_step() if exchange is not None else accum.data_ptr()
+            ctx.memset(acc_ptr, 0, n * 16, stream=stream)
+            first = 0 if tiled else parallel.subframe_block_for_rank(rank, world, frame_subframes)[0]
+        else:
+            acc_ptr, first = accum.data_ptr(), 0   # a fresh frame: subframe 0 restarts the running average (cpp:267-278)
         p = ptb.make_params(W, H, subframe_index=first, dof=True, **CAMERAS[CAMERA])
-        p.accum_buffer, p.frame_buffer, p.handle = acc_ptr, frame_ptr, handle
-        ctx.launch(p, cfg_used, stream=stream)
+        p.accum_buffer, p.frame_buffer, p.handle = acc_ptr, (None if multi else frame_ptr), handle
+        if cfg_used.subframes_per_launch > 0:
+            ctx.launch(p, cfg_used, stream=stream)
         if multi and exchange is not None:
-            exchange.resolve(n, total_subframes, cfg_used, stream, stream_barrier)
+            exchange.resolve(frame_subframes, cfg_used, stream)
         elif multi:
             parallel.reduce_accumulator(accum, dst=0)
             if rank == 0:
-                ctx.resolve(acc_ptr, acc_ptr, frame_ptr, n, parallel.resolve_scale(total_subframes), cfg_used, stream=stream)
+                ctx.resolve(acc_ptr, acc_ptr, frame_ptr, n, parallel.resolve_scale(frame_subframes), cfg_used, stream=stream)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -280,54 +285,78 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    for s in range(args.warmup):
-        one_step(s, cfg)
-    sync_all()
-    ctx.totals(reset=True)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sync_all()
-    e0.record()
-    for s in range(args.steps):
-        one_step(s, cfg)
-    e1.record()
-    sync_all()
-    ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
-    tot = ctx.totals(reset=True)
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    segs = torch.tensor([float(tot["segments"])], dtype=torch.float64, device=dev)
-    if multi:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(segs, op=dist.ReduceOp.SUM)
-    ms_max, seg_total = float(t.item()), float(segs.item())
+    def timed(cfg_used, frame_subframes, steps, warmup, tiled=False, sample_clocks=False):
+        """W warm-up steps, then K steps between CUDA events on the launch stream; max over ranks; device-counted segments."""
+        for _ in range(warmup):
+            one_step(cfg_used, frame_subframes, tiled)
+        sync_all()
+        ctx.totals(reset=True)
+        sampler = ClockSampler(local_rank) if (sample_clocks and rank == 0) else None
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        e0.record()
+        for _ in range(steps):
+            one_step(cfg_used, frame_subframes, tiled)
+        e1.record()
+        sync_all()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if sampler else None
+        tot = ctx.totals(reset=True)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        segs = torch.tensor([float(tot["segments"])], dtype=torch.float64, device=dev)
+        if multi:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(segs, op=dist.ReduceOp.SUM)
+        return float(t.item()), float(segs.item()), clocks
+
+    # ---- headline: weak scaling (64 spp per GPU), arithmetic mode `arith` ----
+    total_subframes = LAUNCHES_PER_STEP * (1 if (tiles or not multi) else world)   # subframes in the frame all ranks produce together
+    cfg = make_cfg(arith, tiled=tiles)
+    ms_max, seg_total, clocks = timed(cfg, total_subframes, args.steps, args.warmup, tiled=tiles, sample_clocks=True)
     value = seg_total / (ms_max * 1e-3) / 1e6
-    gpu_launches = int(ctx.launch_stats().kernel_launches) * args.steps + (args.steps if multi and rank == 0 else 0)
+    gpu_launches = int(ctx.launch_stats().kernel_launches) * args.steps + (3 * args.steps if multi else 0)
+
+    # the other arithmetic mode, same workload, fewer steps: reported beside the headline
+    other_arith = None
+    if other is not None:
+        k_other = max(3, min(args.steps, 8))
+        oms, oseg, _ = timed(make_cfg(other, tiled=tiles), total_subframes, k_other, 2, tiled=tiles)
+        other_arith = {"arith": other, "value": oseg / (oms * 1e-3) / 1e6, "unit": "Msegments/s", "ms_per_step": oms / k_other, "steps": k_other,
+                       "note": ("bit-identical to the CPU oracle (tests/test_gpu_parity.py)" if other == "exact" else
+                                "FMA + MUFU in the shading code, gated by tests/test_gpu_fast_mode.py")}
+
+    # ---- strong scaling (N > 1): the SAME 64-spp frame split over the ranks, by samples and by tiles ----
+    strong = None
+    if multi and not args.no_strong:
+        strong = {"frame": f"{SPP_PER_LAUNCH * LAUNCHES_PER_STEP} spp of {W}x{H} in total, all ranks together", "arith": arith}
+        k_s = max(3, min(args.steps, 8))
+        mine = parallel.subframe_block_for_rank(rank, world, LAUNCHES_PER_STEP)
+        sms, sseg, _ = timed(make_cfg(arith, subframes=len(mine)), LAUNCHES_PER_STEP, k_s, 2)
+        strong["samples"] = {"ms_per_frame": sms / k_s, "value": sseg / (sms * 1e-3) / 1e6, "subframes_per_rank": -(-LAUNCHES_PER_STEP // world)}
+        tms, tseg, _ = timed(make_cfg(arith, tiled=True), LAUNCHES_PER_STEP, k_s, 2, tiled=True)
+        strong["tiles"] = {"ms_per_frame": tms / k_s, "value": tseg / (tms * 1e-3) / 1e6, "strip_rows": 16}
 
     # ---- roofline of the dominant kernel + stage shares (CUDA events inside ptb_launch, same stream) ----
-    # (1) the timed pipeline with profile_stages: for the fused pipeline "trace" is the one persistent kernel
-    def profiled(pipeline):
-        cfgp = ptb.default_render_cfg(spp_per_launch=SPP_PER_LAUNCH, max_depth=DEPTH, subframes_per_launch=LAUNCHES_PER_STEP,
-                                      pipeline=pipeline, accumulate_mode=cfg.accumulate_mode, write_frame=cfg.write_frame, profile_stages=1,
-                                      row_begin=band[0], row_end=band[1], **il)
+    def profiled(pipeline, mode):
+        cfgp = make_cfg(mode, tiled=tiles, pipeline=pipeline, profile_stages=1)
         acc = {k: 0.0 for k in ("raygen", "trace", "shade", "miss", "resolve", "total")}
         reps = max(1, min(args.steps, 3))
+        scratch_acc = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
         for _ in range(reps):
-            zero_accum()
-            first = 0 if tiles else parallel.subframe_block_for_rank(rank, world, LAUNCHES_PER_STEP * world)[0]
+            first = 0 if (tiles or not multi) else parallel.subframe_block_for_rank(rank, world, total_subframes)[0]
             pp = ptb.make_params(W, H, subframe_index=first, dof=True, **CAMERAS[CAMERA])
-            pp.accum_buffer, pp.frame_buffer, pp.handle = acc_ptr, frame_ptr, handle
+            pp.accum_buffer, pp.frame_buffer, pp.handle = scratch_acc.data_ptr(), (None if multi else frame.data_ptr()), handle
             ctx.launch(pp, cfgp, stream=stream)
             for kk, v in ctx.stage_ms().items():
                 acc[kk] += v / reps
         return acc
-    stage = profiled(args.pipeline)
-    # (2) per-stage split from the same stages run as separate kernels (pipeline 2); explains where the time goes
-    stage_split = profiled(2) if args.pipeline in (3, 4) else stage
+    stage = profiled(args.pipeline, arith)
+    # per-stage split from the same stages run as separate kernels (pipeline 2); explains where the time goes
+    stage_split = profiled(2, arith) if args.pipeline in (3, 4) else stage
     # traversal work per segment, from one instrumented launch of subframe 0
-    cfg_cnt = ptb.default_render_cfg(spp_per_launch=SPP_PER_LAUNCH, max_depth=DEPTH, write_frame=0, count_traversal=1, pipeline=args.pipeline)
+    cfg_cnt = ptb.default_render_cfg(spp_per_launch=SPP_PER_LAUNCH, max_depth=DEPTH, write_frame=0, count_traversal=1, pipeline=args.pipeline, arith_mode=ARITH[arith])
     p = ptb.make_params(W, H, subframe_index=0, dof=True, **CAMERAS[CAMERA])
     scratch = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
     p.accum_buffer, p.frame_buffer, p.handle = scratch.data_ptr(), frame.data_ptr(), handle
@@ -338,9 +367,10 @@ def main():
     hit_frac = lst.hits / max(lst.segments, 1)
     seg_per_step = seg_total / (args.steps * world)
     # Algorithmic bytes per segment:
-    #   traversal stage: list 4 + ray 32 read, hit record 16 + status 1 written, 64 B per node, 48 B per triangle
+    #   traversal stage: list 4 + ray 32 read, hit record 16 + status 1 written, node bytes per node visit, 48 B per triangle
     #   shade (per hit): 80 state read + 64 written + 120 attributes;  miss: 48 read + 64 env taps + 32 pixsum + 64 regenerated ray
-    trace_bytes_per_seg = 4 + 32 + 16 + 1 + 64.0 * nodes_per_seg + 48.0 * tris_per_seg
+    node_bytes = 128.0 if bst.bvh_width == 4 else 64.0
+    trace_bytes_per_seg = 4 + 32 + 16 + 1 + node_bytes * nodes_per_seg + 48.0 * tris_per_seg
     shade_bytes_per_seg = hit_frac * (80 + 64 + 120) + (1.0 - hit_frac) * (48 + 64 + 32 + 64)
     peak, peak_src = measured_peaks()
     l2_peak = ctx.microbench_read(32 << 20, 40)    # 32 MiB working set: L2 -> SM read bandwidth
@@ -353,22 +383,34 @@ def main():
         launches_k = SPP_PER_LAUNCH * (DEPTH + 1)
         bytes_per_seg = trace_bytes_per_seg
     achieved = bytes_per_seg * seg_per_step / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
-    traffic = None
-    tf = ROOT / "profiles" / "dominant_kernel_dram_bytes.json"
-    if tf.exists():
+    # what ncu measured for this kernel on this workload (profiles/r2_ncu_summary.json, written by tools/ncu_to_json.py from
+    # the --set full capture kept next to it): DRAM bytes per launch, issue-slot use, lanes per instruction, instruction count
+    ncu = {}
+    nf = ROOT / "profiles" / "r2_ncu_summary.json"
+    if nf.exists():
         try:
-            traffic = json.loads(tf.read_text()).get(kernel, {}).get("dram_bytes_per_launch")
+            ncu = json.loads(nf.read_text()).get(f"{args.config}:{arith}:pipeline{args.pipeline}", {})
         except Exception:
-            traffic = None
+            ncu = {}
+    traffic = ncu.get("dram_bytes_per_launch")
+    ncu_seg = ncu.get("segments_per_launch")
     roofline = {
-        "kernel": kernel, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": traffic, "peak_source": peak_src,
-        "l2_peak_gbs": l2_peak, "frac_of_l2_peak": achieved / l2_peak if l2_peak > 0 else None, "hbm_read_gbs_own_microbench": hbm_read,
+        "kernel": kernel, "arith": arith,
+        "bound": "latency/issue",
+        "bound_note": "no memory level is near its peak (see dram_frac, l2_frac): the kernel is bound by instruction issue and dependent-load latency "
+                      "at 8 warps per scheduler; `frac` below is ALGORITHMIC bytes over the HBM copy peak (SURVEY.md section 8d) -- most of those bytes "
+                      "are served by L1/L2, so it is not an HBM utilisation",
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+        "traffic": traffic,
+        "dram_frac": (traffic * (seg_per_step / ncu_seg) / (kernel_ms * 1e-3) / 1e9 / peak) if (traffic and ncu_seg and kernel_ms > 0) else None,
+        "l2_peak_gbs": l2_peak, "l2_frac": achieved / l2_peak if l2_peak > 0 else None, "hbm_read_gbs_own_microbench": hbm_read,
+        "issue_slot_util": ncu.get("issue_slot_util"), "lanes_per_inst": ncu.get("lanes_per_inst"),
+        "thread_inst_per_segment": ncu.get("thread_inst_per_segment"), "warp_inst_per_launch": ncu.get("warp_inst"),
+        "ncu_l2_throughput_pct": ncu.get("l2_throughput_pct"), "ncu_dram_throughput_pct": ncu.get("dram_throughput_pct"),
+        "ncu_stalls_per_issue": ncu.get("stalls_per_issue"), "ncu_source": ncu.get("source"),
         "algorithmic_bytes_per_segment": bytes_per_seg, "algorithmic_bytes_per_launch": bytes_per_seg * seg_per_step / launches_k,
         "avg_launch_ms": kernel_ms / launches_k, "launches_per_step": launches_k,
         "nodes_per_segment": nodes_per_seg, "tris_per_segment": tris_per_seg, "hit_fraction": hit_frac,
-        "note": "BVH (1.4 MB, huge primitives split off at the root) and textures (4 MB) are L2-resident and the fused kernel keeps a chunk's path state in L1/L2 between stages, "
-                "so most algorithmic bytes never reach HBM: ncu shows the kernels issue-bound (profiles/), the fraction is of the HBM copy peak",
         "share_of_step": kernel_ms / stage["total"] if stage["total"] > 0 else None,
         "stage_ms_per_step_separate_kernels": {k: v for k, v in stage_split.items()},
         "stage_share_separate_kernels": {k: (stage_split[k] / stage_split["total"] if stage_split["total"] > 0 else 0.0) for k in ("raygen", "trace", "shade", "miss", "resolve")},
@@ -381,26 +423,32 @@ def main():
     L = ptb.lib()
 
     def e2e_step():
-        L.ptb_copy_to_device(ctx._h, C.c_void_p(acc_ptr), C.c_void_p(h_accum.data_ptr()), C.c_size_t(n * 16), C.c_void_p(stream))
-        one_step(0, cfg)
+        # the frame's accumulator goes up from the host (the reference keeps it on the device across launches; a host
+        # caller of the C ABI owns it), the step renders, accumulator + 8-bit frame come back
         if rank == 0:
-            res_ptr = exchange.out_accum if exchange is not None else acc_ptr
-            L.ptb_copy_to_host(ctx._h, C.c_void_p(h_accum.data_ptr()), C.c_void_p(res_ptr), C.c_size_t(n * 16), C.c_void_p(stream))
+            L.ptb_copy_to_device(ctx._h, C.c_void_p(result_accum_ptr), C.c_void_p(h_accum.data_ptr()), C.c_size_t(n * 16), C.c_void_p(stream))
+        one_step(cfg, total_subframes, tiles)
+        if rank == 0:
+            L.ptb_copy_to_host(ctx._h, C.c_void_p(h_accum.data_ptr()), C.c_void_p(result_accum_ptr), C.c_size_t(n * 16), C.c_void_p(stream))
             L.ptb_copy_to_host(ctx._h, C.c_void_p(h_frame.data_ptr()), C.c_void_p(frame_ptr), C.c_size_t(n * 4), C.c_void_p(stream))
 
     e2e_step()
     sync_all()
+    ctx.totals(reset=True)
     t0 = time.perf_counter()
-    for s in range(args.steps):
+    for s_ in range(args.steps):
         e2e_step()
     sync_all()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    segs = torch.tensor([float(ctx.totals(reset=True)["segments"])], dtype=torch.float64, device=dev)
     if multi:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = seg_total / float(t.item()) / 1e6
+        dist.all_reduce(segs, op=dist.ReduceOp.SUM)
+    e2e_value = float(segs.item()) / float(t.item()) / 1e6
     e2e = {"value": e2e_value, "unit": "Msegments/s", "h2d_bytes_per_step": n * 16, "d2h_bytes_per_step": n * 16 + n * 4,
            "timing": "host wall clock around K steps incl. pinned h2d/d2h copies and a stream sync per step"}
+    timed_out = bool(exchange.timed_out(stream)) if exchange is not None else False
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -409,24 +457,34 @@ def main():
         cpu_baseline, _ = cpu_reference_sample(oh, ptb, osc, args.cpu_rows)
 
     if rank == 0:
+        pool_gb = min(LAUNCHES_PER_STEP * W * H * 97, 2 << 30) / 1e9
         line = {
             "metric": "Msegments/s", "value": value, "unit": "Msegments/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong" if tiles else "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "spp_per_step_per_gpu": SPP_PER_LAUNCH * LAUNCHES_PER_STEP, "split": ("tiles (16-row strips dealt round-robin)" if tiles else "samples") if multi else "none",
-                       "l2": "no flush: the path pool of one step is 8 x 1920 x 1080 slots x 97 B = 1.6 GB (> 126 MB L2) and is rewritten every iteration",
+            "config": {"workload": WORKLOAD, "arith_mode": arith,
+                       "arith_note": ("fast arithmetic: FMA contraction + MUFU rcp/sqrt/sin/cos in the shading code (the reference's own build is --use_fast_math); camera rays of the "
+                                      "pinhole model and all ray-triangle tests stay IEEE-exact; gate: tests/test_gpu_fast_mode.py (primary-hit IDs, image error bounds vs the CPU oracle)"
+                                      if arith == "fast" else "exact arithmetic: accumulation buffer and frame bit-identical to the CPU oracle (tests/test_gpu_parity.py)"),
+                       "spp_per_step_per_gpu": SPP_PER_LAUNCH * LAUNCHES_PER_STEP, "split": ("tiles (16-row strips dealt round-robin)" if tiles else "samples") if multi else "none",
+                       "l2": f"no flush: the path pool of one step is {pool_gb:.1f} GB of path state (> 126 MB L2) and is rewritten every wavefront iteration",
                        "pipeline": {1: "global queues", 2: "block-local wavefront, one kernel per stage and iteration", 3: "block-local wavefront, fused persistent kernel",
                                     4: "persistent path pool (blocks own positions, slots handed out from one counter)"}[args.pipeline],
                        "subframes_per_launch": LAUNCHES_PER_STEP,
                        "multi_gpu": ("scene replicated, subframes split by rank; exchange: " + exchange_note) if multi else "single GPU, reference accumulate mode",
-                       "bvh": {"triangles": bst.num_triangles, "nodes": bst.num_nodes, "max_depth": bst.max_depth, "sah": bst.sah_cost, "build_ms": bst.build_ms}},
+                       "bvh": {"triangles": bst.num_triangles, "nodes": bst.num_nodes, "max_depth": bst.max_depth, "width": bst.bvh_width, "sah": bst.sah_cost, "build_ms": bst.build_ms}},
             "spp_per_s_1080p": SPP_PER_LAUNCH * total_subframes * args.steps / (ms_max * 1e-3) * (W * H / (1920.0 * 1080.0)),
             "segments_per_step": seg_total / args.steps,
             "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "other_arith": other_arith, "strong": strong,
         }
+        if timed_out:
+            line["exchange_error"] = "a peer signal timed out (flag wait gave up after 4 s): numbers of this run are invalid"
         print(json.dumps(line))
     if exchange is not None:
         torch.cuda.synchronize()
+        if multi:
+            dist.barrier()
         exchange.close()
     if multi:
         dist.barrier()

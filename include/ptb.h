@@ -297,6 +297,24 @@ int ptb_resolve_peers(ptb_context* ctx, const ptb_float4* const* accums, int n_r
 int ptb_resolve_peers_accumulate(ptb_context* ctx, const ptb_float4* const* accums, int n_ranks, const ptb_float4* prev_accum,
                                  float prev_weight, ptb_float4* accum_out, ptb_uchar4* frame, uint32_t first_pixel,
                                  uint32_t n_pixels, float scale, const ptb_render_cfg* cfg, void* stream);
+/* ---- cross-rank ordering without NCCL (one process per GPU, e.g. under torchrun).  Every rank owns a flag block
+ *      (ptb_peer_flags_create; export it with ptb_ipc_export, map the peers' with ptb_ipc_open).  Epochs only grow.
+ *        ptb_peer_signal(kind 0)  stream-ordered "everything I enqueued so far (my rendering) is done": stores epoch into
+ *                                 arrive[my_rank] of EVERY rank's block (peer stores over NVLink);
+ *        ptb_resolve_peers_sync   ptb_resolve_peers_accumulate whose blocks first wait (on the device) until all n ranks have
+ *                                 signalled `epoch` in my_flags, and whose last block stores `epoch` into done[my_rank] of
+ *                                 the ROOT's block (root_flags, may be null);
+ *        ptb_peer_wait(kind 1)    on the root: device-side wait until done[r] >= epoch for all r: the frame is complete.
+ *      With double-buffered accumulators this is the only ordering a step needs.  A wait that sees no
+ *      signal for 4 s gives up and sets the block's error word (ptb_peer_flags_error) instead of hanging the GPU. */
+int ptb_peer_flags_create(ptb_context* ctx, uint32_t** flags);   /* release with ptb_device_free */
+int ptb_peer_signal(ptb_context* ctx, uint32_t* const* flag_blocks, int n_ranks, int my_rank, int kind, uint32_t epoch, void* stream);
+int ptb_peer_wait(ptb_context* ctx, uint32_t* my_flags, int kind, int n_ranks, uint32_t epoch, void* stream);
+int ptb_peer_flags_error(ptb_context* ctx, const uint32_t* flags, void* stream, int* timed_out);
+int ptb_resolve_peers_sync(ptb_context* ctx, const ptb_float4* const* accums, int n_ranks, int my_rank, uint32_t* my_flags,
+                           uint32_t* root_flags, uint32_t epoch, const ptb_float4* prev_accum, float prev_weight,
+                           ptb_float4* accum_out, ptb_uchar4* frame, uint32_t first_pixel, uint32_t n_pixels, float scale,
+                           const ptb_render_cfg* cfg, void* stream);
 /* CUDA IPC plumbing for the above (one process per GPU): export a cudaMalloc'ed buffer, open a peer's, close it */
 int ptb_ipc_export(ptb_context* ctx, const void* device_ptr, unsigned char handle[64]);
 int ptb_ipc_open(ptb_context* ctx, const unsigned char handle[64], void** device_ptr);

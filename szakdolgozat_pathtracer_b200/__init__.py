@@ -120,7 +120,7 @@ EXPORTS = [
     "ptb_scene_copy_triangles", "ptb_scene_copy_material_ids", "ptb_scene_get_material", "ptb_scene_copy_texture",
     "ptb_scene_env_size", "ptb_scene_copy_env", "ptb_default_build_cfg", "ptb_accel_build", "ptb_accel_read",
     "ptb_camera_uvw", "ptb_params_default_camera", "ptb_default_render_cfg", "ptb_launch", "ptb_launch_get_stats", "ptb_launch_get_stage_ms", "ptb_context_get_totals",
-    "ptb_resolve", "ptb_resolve_peers", "ptb_resolve_peers_accumulate", "ptb_multi_create", "ptb_multi_destroy", "ptb_multi_device_count", "ptb_multi_context", "ptb_multi_stream", "ptb_multi_accel_build", "ptb_multi_launch", "ptb_multi_synchronize", "ptb_multi_get_totals", "ptb_ipc_export", "ptb_ipc_open", "ptb_ipc_close", "ptb_trace_rays", "ptb_output_create", "ptb_output_resize", "ptb_output_map", "ptb_output_unmap",
+    "ptb_resolve", "ptb_resolve_peers", "ptb_resolve_peers_accumulate", "ptb_resolve_peers_sync", "ptb_peer_flags_create", "ptb_peer_signal", "ptb_peer_wait", "ptb_peer_flags_error", "ptb_multi_create", "ptb_multi_destroy", "ptb_multi_device_count", "ptb_multi_context", "ptb_multi_stream", "ptb_multi_accel_build", "ptb_multi_launch", "ptb_multi_synchronize", "ptb_multi_get_totals", "ptb_ipc_export", "ptb_ipc_open", "ptb_ipc_close", "ptb_trace_rays", "ptb_output_create", "ptb_output_resize", "ptb_output_map", "ptb_output_unmap",
     "ptb_output_host_ptr", "ptb_output_width", "ptb_output_height", "ptb_output_destroy", "ptb_device_alloc",
     "ptb_device_free", "ptb_device_memset", "ptb_copy_to_device", "ptb_copy_to_host", "ptb_image_load_rgba8",
     "ptb_image_load_float4", "ptb_save_image", "ptb_save_accum_raw", "ptb_load_accum_raw", "ptb_free", "ptb_obj_read", "ptb_microbench_read", "ptb_test_env_sample", "ptb_test_device_math",
@@ -377,6 +377,32 @@ class Context:
         arr = (C.c_void_p * len(accum_ptrs))(*accum_ptrs)
         _check(lib().ptb_resolve_peers(self._h, arr, len(accum_ptrs), C.c_void_p(accum_out_ptr), C.c_void_p(frame_ptr), C.c_uint32(first_pixel),
                                        C.c_uint32(n_pixels), C.c_float(scale), C.byref(cfg) if cfg is not None else None, C.c_void_p(stream)))
+
+    def peer_flags_create(self) -> int:
+        p = C.c_void_p()
+        _check(lib().ptb_peer_flags_create(self._h, C.byref(p)))
+        return p.value
+
+    def peer_signal(self, flag_blocks, my_rank, kind, epoch, stream=0):
+        arr = (C.c_void_p * len(flag_blocks))(*flag_blocks)
+        _check(lib().ptb_peer_signal(self._h, arr, len(flag_blocks), int(my_rank), int(kind), C.c_uint32(epoch), C.c_void_p(stream)))
+
+    def peer_wait(self, my_flags, kind, n_ranks, epoch, stream=0):
+        _check(lib().ptb_peer_wait(self._h, C.c_void_p(my_flags), int(kind), int(n_ranks), C.c_uint32(epoch), C.c_void_p(stream)))
+
+    def peer_flags_error(self, flags, stream=0) -> bool:
+        e = C.c_int()
+        _check(lib().ptb_peer_flags_error(self._h, C.c_void_p(flags), C.c_void_p(stream), C.byref(e)))
+        return bool(e.value)
+
+    def resolve_peers_sync(self, accum_ptrs, my_rank, my_flags, root_flags, epoch, accum_out_ptr, frame_ptr, first_pixel, n_pixels, scale,
+                           cfg: RenderCfg | None = None, stream=0, prev_accum=0, prev_weight=0.0):
+        """ptb_resolve_peers_sync: waits on the device for all ranks' arrive signals, reduces + tonemaps this rank's slice, signals done."""
+        arr = (C.c_void_p * len(accum_ptrs))(*accum_ptrs)
+        _check(lib().ptb_resolve_peers_sync(self._h, arr, len(accum_ptrs), int(my_rank), C.c_void_p(my_flags), C.c_void_p(root_flags), C.c_uint32(epoch),
+                                            C.c_void_p(prev_accum), C.c_float(prev_weight), C.c_void_p(accum_out_ptr), C.c_void_p(frame_ptr),
+                                            C.c_uint32(first_pixel), C.c_uint32(n_pixels), C.c_float(scale), C.byref(cfg) if cfg is not None else None,
+                                            C.c_void_p(stream)))
 
     def ipc_export(self, ptr) -> bytes:
         h = (C.c_ubyte * 64)()

@@ -26,18 +26,26 @@
 
 namespace PTB_NS {
 
-#ifndef PTB_CHUNK_THREADS
-#define PTB_CHUNK_THREADS 256    // 8 slots per thread in the compaction step (measured on C2: 256 > 512 > 128)
+#ifndef PTB_CHUNK_THREADS        // threads per block.  Measured on C2 / C2 close camera / C5 (profiles/r2_experiments.md):
+#if PTB_FAST                     //   exact build: 256 > 128 (25.2 vs 26.0 ms);  fast build: 128 > 256 > 64 (19.4 / 20.3 / 20.9 ms):
+#define PTB_CHUNK_THREADS 128    //   with the leaner shading code the stage barriers weigh more, and a barrier over 4 warps
+#else                            //   waits less than one over 8
+#define PTB_CHUNK_THREADS 256
+#endif
 #endif
 #ifndef PTB_CHUNK_SPT
 #define PTB_CHUNK_SPT 8          // default slots per thread (1, 2, 4, 8 or 16)
 #endif
 #define PTB_CHUNK (PTB_CHUNK_THREADS * PTB_CHUNK_SPT)  // slots per block at the default SPT
 #ifndef PTB_SHADE_DYNAMIC
-#define PTB_SHADE_DYNAMIC 0      // 1: the shade + miss stage hands out its list in warp-sized batches (see chunk_stage_shade_miss)
-#endif
-#ifndef PTB_STATUS_SMEM
-#define PTB_STATUS_SMEM 0        // 1: the fused kernel keeps its chunk's status bytes in shared memory
+#define PTB_SHADE_DYNAMIC 1      // 1: the shade + miss stage hands out its list in warp-sized batches (see chunk_stage_shade_miss):
+#endif                           //    +1.4 % exact, +2..3 % fast
+#ifndef PTB_TRACE_TWO_LISTS
+#define PTB_TRACE_TWO_LISTS 1    // 1: the fused kernel lists bounce rays and freshly started camera rays separately, so that warps
+#endif                           // of the trace stage mostly hold rays of one kind (camera rays of neighbouring pixels are coherent):
+                                 // +2.6 % on C2 (both builds), +3..5 % on the close cameras and C5
+#ifndef PTB_STATUS_SMEM          // 1: the fused kernel keeps its chunk's status bytes in shared memory: +1 % at 256 threads per block,
+#define PTB_STATUS_SMEM (!PTB_FAST)  // -1.7 % at 128 (eight blocks' worth of shared memory takes the next L1 carve-out step)
 #endif
 #ifndef PTB_MINB_WIDE
 #define PTB_MINB_WIDE 8          // fused kernel, launches that fill the chip: resident 128-thread units per SM the register
@@ -46,7 +54,7 @@ namespace PTB_NS {
 // smaller chunks for small launches (a 600 x 400 frame has 117 chunks of 2048 slots -- less than one block per SM -- but
 // 938 chunks of 256), everything else uses the default through the aliases below.
 
-enum SlotStatus : unsigned char { ST_DONE = 0, ST_TRACE = 1, ST_HIT = 2, ST_MISS = 3 };
+enum SlotStatus : unsigned char { ST_DONE = 0, ST_TRACE = 1, ST_HIT = 2, ST_MISS = 3, ST_TRACE_NEW = 4 };  // _NEW: a fresh camera ray (fused kernel only)
 
 template <int SPT = PTB_CHUNK_SPT>
 struct ChunkSharedT {
@@ -159,7 +167,8 @@ PTB_DEV void chunk_build_two(ChunkSharedT<SPT>& sh, const unsigned char* __restr
 template <bool COUNT, int QUANTUM, int SPT>
 PTB_DEV void chunk_stage_trace(ChunkSharedT<SPT>& sh, const SceneView& s, const FrameView& f, const PathView& p,
                                unsigned char* __restrict__ status, uint32_t base, unsigned int n, bool first_iteration,
-                               TravCounters& tc, uint32_t sbase = 0) {
+                               TravCounters& tc, uint32_t sbase = 0, unsigned int n_front = 0xffffffffu) {
+    // the list is [0, n_front) at the front of sh.list and the remaining n - n_front entries at its back (chunk_build_two)
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
     int stack[PTB_BVH_STACK];
@@ -180,7 +189,7 @@ PTB_DEV void chunk_stage_trace(ChunkSharedT<SPT>& sh, const SceneView& s, const 
                 b0 = __shfl_sync(0xffffffffu, b0, leader);
                 const unsigned int idx = b0 + (unsigned int)__popc(need & lt_mask);
                 if (!have && idx < n) {
-                    slot = base + sh.list[idx];
+                    slot = base + sh.list[idx < n_front ? idx : ChunkSharedT<SPT>::CHUNK - n + idx];
                     const float4 o4 = ldp(&p.ray_o[slot]), d4 = ldp(&p.ray_d[slot]);
                     trav_begin(t, stack, mk3(o4), mk3(d4), f.tmin, f.tmax);
                     have = true;
@@ -245,7 +254,7 @@ PTB_DEV void chunk_stage_miss(ChunkSharedT<SPT>& sh, const SceneView& s, const F
 template <int SPT>
 PTB_DEV void chunk_stage_shade_miss(ChunkSharedT<SPT>& sh, const SceneView& s, const FrameView& f, const PathView& p,
                                     unsigned char* __restrict__ status, uint32_t base, unsigned int n_hit, unsigned int n_miss,
-                                    uint32_t sbase = 0) {
+                                    uint32_t sbase = 0, bool mark_new = false) {
     const unsigned int total = n_hit + n_miss;
 #if PTB_SHADE_DYNAMIC
     // warps take 32 consecutive items at a time from the list cursor (reset by chunk_build_two): a warp that drew cheap items
@@ -278,7 +287,8 @@ PTB_DEV void chunk_stage_shade_miss(ChunkSharedT<SPT>& sh, const SceneView& s, c
             b.origin = mk3(0.0f); b.direction = mk3(0.0f);
             b.done = 1;
         }
-        status[slot - sbase] = after_segment(f, p, slot, b, mi.x, (int)mi.y, mi.z) ? ST_TRACE : ST_DONE;
+        const int next = after_segment(f, p, slot, b, mi.x, (int)mi.y, mi.z);
+        status[slot - sbase] = next == 0 ? ST_DONE : (next == 2 && mark_new ? ST_TRACE_NEW : ST_TRACE);
     }
 }
 
@@ -371,14 +381,18 @@ __global__ void __launch_bounds__(PTB_CHUNK_THREADS, (MINB * 128 + PTB_CHUNK_THR
 #endif
     for (unsigned int phase = 0;; phase ^= 1u) {
         unsigned int na, nb;
+#if PTB_TRACE_TWO_LISTS
+        chunk_build_two(sh, stp_, base - sbase, sn, phase ? ST_HIT : ST_TRACE, phase ? ST_MISS : ST_TRACE_NEW, &na, &nb);
+#else
         chunk_build_two(sh, stp_, base - sbase, sn, phase ? ST_HIT : ST_TRACE, phase ? ST_MISS : (unsigned char)0xff, &na, &nb);
+#endif
         if (phase == 0u) {
-            if (na == 0u) break;  // every pixel of the chunk has finished its samples
-            if (threadIdx.x == 0) sh.count[0] += na;
-            chunk_stage_trace<COUNT, QUANTUM>(sh, s, f, p, stp_, base, na, iter == 0, tc, sbase);
+            if (na + nb == 0u) break;  // every pixel of the chunk has finished its samples
+            if (threadIdx.x == 0) sh.count[0] += na + nb;
+            chunk_stage_trace<COUNT, QUANTUM>(sh, s, f, p, stp_, base, na + nb, iter == 0, tc, sbase, na);
             ++iter;
         } else {
-            chunk_stage_shade_miss(sh, s, f, p, stp_, base, na, nb, sbase);
+            chunk_stage_shade_miss(sh, s, f, p, stp_, base, na, nb, sbase, PTB_TRACE_TWO_LISTS != 0);
         }
         __syncthreads();  // status / hit records of this chunk are block-visible from here on
     }

@@ -429,9 +429,9 @@ PTB_DEV void closest_hit(const SceneView& s, const FrameView& f, int prim_idx, f
     io.seed = seed;
 }
 
-// Raygen side after a segment (cu:376-395) plus path regeneration.  Returns true
-// when the slot has another ray to trace.
-PTB_DEV bool after_segment(const FrameView& f, const PathView& p, uint32_t slot, const Bounce& b, uint32_t seed_rg,
+// Raygen side after a segment (cu:376-395) plus path regeneration.  Returns 0 when the slot has finished its samples,
+// 1 when it continues with a bounce ray, 2 when it starts the camera ray of its next sample.
+PTB_DEV int after_segment(const FrameView& f, const PathView& p, uint32_t slot, const Bounce& b, uint32_t seed_rg,
                            int depth, uint32_t sample) {
     const float pr = fmaxf(b.atten.x, fmaxf(b.atten.y, b.atten.z));
     bool done = b.done != 0;
@@ -441,7 +441,7 @@ PTB_DEV bool after_segment(const FrameView& f, const PathView& p, uint32_t slot,
         stp(&p.ray_d[slot], make_float4(b.direction.x, b.direction.y, b.direction.z, 0.0f));
         stp(&p.atten_seed[slot], make_float4(b.atten.x, b.atten.y, b.atten.z, __uint_as_float(b.seed)));
         stp(&p.misc[slot], make_uint4(seed_rg, (uint32_t)(depth - 1), sample, 0u));
-        return true;
+        return 1;
     }
     // cu:384-387; a path with done && !(p > 0) loops forever in the reference: it contributes 0 here
     const float3 path_rgb = pr > 0.0f ? b.radiance / pr : mk3(0.0f);
@@ -449,7 +449,7 @@ PTB_DEV bool after_segment(const FrameView& f, const PathView& p, uint32_t slot,
     sum.x = sum.x + path_rgb.x; sum.y = sum.y + path_rgb.y; sum.z = sum.z + path_rgb.z;
     stp(&p.pixsum[slot], sum);
     sample += 1u;
-    if (sample >= (uint32_t)f.spp) return false;
+    if (sample >= (uint32_t)f.spp) return 0;
     float3 o, d;
     const uint32_t pix = fd_mod(slot, f.div_pixels);
     const uint32_t prow = fd_div(pix, f.div_w);
@@ -458,7 +458,7 @@ PTB_DEV bool after_segment(const FrameView& f, const PathView& p, uint32_t slot,
     stp(&p.ray_d[slot], make_float4(d.x, d.y, d.z, 0.0f));
     stp(&p.atten_seed[slot], make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(seed_rg)));
     stp(&p.misc[slot], make_uint4(seed_rg, (uint32_t)f.max_depth, sample, 0u));
-    return true;
+    return 2;
 }
 
 #if !PTB_FAST  // the global-queue pipeline, the display transform and the self tests exist in the exact build only
@@ -594,23 +594,73 @@ __global__ void __launch_bounds__(256) k_resolve_scaled(const float4* __restrict
     if (frame) frame[i] = display_color(c, exposure_scale, inv_gamma, contrast);
 }
 
-// Fused reduce-scatter -> tonemap -> gather over peer memory: every rank runs this over ITS slice of the frame, reading
-// that slice from all ranks' accumulators (local HBM or NVLink peer loads) and storing the result where the root wants it.
 #define PTB_MAX_RANKS 16
 struct PeerAccums { const float4* a[PTB_MAX_RANKS]; int n; };
-// prev (optional, may alias accum_out): what the frame's accumulator holds from earlier launches, as a mean over prev_weight
-// subframes; it enters the sum first, weighted, so that a progressive render continues across launches.
-__global__ void __launch_bounds__(256) k_resolve_peers(PeerAccums peers, const float4* prev, float prev_weight, float4* accum_out,
+// ---- cross-rank ordering without NCCL: epoch flags in peer-mapped device memory ---------------------------------------
+// Every rank owns one flag block of PTB_FLAG_WORDS 32-bit words (cudaMalloc'ed, mapped by the peers through CUDA IPC or
+// peer access):  [0, 16) arrive[r] = last epoch rank r finished rendering,  [16, 32) done[r] = last epoch rank r's slice of
+// the frame landed in THIS rank's buffers (used on the root),  [32] error (a wait timed out),  [33] block counter.
+// Epochs only grow, so nothing is ever reset and a late reader cannot miss a signal.
+#define PTB_FLAG_WORDS 64
+#define PTB_FLAG_DONE 16
+#define PTB_FLAG_ERROR 32
+#define PTB_FLAG_COUNTER 33
+#define PTB_FLAG_TIMEOUT_NS 4000000000ull  // a peer that never arrives ends the wait with the error word set, not with a hang
+
+PTB_DEV unsigned long long global_timer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+PTB_DEV void flag_store_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+PTB_DEV uint32_t flag_load_sys(const uint32_t* p) { uint32_t v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+// spins until flags[k] >= epoch; false after PTB_FLAG_TIMEOUT_NS
+PTB_DEV bool flag_wait(const uint32_t* flags, int k, uint32_t epoch) {
+    const unsigned long long t0 = global_timer_ns();
+    while ((int32_t)(flag_load_sys(flags + k) - epoch) < 0) {
+        __nanosleep(200);
+        if (global_timer_ns() - t0 > PTB_FLAG_TIMEOUT_NS) return false;
+    }
+    return true;
+}
+
+struct PeerFlags { uint32_t* f[PTB_MAX_RANKS]; int n; };
+// rank `me` tells every rank that everything before this kernel in its stream (its rendering) is complete
+__global__ void k_peer_signal(PeerFlags peers, int me, int word0, uint32_t epoch) {
+    if ((int)threadIdx.x < peers.n) { __threadfence_system(); flag_store_sys(peers.f[threadIdx.x] + word0 + me, epoch); }
+}
+// waits until flags[word0 + r] >= epoch for r < n (root: every slice has landed)
+__global__ void k_peer_wait(uint32_t* flags, int word0, int n, uint32_t epoch) {
+    if ((int)threadIdx.x < n && !flag_wait(flags, word0 + (int)threadIdx.x, epoch)) flags[PTB_FLAG_ERROR] = 1u;
+}
+
+// Fused reduce-scatter -> accumulate -> tonemap -> gather over peer memory: every rank runs this over ITS slice of the frame,
+// reading that slice from all ranks' accumulators (local HBM or NVLink peer loads) and storing the result where the root
+// wants it.  prev (optional, may alias accum_out): what the frame's accumulator holds from earlier launches, as a mean over
+// prev_weight subframes; it enters the sum first, weighted, so that a progressive render continues across launches.
+// Optional ordering inside the kernel (my_flags != nullptr): every block first waits until all n ranks have signalled
+// `epoch` in my_flags (k_peer_signal), and the last block to finish stores `epoch` into root_done (the root's done[me]).
+struct PeerSync { uint32_t* my_flags; uint32_t* root_done; int n; uint32_t epoch; };
+__global__ void __launch_bounds__(256) k_resolve_peers(PeerAccums peers, PeerSync sync, const float4* prev, float prev_weight, float4* accum_out,
                                                        uchar4* __restrict__ frame, uint32_t first, uint32_t n, float scale,
                                                        float exposure_scale, float inv_gamma, float contrast) {
+    if (sync.my_flags) {
+        if ((int)threadIdx.x < sync.n && !flag_wait(sync.my_flags, (int)threadIdx.x, sync.epoch)) sync.my_flags[PTB_FLAG_ERROR] = 1u;
+        __syncthreads();
+    }
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t px = first + i;
-    float3 sum = prev ? mk3(prev[px]) * prev_weight : mk3(0.0f);
-    for (int k = 0; k < peers.n; ++k) sum = sum + mk3(peers.a[k][px]);  // fixed rank order: deterministic
-    const float3 c = sum * scale;
-    if (accum_out) accum_out[px] = make_float4(c.x, c.y, c.z, 1.0f);
-    if (frame) frame[px] = display_color(c, exposure_scale, inv_gamma, contrast);
+    if (i < n) {
+        const uint32_t px = first + i;
+        float3 sum = prev ? mk3(prev[px]) * prev_weight : mk3(0.0f);
+        for (int k = 0; k < peers.n; ++k) sum = sum + mk3(peers.a[k][px]);  // fixed rank order: deterministic
+        const float3 c = sum * scale;
+        if (accum_out) accum_out[px] = make_float4(c.x, c.y, c.z, 1.0f);
+        if (frame) frame[px] = display_color(c, exposure_scale, inv_gamma, contrast);
+    }
+    if (sync.root_done) {
+        __threadfence_system();   // this thread's stores to the root are visible system-wide before the counter moves
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned int prevc = atomicAdd(sync.my_flags + PTB_FLAG_COUNTER, 1u);
+            if (prevc == gridDim.x - 1u) { sync.my_flags[PTB_FLAG_COUNTER] = 0u; __threadfence_system(); flag_store_sys(sync.root_done, sync.epoch); }
+        }
+    }
 }
 
 // ---- batch ray query + device self tests ----------------------------------------------------------

@@ -670,16 +670,65 @@ int ptb_resolve_peers(ptb_context* ctx, const ptb_float4* const* accums, int n_r
 int ptb_resolve_peers_accumulate(ptb_context* ctx, const ptb_float4* const* accums, int n_ranks, const ptb_float4* prev_accum, float prev_weight,
                                  ptb_float4* accum_out, ptb_uchar4* frame, uint32_t first_pixel, uint32_t n_pixels, float scale,
                                  const ptb_render_cfg* cfg_in, void* stream_) {
+    return ptb_resolve_peers_sync(ctx, accums, n_ranks, 0, nullptr, nullptr, 0u, prev_accum, prev_weight, accum_out, frame, first_pixel, n_pixels, scale,
+                                  cfg_in, stream_);
+}
+
+int ptb_resolve_peers_sync(ptb_context* ctx, const ptb_float4* const* accums, int n_ranks, int my_rank, uint32_t* my_flags, uint32_t* root_flags,
+                           uint32_t epoch, const ptb_float4* prev_accum, float prev_weight, ptb_float4* accum_out, ptb_uchar4* frame,
+                           uint32_t first_pixel, uint32_t n_pixels, float scale, const ptb_render_cfg* cfg_in, void* stream_) {
     if (!ctx || !accums || n_ranks < 1 || n_ranks > PTB_MAX_RANKS) return fail(PTB_ERR_INVALID, "ptb_resolve_peers: bad arguments");
+    if (my_rank < 0 || my_rank >= n_ranks || (root_flags && !my_flags)) return fail(PTB_ERR_INVALID, "ptb_resolve_peers_sync: bad rank / flag blocks");
     ptb_render_cfg cfg;
     if (cfg_in) cfg = *cfg_in; else ptb_default_render_cfg(&cfg);
     PeerAccums pa;
     pa.n = n_ranks;
     for (int k = 0; k < n_ranks; ++k) { if (!accums[k]) return fail(PTB_ERR_INVALID, "ptb_resolve_peers: null accumulator"); pa.a[k] = (const float4*)accums[k]; }
+    PeerSync sy;
+    sy.my_flags = my_flags; sy.root_done = root_flags ? root_flags + PTB_FLAG_DONE + my_rank : nullptr; sy.n = n_ranks; sy.epoch = epoch;
     CU(cudaSetDevice(ctx->device));
-    if (n_pixels) k_resolve_peers<<<(n_pixels + 255u) / 256u, 256, 0, (cudaStream_t)stream_>>>(pa, (const float4*)prev_accum, prev_weight, (float4*)accum_out, (uchar4*)frame, first_pixel, n_pixels,
+    // with a done signal the kernel must run even for an empty slice (one block: the signal itself)
+    const uint32_t blocks = n_pixels ? (n_pixels + 255u) / 256u : (root_flags ? 1u : 0u);
+    if (blocks) k_resolve_peers<<<blocks, 256, 0, (cudaStream_t)stream_>>>(pa, sy, (const float4*)prev_accum, prev_weight, (float4*)accum_out, (uchar4*)frame, first_pixel, n_pixels,
                                                                                                 scale, exp2f(cfg.exposure), 1.0f / cfg.gamma, cfg.contrast);
     CU(cudaGetLastError());
+    return PTB_OK;
+}
+
+int ptb_peer_signal(ptb_context* ctx, uint32_t* const* flag_blocks, int n_ranks, int my_rank, int kind, uint32_t epoch, void* stream_) {
+    if (!ctx || !flag_blocks || n_ranks < 1 || n_ranks > PTB_MAX_RANKS || my_rank < 0 || my_rank >= n_ranks || (kind != 0 && kind != 1))
+        return fail(PTB_ERR_INVALID, "ptb_peer_signal: bad arguments");
+    PeerFlags pf; pf.n = n_ranks;
+    for (int k = 0; k < n_ranks; ++k) { if (!flag_blocks[k]) return fail(PTB_ERR_INVALID, "ptb_peer_signal: null flag block"); pf.f[k] = flag_blocks[k]; }
+    CU(cudaSetDevice(ctx->device));
+    k_peer_signal<<<1, 32, 0, (cudaStream_t)stream_>>>(pf, my_rank, kind ? PTB_FLAG_DONE : 0, epoch);
+    CU(cudaGetLastError());
+    return PTB_OK;
+}
+
+int ptb_peer_wait(ptb_context* ctx, uint32_t* my_flags, int kind, int n_ranks, uint32_t epoch, void* stream_) {
+    if (!ctx || !my_flags || n_ranks < 1 || n_ranks > PTB_MAX_RANKS || (kind != 0 && kind != 1)) return fail(PTB_ERR_INVALID, "ptb_peer_wait: bad arguments");
+    CU(cudaSetDevice(ctx->device));
+    k_peer_wait<<<1, 32, 0, (cudaStream_t)stream_>>>(my_flags, kind ? PTB_FLAG_DONE : 0, n_ranks, epoch);
+    CU(cudaGetLastError());
+    return PTB_OK;
+}
+
+int ptb_peer_flags_create(ptb_context* ctx, uint32_t** flags) {
+    if (!ctx || !flags) return fail(PTB_ERR_INVALID, "ptb_peer_flags_create: bad arguments");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMalloc((void**)flags, PTB_FLAG_WORDS * sizeof(uint32_t)));
+    CU(cudaMemset(*flags, 0, PTB_FLAG_WORDS * sizeof(uint32_t)));
+    return PTB_OK;
+}
+
+int ptb_peer_flags_error(ptb_context* ctx, const uint32_t* flags, void* stream_, int* timed_out) {
+    if (!ctx || !flags || !timed_out) return fail(PTB_ERR_INVALID, "ptb_peer_flags_error: bad arguments");
+    CU(cudaSetDevice(ctx->device));
+    uint32_t w = 0;
+    CU(cudaMemcpyAsync(&w, flags + PTB_FLAG_ERROR, sizeof(w), cudaMemcpyDeviceToHost, (cudaStream_t)stream_));
+    CU(cudaStreamSynchronize((cudaStream_t)stream_));
+    *timed_out = w != 0;
     return PTB_OK;
 }
 

@@ -51,36 +51,64 @@ def pixel_slice_for_rank(rank: int, world: int, n_pixels: int) -> tuple[int, int
 
 
 class PeerExchange:
-    """One process per GPU: every rank exports its sum-mode accumulator (and the root its result buffers) through CUDA
-    IPC; resolve() then runs ptb_resolve_peers on this rank's slice.  NCCL is used only for two stream-ordered barriers."""
+    """One process per GPU (torchrun): the fused peer-memory exchange of a sample-split (or tile-split) frame, ordered by
+    epoch flags in peer-mapped device memory instead of NCCL barriers (include/ptb.h: ptb_peer_signal,
+    ptb_resolve_peers_sync, ptb_peer_wait).
 
-    def __init__(self, ctx, rank, world, accum_ptr, out_accum_ptr, out_frame_ptr):
+    Every rank owns TWO sum-mode accumulators (steps alternate between them) and one flag block; the root also owns the
+    result buffers.  All of it is exported through CUDA IPC once, at set-up (torch.distributed is used for that
+    all-gather only).  One step on rank r:
+        acc = begin_step()            the accumulator of this step (zero it, render into it)
+        resolve(...)                  signal "rendered" to every rank -> ONE kernel: wait for all ranks' signals, reduce
+                                      this rank's slice of the frame out of all accumulators (NVLink peer loads), tonemap,
+                                      store into the root's buffers, last block signals "slice landed" to the root
+                                      -> root only: device-side wait for all slices.
+    Why two accumulators are enough: rank r re-uses accumulator A two steps later, after its resolve of the step in between,
+    which waited for every peer's "rendered" signal of that step -- and a peer sends that only after its own resolve of
+    the earlier step (the one that read A) has finished, by stream order."""
+
+    def __init__(self, ctx, rank, world, n_pixels):
         import torch.distributed as dist
-        self.ctx, self.rank, self.world = ctx, rank, world
-        mine = dict(accum=ctx.ipc_export(accum_ptr))
+        self.ctx, self.rank, self.world, self.n_pixels = ctx, rank, world, n_pixels
+        self.epoch = 0
+        self.accum = [ctx.alloc(n_pixels * 16), ctx.alloc(n_pixels * 16)]
+        self.flags = ctx.peer_flags_create()
+        mine = dict(accum0=ctx.ipc_export(self.accum[0]), accum1=ctx.ipc_export(self.accum[1]), flags=ctx.ipc_export(self.flags))
+        self._owned = list(self.accum) + [self.flags]
         if rank == 0:
-            mine.update(out_accum=ctx.ipc_export(out_accum_ptr), out_frame=ctx.ipc_export(out_frame_ptr))
+            self.out_accum, self.out_frame = ctx.alloc(n_pixels * 16), ctx.alloc(n_pixels * 4)
+            self._owned += [self.out_accum, self.out_frame]
+            mine.update(out_accum=ctx.ipc_export(self.out_accum), out_frame=ctx.ipc_export(self.out_frame))
         gathered = [None] * world
         dist.all_gather_object(gathered, mine)
         self._opened = []
-        self.accums = []
-        for r in range(world):
-            if r == rank:
-                self.accums.append(accum_ptr)
-            else:
-                p = ctx.ipc_open(gathered[r]["accum"]); self._opened.append(p); self.accums.append(p)
-        if rank == 0:
-            self.out_accum, self.out_frame = out_accum_ptr, out_frame_ptr
-        else:
-            self.out_accum = ctx.ipc_open(gathered[0]["out_accum"]); self.out_frame = ctx.ipc_open(gathered[0]["out_frame"])
-            self._opened += [self.out_accum, self.out_frame]
 
-    def resolve(self, n_pixels, n_subframes, cfg, stream, barrier):
-        """barrier(): a stream-ordered cross-rank barrier (e.g. a 1-element NCCL all_reduce on `stream`)."""
-        barrier()  # every rank has finished rendering into its accumulator
-        first, count = pixel_slice_for_rank(self.rank, self.world, n_pixels)
-        self.ctx.resolve_peers(self.accums, self.out_accum, self.out_frame, first, count, resolve_scale(n_subframes), cfg, stream)
-        barrier()  # every slice has landed in the root's buffers
+        def opened(handle):
+            ptr = ctx.ipc_open(handle)
+            self._opened.append(ptr)
+            return ptr
+        self.accums = [[self.accum[b] if r == rank else opened(gathered[r][f"accum{b}"]) for r in range(world)] for b in (0, 1)]
+        self.flag_blocks = [self.flags if r == rank else opened(gathered[r]["flags"]) for r in range(world)]
+        if rank != 0:
+            self.out_accum, self.out_frame = opened(gathered[0]["out_accum"]), opened(gathered[0]["out_frame"])
+
+    def begin_step(self) -> int:
+        """Device pointer of the accumulator this step renders into."""
+        self.epoch += 1
+        return self.accum[self.epoch & 1]
+
+    def resolve(self, n_subframes, cfg, stream):
+        """After this step's rendering has been enqueued on `stream`."""
+        e = self.epoch
+        self.ctx.peer_signal(self.flag_blocks, self.rank, 0, e, stream)
+        first, count = pixel_slice_for_rank(self.rank, self.world, self.n_pixels)
+        self.ctx.resolve_peers_sync(self.accums[e & 1], self.rank, self.flags, self.flag_blocks[0], e, self.out_accum, self.out_frame,
+                                    first, count, resolve_scale(n_subframes), cfg, stream)
+        if self.rank == 0:
+            self.ctx.peer_wait(self.flags, 1, self.world, e, stream)
+
+    def timed_out(self, stream=0) -> bool:
+        return self.ctx.peer_flags_error(self.flags, stream)
 
     def close(self):
         for p in self._opened:
@@ -89,6 +117,12 @@ class PeerExchange:
             except Exception:
                 pass
         self._opened = []
+        for p in self._owned:
+            try:
+                self.ctx.free(p)
+            except Exception:
+                pass
+        self._owned = []
 
 
 def row_band_for_rank(rank: int, world: int, height: int) -> tuple[int, int]:

@@ -110,3 +110,53 @@ def test_multi_argument_errors(ptb, assets):
         m.root.free(d)
     finally:
         m.close()
+
+
+def test_peer_flags_order_the_exchange_without_nccl(ptb, ctx):
+    """ptb_peer_signal / ptb_resolve_peers_sync / ptb_peer_wait with three 'ranks' on one device, each on its own stream: the
+    resolve kernels wait on the device for all signals, the root's wait sees all three slices; same result as the plain
+    kernel.  Then a wait for an epoch nobody signals: it must give up (error word set) instead of hanging."""
+    import torch
+    from szakdolgozat_pathtracer_b200 import parallel
+    rng = np.random.default_rng(11)
+    n, world = 5000, 3
+    accs = [(rng.random((n, 4), dtype=np.float32) * 2).astype(np.float32) for _ in range(world)]
+    ptrs = [ctx.alloc(n * 16) for _ in range(world)]
+    flags = [ctx.peer_flags_create() for _ in range(world)]
+    d_out, d_frame, d_out2, d_frame2 = ctx.alloc(n * 16), ctx.alloc(n * 4), ctx.alloc(n * 16), ctx.alloc(n * 4)
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    try:
+        for pp, a in zip(ptrs, accs):
+            ctx.to_device(pp, a)
+        ctx.memset(d_out, 0, n * 16); ctx.memset(d_frame, 0, n * 4)
+        ctx.synchronize()
+        for epoch in (1, 2):   # twice: epochs only grow, nothing is reset in between
+            for r in (2, 0, 1):   # resolves are enqueued BEFORE some of the signals they wait for
+                first, cnt = parallel.pixel_slice_for_rank(r, world, n)
+                if r == 2:
+                    ctx.peer_signal(flags, r, 0, epoch, stream=streams[r].cuda_stream)
+                    ctx.resolve_peers_sync(ptrs, r, flags[r], flags[0], epoch, d_out, d_frame, first, cnt, 1.0 / 3.0, stream=streams[r].cuda_stream)
+                else:
+                    ctx.resolve_peers_sync(ptrs, r, flags[r], flags[0], epoch, d_out, d_frame, first, cnt, 1.0 / 3.0, stream=streams[r].cuda_stream)
+            for r in (0, 1):
+                # a second stream per rank for the late signals (on the rank's own stream they would queue behind its waiting kernel)
+                s2 = torch.cuda.Stream()
+                ctx.peer_signal(flags, r, 0, epoch, stream=s2.cuda_stream)
+            ctx.peer_wait(flags[0], 1, world, epoch, stream=streams[0].cuda_stream)
+            streams[0].synchronize()
+            out = ctx.to_host(d_out, (n, 4), np.float32)
+            frame = ctx.to_host(d_frame, (n, 4), np.uint8)
+            for r in range(world):
+                first, cnt = parallel.pixel_slice_for_rank(r, world, n)
+                ctx.resolve_peers(ptrs, d_out2, d_frame2, first, cnt, 1.0 / 3.0)
+            ctx.synchronize()
+            assert np.array_equal(out, ctx.to_host(d_out2, (n, 4), np.float32)) and np.array_equal(frame, ctx.to_host(d_frame2, (n, 4), np.uint8))
+            assert not ctx.peer_flags_error(flags[0])
+            ctx.memset(d_out, 0, n * 16)
+            torch.cuda.synchronize()
+        ctx.peer_wait(flags[1], 0, world, 99)   # nobody signals epoch 99
+        assert ctx.peer_flags_error(flags[1]), "a wait without a signal must time out and set the error word"
+    finally:
+        torch.cuda.synchronize()
+        for pp in ptrs + flags + [d_out, d_frame, d_out2, d_frame2]:
+            ctx.free(pp)
