@@ -130,7 +130,9 @@ int ptb_multi_launch(ptb_multi* m, const ptb_Params* params, const ptb_render_cf
     ptb_render_cfg cfg;
     if (cfg_in) cfg = *cfg_in; else ptb_default_render_cfg(&cfg);
     if (!m->handle[0]) return fail(PTB_ERR_INVALID, "ptb_multi_launch: no scene has been built (ptb_multi_accel_build)");
-    if (cfg.row_begin || cfg.row_end || cfg.row_interleave_count > 1) return fail(PTB_ERR_INVALID, "ptb_multi_launch: the row partition is chosen by the split mode");
+    // a row band (a crop of the frame) is the caller's business under the sample split; the tile split owns the row partition
+    if (cfg.row_interleave_count > 1 || (split == PTB_SPLIT_TILES && (cfg.row_begin || cfg.row_end)))
+        return fail(PTB_ERR_INVALID, "ptb_multi_launch: the row partition is chosen by the split mode");
     if (cfg.accumulate_mode != 0) return fail(PTB_ERR_INVALID, "ptb_multi_launch: accumulate_mode must be 0 (the running average of the reference)");
     const int K = cfg.subframes_per_launch < 1 ? 1 : cfg.subframes_per_launch;
     const int n = m->n;

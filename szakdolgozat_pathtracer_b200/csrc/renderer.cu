@@ -367,12 +367,30 @@ int ptb_launch(ptb_context* ctx, const ptb_Params* P, const ptb_render_cfg* cfg_
     CU(cudaSetDevice(ctx->device));
 
     const int n_sub = cfg.subframes_per_launch < 1 ? 1 : cfg.subframes_per_launch;
-    // The path pool is bounded: a launch whose n_sub * W * H slots would need more than max_pool_bytes of path state
+    uint32_t row0 = 0, rows = P->image_height;
+    if (cfg.row_begin != 0 || cfg.row_end != 0) {
+        if (cfg.row_begin < 0 || cfg.row_end <= cfg.row_begin || (uint32_t)cfg.row_end > P->image_height)
+            return fail(PTB_ERR_INVALID, "ptb_launch: bad row band");
+        row0 = (uint32_t)cfg.row_begin; rows = (uint32_t)(cfg.row_end - cfg.row_begin);
+    }
+    uint32_t il_n = 0, il_r = 0, il_h = 0;
+    if (cfg.row_interleave_count > 1) {
+        if (cfg.row_begin != 0 || cfg.row_end != 0 || cfg.row_interleave_index < 0 || cfg.row_interleave_index >= cfg.row_interleave_count ||
+            cfg.row_interleave_height < 1)
+            return fail(PTB_ERR_INVALID, "ptb_launch: bad row interleave");
+        il_n = (uint32_t)cfg.row_interleave_count; il_r = (uint32_t)cfg.row_interleave_index; il_h = (uint32_t)cfg.row_interleave_height;
+        const uint32_t strips = (P->image_height + il_h - 1u) / il_h;                 // strips in the frame
+        const uint32_t mine = strips > il_r ? (strips - il_r + il_n - 1u) / il_n : 0u;  // strips il_r, il_r + il_n, ...
+        rows = mine * il_h;                                                             // the last one may be padded
+        if (rows == 0) return PTB_OK;  // more ranks than strips: nothing to render
+    }
+    const uint32_t n_pixels = P->image_width * rows;
+    // The path pool is bounded: a launch whose n_sub * pixels slots would need more than max_pool_bytes of path state
     // (97 B per slot) is rendered as consecutive batches of subframes, each one wavefront -- bit-identical to the single
     // wavefront (and to n_sub separate launches); counters of the batches add up.
     {
         const uint64_t cap_bytes = cfg.max_pool_bytes > 0 ? (uint64_t)cfg.max_pool_bytes : (2ull << 30);
-        const uint64_t px = (uint64_t)P->image_width * P->image_height;   // an upper bound of the launch's pixels (bands render fewer)
+        const uint64_t px = n_pixels;   // pixels this launch renders (a band or a set of strips renders fewer than W * H)
         uint64_t max_sub = cap_bytes / (px * PTB_SLOT_BYTES);
         if (max_sub < 1) max_sub = 1;
         if ((uint64_t)n_sub > max_sub && cfg.pipeline != PTB_PIPELINE_POOL_FUSED) {
@@ -392,24 +410,6 @@ int ptb_launch(ptb_context* ctx, const ptb_Params* P, const ptb_render_cfg* cfg_
             return PTB_OK;
         }
     }
-    uint32_t row0 = 0, rows = P->image_height;
-    if (cfg.row_begin != 0 || cfg.row_end != 0) {
-        if (cfg.row_begin < 0 || cfg.row_end <= cfg.row_begin || (uint32_t)cfg.row_end > P->image_height)
-            return fail(PTB_ERR_INVALID, "ptb_launch: bad row band");
-        row0 = (uint32_t)cfg.row_begin; rows = (uint32_t)(cfg.row_end - cfg.row_begin);
-    }
-    uint32_t il_n = 0, il_r = 0, il_h = 0;
-    if (cfg.row_interleave_count > 1) {
-        if (cfg.row_begin != 0 || cfg.row_end != 0 || cfg.row_interleave_index < 0 || cfg.row_interleave_index >= cfg.row_interleave_count ||
-            cfg.row_interleave_height < 1)
-            return fail(PTB_ERR_INVALID, "ptb_launch: bad row interleave");
-        il_n = (uint32_t)cfg.row_interleave_count; il_r = (uint32_t)cfg.row_interleave_index; il_h = (uint32_t)cfg.row_interleave_height;
-        const uint32_t strips = (P->image_height + il_h - 1u) / il_h;                 // strips in the frame
-        const uint32_t mine = strips > il_r ? (strips - il_r + il_n - 1u) / il_n : 0u;  // strips il_r, il_r + il_n, ...
-        rows = mine * il_h;                                                             // the last one may be padded
-        if (rows == 0) return PTB_OK;  // more ranks than strips: nothing to render
-    }
-    const uint32_t n_pixels = P->image_width * rows;
     if ((uint64_t)n_pixels * (uint64_t)n_sub > 0x7fffffffull) return fail(PTB_ERR_INVALID, "ptb_launch: subframes_per_launch * pixels too large");
     const uint32_t slots = n_pixels * (uint32_t)n_sub;
     const uint32_t iters = (uint32_t)cfg.spp_per_launch * (uint32_t)(cfg.max_depth + 1);

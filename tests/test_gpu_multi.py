@@ -101,8 +101,9 @@ def test_multi_argument_errors(ptb, assets):
             m.launch(p, ptb.default_render_cfg(write_frame=0))
         sc = load_config(ptb, assets, "c1", small=True)
         m.accel_build(sc)
-        with pytest.raises(ptb.PtbError):   # the row partition belongs to the split mode
-            m.launch(p, ptb.default_render_cfg(write_frame=0, row_begin=0, row_end=8))
+        with pytest.raises(ptb.PtbError):   # the row partition belongs to the tile split
+            m.launch(p, ptb.default_render_cfg(write_frame=0, row_begin=0, row_end=8), ptb.PTB_SPLIT_TILES)
+        m.launch(p, ptb.default_render_cfg(write_frame=0, row_begin=0, row_end=8, spp_per_launch=1, max_depth=1))   # a crop under the sample split is fine
         with pytest.raises(ptb.PtbError):
             m.launch(p, ptb.default_render_cfg(write_frame=0), 7)
         m.launch(p, ptb.default_render_cfg(write_frame=0, spp_per_launch=1, max_depth=1))
