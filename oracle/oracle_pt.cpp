@@ -99,6 +99,18 @@ inline v3 random_in_unit_sphere(uint32_t& seed, const Ctx& c) {
     return p;
 }
 
+// sutil/vec_math.h refract(r, i, n, ior) (SDK 8, restated as in ref_shim/shim_all.h; the reference passes its `eta` as ior,
+// cu:846): returns the refracted direction, or 0 on total internal reflection.
+inline v3 refract_sdk(v3 i, v3 n, float ior) {
+    v3 nn = n;
+    float negNdotV = dot(i, nn);
+    float eta;
+    if (negNdotV > 0.0f) { eta = ior; nn = -n; negNdotV = -negNdotV; } else { eta = 1.0f / ior; }
+    const float k = 1.0f - eta * eta * (1.0f - negNdotV * negNdotV);
+    if (k < 0.0f) return mk3(0.0f);
+    return normalize(eta * i - (eta * negNdotV + sqrtf(k)) * nn);
+}
+
 // cu:266-277
 inline v3 tonemap(v3 x) {
     const float A = 0.15f, B = 0.50f, C = 0.10f, D = 0.20f, E = 0.02f, F = 0.30f;
@@ -212,7 +224,7 @@ inline v3 setMaterialProperty(const OrcTexture& tx, v3 fallback, float u, float 
 
 inline v3 attr3(const float* a, uint32_t idx) { const float* p = a + (size_t)idx * 4; return mk3(p[0], p[1], p[2]); }
 
-// cu:616-801, 858-871 (the transparent branch cu:803-856 is unreachable).
+// cu:616-871 (incl. the transparent branch cu:803-856, reachable only through HitGroupData.transparent).
 void closest_hit(const Ctx& c, uint32_t prim_idx, float b1, float b2, float t_hit, v3 ray_orig, v3 ray_dir, Payload& io) {
     const OrcScene& sc = *c.sc;
     const OrcMaterial& m = sc.mats[sc.mat_ids[prim_idx]];
@@ -314,6 +326,34 @@ void closest_hit(const Ctx& c, uint32_t prim_idx, float b1, float b2, float t_hi
         p.specular_bounce = 0;
     }
     v3 brdf = specular_probability * (brdf_specular / spdf) + (1.0f - specular_probability) * (diffuse_albedo / dpdf);
+
+    // cu:803-856: glass.  Never reached by the reference's own scenes (transparent is false everywhere it is set,
+    // optixSphere.cpp:562,581,663) but reachable through HitGroupData.transparent (optixSphere.cpp:1215).  Attenuation is
+    // left as it came in; one more draw picks reflection or refraction by Schlick's reflectance.
+    if (m.transparent_flag) {
+        float cos_theta_i = dot(normal, -ray_dir);
+        float eta = ior;
+        v3 N = normal;
+        if (cos_theta_i < 0.0f) { cos_theta_i = -cos_theta_i; N = -normal; eta = 1.0f / eta; }
+        float reflectance = Fresnel_Schlick_float(cos_theta_i, ior);
+        if (rnd(seed, c) < reflectance) {
+            // cu:834-841: the half vector is sampled again, from the SECOND pair (r1, r2), and moved into the frame of the
+            // shading normal (Onb::inverse_transform works in place); the results of both normalize() calls are discarded
+            v3 hv = GGX_importance_sample(r1, r2, alpha);
+            hv = Onb(normal).inverse_transform(hv);
+            p.direction = reflect(ray_dir, hv);
+            p.specular_bounce = 1;
+        } else {
+            v3 refract_dir = refract_sdk(ray_dir, N, eta);  // cu:846; normalize() result discarded (cu:847)
+            v3 rs = random_in_unit_sphere(seed, c);
+            p.direction = refract_dir + 0.8f * alpha * rs;
+            p.specular_bounce = 0;
+        }
+        p.origin = hit_pos;
+        p.seed = seed;
+        io = p;
+        return;
+    }
 
     if (length(brdf) >= 1e-10f) p.atten = p.atten * (brdf * IdotN);
     p.origin = hit_pos;

@@ -159,7 +159,6 @@ int ptb_scene_set_materials(ptb_scene* scene, const ptb_HitGroupData* mats, int 
         if (h.has_roughness_map && h.roughness_texture_data) texture_from_float4(m.tex[TEX_ROUGHNESS], h.roughness_texture_data, h.roughness_width, h.roughness_height);
         if (h.has_normal_map && h.normal_texture_data) texture_from_float4(m.tex[TEX_NORMAL], h.normal_texture_data, h.normal_width, h.normal_height);
         if (h.has_metallic_map && h.metallic_texture_data) texture_from_float4(m.tex[TEX_METALLIC], h.metallic_texture_data, h.metallic_width, h.metallic_height);
-        if (m.transparent) return fail(PTB_ERR_UNSUPPORTED, "transparent materials are unreachable in the reference (optixSphere.cu:803-856) and not implemented");
     }
     scene->mats.swap(table);
     scene->revision++;

@@ -300,6 +300,43 @@ PTB_DEV float3 GGX_importance_sample(float r1, float r2, float alpha) {
     return normalize(mk3(sinTheta * c, cosTheta, sinTheta * s));
 }
 
+// The glass branch of the closest hit (cu:803-856): reachable only through HitGroupData.transparent (optixSphere.cpp:1215;
+// every material the reference itself creates has transparent = false, optixSphere.cpp:562,581,663).  One more draw picks
+// reflection (about a half vector sampled again, from the second pair (r1, r2), and moved into the frame of the shading normal;
+// the reference discards the results of its normalize() calls, cu:836-841) or refraction (sutil refract() with the reference's eta as its
+// ior argument, cu:846, plus 0.8 * alpha * random_in_unit_sphere, cu:848).  The attenuation is left as it came in.
+// __noinline__: keeps registers and code of the hot path as they are.
+// Everything goes in and out BY VALUE: a reference to the caller's seed would pin that variable to local memory for the whole shader.
+struct GlassOut { float3 direction; uint32_t seed; };
+__device__ __noinline__ GlassOut glass_bounce(float3 normal, float3 ray_dir, float ior, float alpha, float r1, float r2, uint32_t seed) {
+    GlassOut out;
+    float cos_theta_i = dot(normal, -ray_dir);
+    float eta = ior;
+    float3 N = normal;
+    if (cos_theta_i < 0.0f) { cos_theta_i = -cos_theta_i; N = -normal; eta = ar_rcp(eta); }
+    const float reflectance = Fresnel_Schlick_float(cos_theta_i, ior);
+    if (myrnd(seed) < reflectance) {
+        const float3 hv = Onb(normal).inverse_transform(GGX_importance_sample(r1, r2, alpha));
+        out.direction = reflect(ray_dir, hv); out.seed = seed;
+        return out;
+    }
+    // sutil/vec_math.h refract(r, i, n, ior)
+    float3 nn = N;
+    float negNdotV = dot(ray_dir, nn);
+    float e2;
+    if (negNdotV > 0.0f) { e2 = eta; nn = -N; negNdotV = -negNdotV; } else { e2 = ar_rcp(eta); }
+    const float kk = 1.0f - e2 * e2 * (1.0f - negNdotV * negNdotV);
+    float3 refract_dir = mk3(0.0f);
+    if (!(kk < 0.0f)) refract_dir = normalize(e2 * ray_dir - (e2 * negNdotV + ar_sqrt(kk)) * nn);
+    float3 p;
+    do {
+        const float a = myrnd(seed), b = myrnd(seed), c = myrnd(seed);
+        p = 2.0f * mk3(a, b, c) - mk3(1.0f, 1.0f, 1.0f);
+    } while (p.x * p.x + p.y * p.y + p.z * p.z >= 1.0f);
+    out.direction = refract_dir + 0.8f * alpha * p; out.seed = seed;
+    return out;
+}
+
 // What closest hit / miss hand back to the raygen-side logic (Payload, optixSphere.h:33-45).
 struct Bounce {
     float3 atten, radiance, origin, direction;
@@ -307,7 +344,7 @@ struct Bounce {
     int done;
 };
 
-// __closesthit__radiance (cu:616-801, 858-871); the glass branch cu:803-856 is unreachable.
+// __closesthit__radiance (cu:616-871); the glass branch cu:803-856 lives in glass_bounce.
 PTB_DEV void closest_hit(const SceneView& s, const FrameView& f, int prim_idx, float b1, float b2, float t_hit,
                          float3 ray_orig, float3 ray_dir, int depth, Bounce& io) {
     const DevMaterial& m = s.mats[__ldg(s.mat_ids + prim_idx)];
@@ -424,6 +461,13 @@ PTB_DEV void closest_hit(const SceneView& s, const FrameView& f, int prim_idx, f
     const float3 brdf = specular_probability * (brdf_specular / spdf) + (1.0f - specular_probability) * (diffuse_albedo / dpdf);
 #endif
 
+    if (m.transparent) {  // cu:803-856; kept out of line: no scene of the reference reaches it (see glass_bounce)
+        const GlassOut g = glass_bounce(normal, ray_dir, ior, alpha, r1, r2, seed);
+        io.direction = g.direction;
+        io.origin = hit_pos;
+        io.seed = g.seed;
+        return;
+    }
     if (length(brdf) >= 1e-10f) io.atten = io.atten * (brdf * IdotN);
     io.origin = hit_pos;
     io.seed = seed;

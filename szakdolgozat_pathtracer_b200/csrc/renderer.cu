@@ -232,6 +232,7 @@ int ptb_accel_build(ptb_context* ctx, ptb_scene* scene, const ptb_build_cfg* cfg
         if (scene->devs[i]->owner == ctx || scene->devs[i]->owner == nullptr) { free_device_scene(scene->devs[i]); scene->devs.erase(scene->devs.begin() + i); }
         else ++i;
     }
+    CU(cudaSetDevice(ctx->device));  // freeing another device's stale upload switched the current device
     DeviceScene* d = new DeviceScene();
     d->device = ctx->device; d->revision = scene->revision; d->source = scene;
     const uint32_t n = (uint32_t)scene->tris.size();
@@ -274,7 +275,7 @@ int ptb_accel_build(ptb_context* ctx, ptb_scene* scene, const ptb_build_cfg* cfg
         DevMaterial& o = dm[i];
         memset(&o, 0, sizeof(o));
         for (int c = 0; c < 3; ++c) { o.emission[c] = m.emission_color[c]; o.diffuse[c] = m.diffuse_color[c]; o.specular[c] = m.specular[c]; }
-        o.roughness = m.roughness; o.metallic = m.metallic ? 1 : 0;
+        o.roughness = m.roughness; o.metallic = m.metallic ? 1 : 0; o.transparent = m.transparent ? 1 : 0;
         for (int k = 0; k < TEX_COUNT; ++k) {
             const Texture& t = m.tex[k];
             if (!t.has) continue;

@@ -14,7 +14,7 @@ struct DevMaterial {
     float emission[3], diffuse[3], specular[3];
     float roughness;
     int metallic;
-    int _pad;
+    int transparent;
 };
 
 struct SceneView {

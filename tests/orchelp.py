@@ -124,7 +124,7 @@ class OracleScene:
             om.specular[:] = [float(x) for x in m.get("specular", (0.5, 0.5, 0.5))]
             om.roughness_value = float(m.get("roughness", 0.4))
             om.metallic_flag = int(bool(m.get("metallic", False)))
-            om.transparent_flag = 0
+            om.transparent_flag = int(bool(m.get("transparent", False)))
         self.c = OrcScene()
         self.c.vertices, self.c.normals = self.vertices.ctypes.data, self.normals.ctypes.data
         self.c.texcoords, self.c.mat_ids = self.texcoords.ctypes.data, self.mat_ids.ctypes.data
@@ -138,7 +138,7 @@ class OracleScene:
         for i in range(scene.num_materials):
             mi = scene.material(i)
             m = dict(emission_color=list(mi.emission_color), diffuse_color=list(mi.diffuse_color), specular=list(mi.specular),
-                     roughness=mi.roughness, metallic=bool(mi.metallic))
+                     roughness=mi.roughness, metallic=bool(mi.metallic), transparent=bool(mi.transparent))
             for kind, key, has in ((0, "albedo", mi.has_albedo), (1, "roughness_map", mi.has_roughness),
                                    (2, "normal_map", mi.has_normal), (3, "metallic_map", mi.has_metallic)):
                 if has:

@@ -30,3 +30,17 @@ def random_rays(rng, n, lo, hi):
     d = tgt - o
     d /= np.linalg.norm(d, axis=1, keepdims=True)
     return o, d.astype(np.float32)
+
+
+def glass_demo_scene(ptb, assets):
+    """The reference's procedural scene (ground + three spheres) with a material table that makes the middle sphere GLASS
+    (HitGroupData.transparent, optixSphere.cu:803-856), the left one rough red and the right one metallic, under a small
+    synthetic environment: the scene of the glass-branch parity tests and of tests/golden/ref_glass_demo.npz."""
+    sc = ptb.Scene.demo()
+    sc.set_materials([dict(diffuse_color=(0.5, 0.5, 0.5), specular=(1, 1, 1), roughness=0.8),
+                      dict(diffuse_color=(0.9, 0.1, 0.1), specular=(1, 0, 0), roughness=0.3),
+                      dict(diffuse_color=(0.9, 0.95, 1.0), specular=(1, 1, 1), roughness=0.12, transparent=True),
+                      dict(diffuse_color=(0.8, 0.7, 0.3), specular=(1, 1, 1), roughness=0.25, metallic=True)])
+    env = assets.make_env(7, 256, 128).astype(np.float32)
+    sc.set_env_pixels(np.concatenate([env, np.ones_like(env[..., :1])], -1))
+    return sc

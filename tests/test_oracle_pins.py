@@ -183,6 +183,37 @@ def test_oracle_c3_matches_live_reference(ptb, oh, assets):
     assert np.array_equal(a1.view(np.uint32), a2.view(np.uint32))
 
 
+def _oracle_glass(ptb, oh, assets, which):
+    from scenes import glass_demo_scene
+    sc = glass_demo_scene(ptb, assets)
+    assert sc.material(2).transparent == 1
+    osc = oh.OracleScene.from_ptb(sc, guard=True)
+    p = ptb.make_params(96, 64, subframe_index=0, dof=True)
+    cfg = oh.default_config("oracle", sat_cuda=0) if which == "oracle" else oh.default_config("ref")
+    a, f, h, st, rc = oh.render(which, osc, oh.params_from_ptb(p), cfg)
+    assert rc == 0
+    return a, f, h, int(st.segments), sc
+
+
+def test_oracle_glass_branch_matches_reference_fixture(ptb, oh, assets):
+    """The transparent branch (optixSphere.cu:803-856: Schlick reflect / sutil refract + 0.8 alpha random_in_unit_sphere) against
+    buffers the reference's own code produced on the host (tools/make_golden.py)."""
+    g = np.load(ROOT / "tests" / "golden" / "ref_glass_demo.npz")
+    a, f, h, seg, sc = _oracle_glass(ptb, oh, assets, "oracle")
+    assert seg == int(g["segments"]) and np.array_equal(h, g["hits"]) and np.array_equal(f, g["frame"])
+    assert np.array_equal(a.view(np.uint32), g["accum"].view(np.uint32))
+    ids = sc.material_ids()
+    assert (ids[h[h >= 0]] == 2).mean() > 0.03   # the glass sphere is in frame
+
+
+def test_oracle_glass_branch_matches_live_reference(ptb, oh, assets):
+    if not oh.have_ref():
+        pytest.skip("oracle/_ref/libref_pt.so not built")
+    a1, f1, h1, s1, _ = _oracle_glass(ptb, oh, assets, "oracle")
+    a2, f2, h2, s2, _ = _oracle_glass(ptb, oh, assets, "ref")
+    assert s1 == s2 and np.array_equal(h1, h2) and np.array_equal(f1, f2) and np.array_equal(a1.view(np.uint32), a2.view(np.uint32))
+
+
 def test_det_pow_accuracy(oh):
     """det_powf (display transform) is the correctly rounded power on the exponents the reference uses."""
     L = oh.load("oracle")

@@ -216,8 +216,8 @@ def test_raw_scene_and_material_table(ptb):
     assert np.allclose(list(m.diffuse_color), (0.1, 0.2, 0.3)) and m.metallic == 1 and m.albedo_w == 6 and m.albedo_h == 4
     assert np.array_equal(sc.texture(0, 0), tex8)      # exactly byte/255 -> kept as RGBA8, widened identically
     assert np.array_equal(sc.texture(0, 1), texf)      # anything else stays float4
-    with pytest.raises(ptb.PtbError):
-        sc.set_materials([dict(transparent=True)])     # glass branch is unreachable in the reference; refused, not faked
+    sc.set_materials([dict(transparent=True)])         # HitGroupData.transparent (optixSphere.cpp:1215): the glass branch
+    assert sc.material(0).transparent == 1
     sc2 = ptb.Scene.from_triangles(tri, np.array([2], np.uint32))
     with pytest.raises(ptb.PtbError):
         sc2.set_materials([dict()])                    # material id beyond the table

@@ -7,6 +7,7 @@
   * ref_c2_crop.npz,       the same for a window of the C2 scene (monkey + albedo map, close camera) and of the C3 scene
     ref_c3_crop.npz        (suitcase with albedo/normal/roughness/metallic maps, close camera): the textured closest-hit
                            branches of optixSphere.cu:682-714
+  * ref_glass_demo.npz      the procedural scene with a transparent sphere: the glass branch of optixSphere.cu:803-856
 Needs /root/reference (oracle/_ref is built from it); the fixtures then travel to boxes that do not have it.
 """
 import hashlib
@@ -70,4 +71,14 @@ for name, c in CROPS.items():
     assert rc == 0
     np.savez_compressed(GOLD / f"ref_{name}_crop.npz", accum=accum[y0:y1, x0:x1], frame=frame[y0:y1, x0:x1], hits=hits[y0:y1, x0:x1],
                         segments=np.int64(st.segments), window=np.array(c["window"]), res=np.array(c["res"]))
+
+# the glass branch (optixSphere.cu:803-856): procedural scene with a transparent middle sphere, reference literals
+from scenes import glass_demo_scene
+sc = glass_demo_scene(ptb, make_assets)
+osc = oh.OracleScene.from_ptb(sc, guard=True)
+W, H = 96, 64
+p = ptb.make_params(W, H, subframe_index=0, dof=True)
+accum, frame, hits, st, rc = oh.render("ref", osc, oh.params_from_ptb(p), oh.default_config("ref"))
+assert rc == 0
+np.savez_compressed(GOLD / "ref_glass_demo.npz", accum=accum, frame=frame, hits=hits, segments=np.int64(st.segments))
 print("golden fixtures written to", GOLD)
