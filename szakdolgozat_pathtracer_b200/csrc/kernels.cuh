@@ -33,6 +33,11 @@ PTB_DEV float4 ldp(const float4* a) { return *a; }
 PTB_DEV uint4 ldp(const uint4* a) { return *a; }
 PTB_DEV void stp(float4* a, float4 v) { *a = v; }
 PTB_DEV void stp(uint4* a, uint4 v) { *a = v; }
+#elif defined(PTB_STATE_CACHE_CG)   // L2 only, normal eviction priority
+PTB_DEV float4 ldp(const float4* a) { return __ldcg(a); }
+PTB_DEV uint4 ldp(const uint4* a) { return __ldcg(a); }
+PTB_DEV void stp(float4* a, float4 v) { __stcg(a, v); }
+PTB_DEV void stp(uint4* a, uint4 v) { __stcg(a, v); }
 #else
 PTB_DEV float4 ldp(const float4* a) { return __ldcs(a); }
 PTB_DEV uint4 ldp(const uint4* a) { return __ldcs(a); }

