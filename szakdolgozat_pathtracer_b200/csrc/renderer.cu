@@ -81,6 +81,8 @@ struct ptb_context {
     float4 *shadow_o = nullptr, *shadow_d = nullptr, *shadow_c = nullptr; unsigned char* shadow_flag = nullptr; uint32_t shadow_slots = 0;
     int last_pipeline = 0;
     bool keep_launch_totals = false;  // set by ptb_launch while it renders the later batches of a bounded-pool launch
+    bool defer_fold = false;          // ... and while a later batch will fold the launch counters into the running totals
+    float stage_sum[6] = {0, 0, 0, 0, 0, 0}; bool stage_sum_valid = false;  // stage times of the last batched, profiled launch
     // last launch, for ptb_launch_get_stats
     cudaStream_t last_stream = nullptr;
     uint32_t last_iters = 0, last_kernels = 0;
@@ -396,18 +398,28 @@ int ptb_launch(ptb_context* ctx, const ptb_Params* P, const ptb_render_cfg* cfg_
         if (max_sub < 1) max_sub = 1;
         if ((uint64_t)n_sub > max_sub && cfg.pipeline != PTB_PIPELINE_POOL_FUSED) {
             uint32_t kernels = 0; uint64_t paths = 0;
+            float stage_sum[6] = {0, 0, 0, 0, 0, 0};
             for (int first = 0; first < n_sub; first += (int)max_sub) {
                 ptb_Params p2 = *P; p2.subframe_index = P->subframe_index + first;
                 ptb_render_cfg c2 = cfg;
                 c2.subframes_per_launch = n_sub - first < (int)max_sub ? n_sub - first : (int)max_sub;
                 if (first > 0) c2.aux_primary_hit = nullptr;   // primary hits are those of the launch's first subframe
-                ctx->keep_launch_totals = first > 0;
+                ctx->keep_launch_totals = first > 0;                        // later batches add to the first one's launch counters ...
+                ctx->defer_fold = first + (int)max_sub < n_sub;             // ... which are folded into the running totals once, by the last
                 const int rc = ptb_launch(ctx, &p2, &c2, stream_);
-                ctx->keep_launch_totals = false;
+                ctx->keep_launch_totals = false; ctx->defer_fold = false;
                 if (rc != PTB_OK) return rc;
                 kernels += ctx->last_kernels; paths += ctx->last_paths;
+                if (cfg.profile_stages) {  // stage times of a batched launch are the sums over its batches (synchronises: profiling only)
+                    float ms[6];
+                    ctx->stage_sum_valid = false;
+                    const int prc = ptb_launch_get_stage_ms(ctx, ms);
+                    if (prc != PTB_OK) return prc;
+                    for (int k = 0; k < 6; ++k) stage_sum[k] += ms[k];
+                }
             }
             ctx->last_kernels = kernels; ctx->last_paths = paths;
+            if (cfg.profile_stages) { for (int k = 0; k < 6; ++k) ctx->stage_sum[k] = stage_sum[k]; ctx->stage_sum_valid = true; }
             return PTB_OK;
         }
     }
@@ -478,6 +490,7 @@ int ptb_launch(ptb_context* ctx, const ptb_Params* P, const ptb_render_cfg* cfg_
         CU(cudaEventRecord(ctx->events[0], st));
     }
     ctx->prof_iters = 0;
+    ctx->stage_sum_valid = false;
     uint32_t launches = 0;
     uint32_t prof_iters = iters;
     if (cfg.env_importance_sampling) {
@@ -587,7 +600,7 @@ int ptb_launch(ptb_context* ctx, const ptb_Params* P, const ptb_render_cfg* cfg_
         }
     }
     k_resolve<<<(n_pixels + 255u) / 256u, 256, 0, st>>>(f, p);
-    k_fold_totals<<<1, 32, 0, st>>>(ctx->launch_totals, ctx->totals);
+    if (!ctx->defer_fold) k_fold_totals<<<1, 32, 0, st>>>(ctx->launch_totals, ctx->totals);
     launches += 2;
     if (prof) { CU(cudaEventRecord(ctx->events[2 + (size_t)prof_iters * 3], st)); ctx->prof_iters = prof_iters; }
     CU(cudaGetLastError());
@@ -632,6 +645,7 @@ int ptb_context_get_totals(ptb_context* ctx, uint64_t out[4], int reset) {
 
 int ptb_launch_get_stage_ms(ptb_context* ctx, float out[6]) {
     if (!ctx || !out) return fail(PTB_ERR_INVALID, "ptb_launch_get_stage_ms: bad arguments");
+    if (ctx->stage_sum_valid) { for (int i = 0; i < 6; ++i) out[i] = ctx->stage_sum[i]; return PTB_OK; }  // a batched launch: sums
     if (!ctx->prof_iters) return fail(PTB_ERR_INVALID, "ptb_launch_get_stage_ms: the last launch did not set profile_stages");
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->last_stream));

@@ -160,9 +160,12 @@ def test_bounded_pool_batches_bit_identical(ptb, ctx, assets):
             ctx.memset(d_accum, 0, n * 16); ctx.memset(d_hits, 0xFF, n * 4)
             p = ptb.make_params(W, H, subframe_index=3, dof=True, **CAMERAS["monkey_close"])
             p.accum_buffer, p.frame_buffer, p.handle = d_accum, d_frame, handle
+            ctx.totals(reset=True)
             ctx.launch(p, ptb.default_render_cfg(spp_per_launch=3, max_depth=6, subframes_per_launch=7, max_pool_bytes=cap, aux_primary_hit=d_hits,
                                                  count_traversal=1))
             st = ctx.launch_stats()
+            tot = ctx.totals(reset=True)
+            assert tot["segments"] == st.segments and tot["hits"] == st.hits and tot["launches"] == 1, (tot, st.segments)   # folded once
             res.append((ctx.to_host(d_accum, (H, W, 4), np.float32).view(np.uint32), ctx.to_host(d_frame, (H, W, 4), np.uint8),
                         ctx.to_host(d_hits, (H, W), np.int32), (st.segments, st.hits, st.misses, st.paths, st.nodes_visited, st.tris_tested)))
         finally:
