@@ -161,3 +161,43 @@ def test_peer_flags_order_the_exchange_without_nccl(ptb, ctx):
         torch.cuda.synchronize()
         for pp in ptrs + flags + [d_out, d_frame, d_out2, d_frame2]:
             ctx.free(pp)
+
+
+def test_c5_convergence_band_sample_split_tolerance(ptb, ctx, oh, assets):
+    """BASELINE config 5 in small: a band of the 4K frame of the C5 scene at 512 spp (8 subframes x 64), sample-split over 1, 2, 4
+    and 8 contexts.  Stated tolerance of the multi-GPU sum order against the single-GPU running average (tools/c5_convergence.py
+    runs the same check at 4096 spp over real GPUs, profiles/r2_c5_convergence.json: 2.3e-7 / 9e-7): relative RMSE <= 1e-6,
+    maximum relative error <= 1e-5.  N = 1 equals the oracle bit for bit."""
+    sc = load_config(ptb, assets, "c5")
+    W, H, rows0, rows1 = 3840, 2160, 1240, 1248
+    n = W * H
+    cfg_kw = dict(spp_per_launch=64, max_depth=8, subframes_per_launch=8, row_begin=rows0, row_end=rows1, write_frame=0)
+    accs = {}
+    for n_dev in (1, 2, 4, 8):
+        m = ptb.Multi([0] * n_dev)
+        try:
+            m.accel_build(sc)
+            d_a = m.root.alloc(n * 16)
+            m.root.memset(d_a, 0, n * 16); m.root.synchronize()
+            p = ptb.make_params(W, H, subframe_index=0, dof=True)
+            p.accum_buffer = d_a
+            m.launch(p, ptb.default_render_cfg(**cfg_kw), ptb.PTB_SPLIT_SAMPLES)
+            m.synchronize()
+            accs[n_dev] = m.root.to_host(d_a, (H, W, 4), np.float32)[rows0:rows1].copy()
+            m.root.free(d_a)
+        finally:
+            m.close()
+    ref = accs[1][..., :3].astype(np.float64)
+    for n_dev in (2, 4, 8):
+        d = accs[n_dev][..., :3] - ref
+        assert np.sqrt((d ** 2).mean()) / ref.mean() <= 1e-6, n_dev
+        assert (np.abs(d) / (np.abs(ref) + 1e-6)).max() <= 1e-5, n_dev
+    osc = oh.OracleScene.from_ptb(sc, guard=False)
+    win = (1900, 1242, 1932, 1246)
+    ca = np.zeros((H, W, 4), np.float32)
+    for sf in range(8):
+        p = ptb.make_params(W, H, subframe_index=sf, dof=True)
+        ca, _, _, _, rc = oh.render("oracle", osc, oh.params_from_ptb(p), oh.default_config("oracle", spp_per_launch=64, max_depth=8), accum=ca, window=win, want_hits=False)
+        assert rc == 0
+    g = accs[1][win[1] - rows0:win[3] - rows0, win[0]:win[2]]
+    assert np.array_equal(g[..., :3].view(np.uint32), ca[win[1]:win[3], win[0]:win[2], :3].view(np.uint32))
