@@ -193,7 +193,8 @@ typedef struct ptb_build_stats {
     float build_ms;        /* device time of the build (CUDA events) */
     uint64_t bvh_bytes;
     uint32_t bvh_width;    /* 2 or 4: the tree the traversal kernels walk (ptb_build_cfg.bvh_width = 0 picks by scene size) */
-    uint32_t _reserved;
+    float sah_cost_mesh;   /* sah_cost of the subtree beside the huge-primitive leaf under the root (the reference's floor quad
+                              spans the scene and dominates sah_cost), relative to that subtree's own box; = sah_cost without such a leaf */
 } ptb_build_stats;
 
 typedef struct ptb_material_info {

@@ -97,7 +97,7 @@ class BuildCfg(C.Structure):
 class BuildStats(C.Structure):
     _fields_ = [
         ("num_triangles", C.c_uint32), ("num_nodes", C.c_uint32), ("num_leaves", C.c_uint32), ("max_depth", C.c_uint32),
-        ("sah_cost", C.c_float), ("build_ms", C.c_float), ("bvh_bytes", C.c_uint64), ("bvh_width", C.c_uint32), ("_reserved", C.c_uint32),
+        ("sah_cost", C.c_float), ("build_ms", C.c_float), ("bvh_bytes", C.c_uint64), ("bvh_width", C.c_uint32), ("sah_cost_mesh", C.c_float),
     ]
 
 

@@ -579,6 +579,28 @@ bool build_bvh_impl(const float4* d_verts, uint32_t n, const ptb_build_cfg& cfg,
     const float root_area = dx * dy + dy * dz + dz * dx;
     stats.num_nodes = h_counters[0]; stats.num_leaves = h_counters[1]; stats.max_depth = h_counters[2];
     stats.sah_cost = root_area > 0.0f ? h_sah / root_area : 0.0f;
+    // The same statistic without the huge-primitive leaf under the root (the floor quad dominates sah_cost: its box IS the
+    // scene's): cost of the OTHER child's subtree relative to that child's own box.  Equal to sah_cost when the root has no leaf child.
+    stats.sah_cost_mesh = stats.sah_cost;
+    {
+        float h_root[16];
+        CK(cudaMemcpyAsync(h_root, d_nodes, 64, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        int codes[2]; memcpy(codes, h_root + 12, 8);
+        auto half_area_of = [&](int c) {
+            const float lx = c ? h_root[4] : h_root[0], hx = c ? h_root[5] : h_root[1], ly = c ? h_root[6] : h_root[2], hy = c ? h_root[7] : h_root[3];
+            const float lz = c ? h_root[10] : h_root[8], hz = c ? h_root[11] : h_root[9];
+            const float ex = hx - lx, ey = hy - ly, ez = hz - lz;
+            return ex * ey + ey * ez + ez * ex;
+        };
+        for (int c = 0; c < 2; ++c) {
+            if (codes[c] < 0 && codes[1 - c] >= 0) {
+                const float a_leaf = half_area_of(c), a_mesh = half_area_of(1 - c);
+                const float cnt = (float)(((~codes[c]) & 7) + 1);
+                if (a_mesh > 0.0f) stats.sah_cost_mesh = (h_sah - root_area - a_leaf * cnt) / a_mesh;
+            }
+        }
+    }
     stats.build_ms = ms;
     stats.bvh_bytes = (uint64_t)n_nodes * 64 + (uint64_t)n * 48 + (out.nodes4 ? (uint64_t)n_nodes * 128 : 0);
     // the 4-wide traversal pushes up to three entries per level of the collapsed tree (half the 2-wide depth)

@@ -16,9 +16,13 @@
 
 namespace ptb {
 
+#ifndef PTB_TREELET_MAX
 #define PTB_TREELET_MAX 256
+#endif
 #define PTB_SAH_BINS 16
-#define PTB_REFINE_WARPS 2
+#ifndef PTB_REFINE_WARPS
+#define PTB_REFINE_WARPS 2   // warps (= treelets in flight) per block; the shared-memory footprint is ~49 B per treelet triangle and warp
+#endif
 
 struct TreeletTask { unsigned short begin, end; int slot; int depth; };
 

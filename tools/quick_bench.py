@@ -37,7 +37,7 @@ ctx = ptb.Context(0)
 sc = load_config(ptb, make_assets, a.config)
 t0 = time.time()
 handle, bst = ctx.accel_build(sc, ptb.default_build_cfg(max_leaf_size=a.leaf, sah_refine=a.refine, morton_bits=a.morton, treelet_size=a.treelet, bvh_width=a.bvh_width))
-print(f"build: {bst.num_triangles} tris, {bst.num_nodes} nodes, {bst.num_leaves} leaves, depth {bst.max_depth}, sah {bst.sah_cost:.2f}, "
+print(f"build: {bst.num_triangles} tris, {bst.num_nodes} nodes, {bst.num_leaves} leaves, depth {bst.max_depth}, sah {bst.sah_cost:.2f} (mesh subtree {bst.sah_cost_mesh:.2f}), width {bst.bvh_width}, "
       f"{bst.build_ms:.3f} ms device, {1e3 * (time.time() - t0):.1f} ms wall incl. upload")
 W, H = a.width, a.height
 n = W * H
