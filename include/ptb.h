@@ -183,8 +183,9 @@ typedef struct ptb_build_cfg {
     int32_t sah_bins;      /* default 16 */
     int32_t treelet_size;  /* primitives per refinement treelet, default 256 (the maximum; larger values are clamped) */
     int32_t morton_bits;   /* 30 (default: 10 bits per axis) or 63 (21 bits per axis) */
-    int32_t bvh_width;     /* 0 (default): 4-wide traversal for large scenes, 2-wide otherwise; 2 or 4 force one.  The
-                              hit rule does not depend on the tree, so results are identical. */
+    int32_t bvh_width;     /* 0 (default): 4-wide traversal for large scenes, 2-wide otherwise; 2, 4 or 8 force one
+                              (8: quantised 80-byte nodes, leaves of at most 3 triangles).  The hit rule does not depend on
+                              the tree, so results are identical. */
 } ptb_build_cfg;
 
 typedef struct ptb_build_stats {
@@ -192,9 +193,10 @@ typedef struct ptb_build_stats {
     float sah_cost;        /* sum(area*cost)/root area, Ct=1 Ci=1 */
     float build_ms;        /* device time of the build (CUDA events) */
     uint64_t bvh_bytes;
-    uint32_t bvh_width;    /* 2 or 4: the tree the traversal kernels walk (ptb_build_cfg.bvh_width = 0 picks by scene size) */
+    uint32_t bvh_width;    /* 2, 4 or 8: the tree the traversal kernels walk (ptb_build_cfg.bvh_width = 0 picks by scene size) */
     float sah_cost_mesh;   /* sah_cost of the subtree beside the huge-primitive leaf under the root (the reference's floor quad
                               spans the scene and dominates sah_cost), relative to that subtree's own box; = sah_cost without such a leaf */
+    uint32_t num_nodes8;   /* nodes of the 8-wide quantised tree (0 unless bvh_width == 8) */
 } ptb_build_stats;
 
 typedef struct ptb_material_info {
@@ -259,6 +261,10 @@ int ptb_accel_build(ptb_context* ctx, ptb_scene* scene, const ptb_build_cfg* cfg
 /* copies the flattened BVH back: nodes = 16 floats per node (64 B), tris = 12 floats per leaf-ordered triangle */
 int ptb_accel_read(ptb_context* ctx, unsigned long long handle, float* nodes, uint32_t cap_nodes,
                    float* tris, uint32_t cap_tris, uint32_t* n_nodes, uint32_t* n_tris);
+/* the 8-wide quantised copy (ptb_build_cfg.bvh_width = 8): nodes8 = 20 words per node (80 B), tris8 = 12 floats per triangle in
+ * the 8-wide tree's order; *n_nodes8 = 0 when the handle has no such tree */
+int ptb_accel_read8(ptb_context* ctx, unsigned long long handle, uint32_t* nodes8, uint32_t cap_nodes8,
+                    float* tris8, uint32_t cap_tris, uint32_t* n_nodes8, uint32_t* n_tris);
 
 /* ---- camera: sutil::Camera::UVWFrame as used by handleCameraUpdate /
  *      configureCamera (optixSphere.cpp:102-120, 238-247) ---------------------- */

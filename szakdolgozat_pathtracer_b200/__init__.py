@@ -98,6 +98,7 @@ class BuildStats(C.Structure):
     _fields_ = [
         ("num_triangles", C.c_uint32), ("num_nodes", C.c_uint32), ("num_leaves", C.c_uint32), ("max_depth", C.c_uint32),
         ("sah_cost", C.c_float), ("build_ms", C.c_float), ("bvh_bytes", C.c_uint64), ("bvh_width", C.c_uint32), ("sah_cost_mesh", C.c_float),
+        ("num_nodes8", C.c_uint32),
     ]
 
 
@@ -118,7 +119,7 @@ EXPORTS = [
     "ptb_scene_load_obj", "ptb_scene_create", "ptb_scene_create_demo", "ptb_scene_set_materials", "ptb_scene_set_env_file",
     "ptb_scene_set_env_pixels", "ptb_scene_destroy", "ptb_scene_num_triangles", "ptb_scene_num_materials",
     "ptb_scene_copy_triangles", "ptb_scene_copy_material_ids", "ptb_scene_get_material", "ptb_scene_copy_texture",
-    "ptb_scene_env_size", "ptb_scene_copy_env", "ptb_default_build_cfg", "ptb_accel_build", "ptb_accel_read",
+    "ptb_scene_env_size", "ptb_scene_copy_env", "ptb_default_build_cfg", "ptb_accel_build", "ptb_accel_read", "ptb_accel_read8",
     "ptb_camera_uvw", "ptb_params_default_camera", "ptb_default_render_cfg", "ptb_launch", "ptb_launch_get_stats", "ptb_launch_get_stage_ms", "ptb_context_get_totals",
     "ptb_resolve", "ptb_resolve_peers", "ptb_resolve_peers_accumulate", "ptb_resolve_peers_sync", "ptb_peer_flags_create", "ptb_peer_signal", "ptb_peer_wait", "ptb_peer_flags_error", "ptb_multi_create", "ptb_multi_destroy", "ptb_multi_device_count", "ptb_multi_context", "ptb_multi_stream", "ptb_multi_accel_build", "ptb_multi_launch", "ptb_multi_synchronize", "ptb_multi_get_totals", "ptb_ipc_export", "ptb_ipc_open", "ptb_ipc_close", "ptb_trace_rays", "ptb_output_create", "ptb_output_resize", "ptb_output_map", "ptb_output_unmap",
     "ptb_output_host_ptr", "ptb_output_width", "ptb_output_height", "ptb_output_destroy", "ptb_device_alloc",
@@ -348,6 +349,16 @@ class Context:
         nodes = np.zeros((nn.value, 16), np.float32)
         tris = np.zeros((nt.value, 12), np.float32)
         _check(lib().ptb_accel_read(self._h, C.c_ulonglong(handle), _fptr(nodes), nn, _fptr(tris), nt, None, None))
+        return nodes, tris
+
+    def accel_read8(self, handle):
+        """The 8-wide quantised tree: (nodes8 as uint32 [n, 20], tris8 as float32 [n_tris, 12]); empty arrays without one."""
+        nn, nt = C.c_uint32(), C.c_uint32()
+        _check(lib().ptb_accel_read8(self._h, C.c_ulonglong(handle), None, 0, None, 0, C.byref(nn), C.byref(nt)))
+        nodes = np.zeros((nn.value, 20), np.uint32)
+        tris = np.zeros((nt.value, 12), np.float32)
+        if nn.value:
+            _check(lib().ptb_accel_read8(self._h, C.c_ulonglong(handle), nodes.ctypes.data_as(C.POINTER(C.c_uint32)), nn, _fptr(tris), nt, None, None))
         return nodes, tris
 
     def launch(self, params: Params, cfg: RenderCfg | None = None, stream=0):

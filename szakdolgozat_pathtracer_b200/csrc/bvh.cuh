@@ -22,6 +22,7 @@
 // vertices 1 and 2.
 #pragma once
 #include "device_math.cuh"
+#include "views.cuh"
 
 namespace PTB_NS {
 
@@ -90,8 +91,10 @@ struct TravCounters { uint32_t nodes, tris; };
 // by the time it is popped the fetch has been under way for a whole subtree.  Only for trees that do not fit the caches
 // (4-wide traversal, PTB_WIDE_BVH_MIN_TRIS): C4 +1.5 %.
 PTB_DEV void trav_prefetch4(const float4* __restrict__ nodes4, const float4* __restrict__ tris, int code) {
+#ifndef PTB_HOST_SIM   // (tests/host: the traversal compiled for the CPU)
     const void* a = code >= 0 ? (const void*)(nodes4 + (size_t)code * 8) : (const void*)(tris + (size_t)((~code) >> 3) * 3);
     asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
+#endif
 }
 
 // Conservative slab test of one child box against [tmin, tbest].  Leaf boxes are padded at build time
@@ -121,7 +124,9 @@ struct Trav {
     float tmin, tminp, tmax;
     HitRec best;
     int node;  // current internal node (>= 0), leaf code (< 0) or PTB_TRAV_SENTINEL when finished
+               // (8-wide traversal: child_base of the current node group)
     int sp;
+    unsigned grp;  // 8-wide traversal only: hit bits (31..24) | imask (7..0) of the current node group
 };
 
 PTB_DEV void trav_begin(Trav& t, int* stack, float3 o, float3 d, float tmin, float tmax) {
@@ -132,6 +137,21 @@ PTB_DEV void trav_begin(Trav& t, int* stack, float3 o, float3 d, float tmin, flo
     stack[0] = PTB_TRAV_SENTINEL;
     t.sp = 1;
     t.node = 0;
+    t.grp = 0u;
+}
+
+// ray octant of the 8-wide traversal: bit set <=> the ray travels towards + on that axis (sign of 1 / d, so that -0 counts as -)
+PTB_DEV unsigned ray_octant(float3 id) { return (id.x < 0.0f ? 0u : 1u) | (id.y < 0.0f ? 0u : 2u) | (id.z < 0.0f ? 0u : 4u); }
+
+// 8-wide traversal: the root is the only member of a pseudo group (child_base 0, imask 1, its hit bit set); empty stack
+PTB_DEV void trav_begin8(Trav& t, float3 o, float3 d, float tmin, float tmax) {
+    t.o = o; t.id = mk3(ex_div(1.0f, d.x), ex_div(1.0f, d.y), ex_div(1.0f, d.z));
+    t.rs = ray_shear(d, t.id);
+    t.tmin = tmin; t.tminp = ex_mul(tmin, 0.999f); t.tmax = tmax;
+    t.best.t = tmax; t.best.b1 = 0.0f; t.best.b2 = 0.0f; t.best.prim = -1;
+    t.sp = 0;
+    t.node = 0;
+    t.grp = (1u << (24u + ray_octant(t.id))) | 1u;
 }
 
 // tests the triangles of one leaf against the ray (closest-hit rule of the header comment)
@@ -236,21 +256,134 @@ PTB_DEV bool trav_run4(Trav& t, int* stack, const float4* __restrict__ nodes4, c
     return false;
 }
 
-// 2- or 4-wide, by what the scene was built with (uniform over the launch)
-template <bool COUNT>
-PTB_DEV bool trav_run_any(Trav& t, int* stack, const float4* __restrict__ nodes, const float4* __restrict__ nodes4,
-                          const float4* __restrict__ tris, int budget, TravCounters* cnt) {
-    if (nodes4) return trav_run4<COUNT>(t, stack, nodes4, tris, budget, cnt);
-    return trav_run<COUNT>(t, stack, nodes, tris, budget, cnt);
+// ---- 8-wide traversal over the quantised tree (bvh8.cuh: node format, bvh_build.cu: k_collapse8_level) ------------------
+// A stack entry is a NODE GROUP: (child_base, hit bits 31..24 | imask 7..0) -- the children of one node that the ray
+// hit and has not entered yet.  Hit bits are stored at 24 + (slot ^ ray octant): the highest set bit is the child whose
+// slot lies farthest AGAINST the ray direction, i.e. the one the ray reaches first, so children are entered in (approximate)
+// front-to-back order without sorting distances.  Triangles of the leaf children that were hit come out of the same node
+// test as a 24-bit mask over the node's contiguous triangle range and are tested at once.
+// The box test is conservative by construction: (p - o) / d is bounded from below and above with directed rounding, the
+// quantised planes are added with fma.rd / fma.ru, and the quantised boxes contain the 2-wide tree's (padded) boxes.
+// Same hit rule as trav_run, so the result is identical.
+// byte k of w as a float without the conversion unit (I2F runs at a quarter of the FP32 rate and a node test needs 48 of
+// them): the byte is permuted into the mantissa of 2^23 and 2^23 is subtracted -- both exact
+PTB_DEV float u8f(unsigned w, int k) {
+#ifdef PTB_HOST_SIM
+    return (float)((w >> (8 * k)) & 0xffu);
+#else
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650u + (unsigned)k)) - 8388608.0f;
+#endif
 }
 
 template <bool COUNT>
-PTB_DEV HitRec bvh_closest_hit(const float4* __restrict__ nodes, const float4* __restrict__ nodes4, const float4* __restrict__ tris,
-                               float3 o, float3 d, float tmin, float tmax, TravCounters* cnt) {
-    int stack[PTB_BVH_STACK];
+PTB_DEV bool trav_run8(Trav& t, int* stack_i, const uint4* __restrict__ nodes8, const float4* __restrict__ tris8, int budget,
+                       TravCounters* cnt) {
+    uint2* stack = reinterpret_cast<uint2*>(stack_i);   // callers align the array to 16 bytes
+    const unsigned r = ray_octant(t.id);
+    const bool negx = t.id.x < 0.0f, negy = t.id.y < 0.0f, negz = t.id.z < 0.0f;
+    // 1 / d clamped to +-2^100 for the box tests: an axis-parallel ray (1 / d = inf) would turn q * a + b into NaN; with a huge
+    // finite slope the planes of a slab the origin lies in are at -huge / +huge (pass) and both at +-huge otherwise (miss)
+    const float idx = fminf(fmaxf(t.id.x, -1.2676506e30f), 1.2676506e30f), idy = fminf(fmaxf(t.id.y, -1.2676506e30f), 1.2676506e30f),
+                idz = fminf(fmaxf(t.id.z, -1.2676506e30f), 1.2676506e30f);
+    unsigned gbase = (unsigned)t.node, ghits = t.grp;
+    while (budget > 0) {
+        unsigned tbits = 0u, tbase = 0u;
+        while (budget > 0) {
+            if (ghits <= 0x00ffffffu) {   // the current group has no child left
+                if (t.sp == 0) { t.node = PTB_TRAV_SENTINEL; return true; }
+                const uint2 g = stack[--t.sp];
+                gbase = g.x; ghits = g.y;
+            }
+            const int bit = 31 - __clz(ghits);
+            ghits &= ~(1u << bit);
+            const unsigned slot = (unsigned)(bit - 24) ^ r;
+            const unsigned ni = gbase + (unsigned)__popc(ghits & 0xffu & ((1u << slot) - 1u));
+            if (ghits > 0x00ffffffu) stack[t.sp++] = make_uint2(gbase, ghits);
+            const uint4* np = nodes8 + (size_t)ni * 5;
+            const uint4 q0 = __ldg(np + 0), q1 = __ldg(np + 1), q2 = __ldg(np + 2), q3 = __ldg(np + 3), q4 = __ldg(np + 4);
+            if (COUNT) cnt->nodes++;
+            const unsigned ew = q0.w;
+            // a = grid step / d (exact: a power of two times 1 / d), [bn, bf] encloses (p - o) / d
+            const float ax = ex_mul(__uint_as_float((ew & 0xffu) << 23), idx), ay = ex_mul(__uint_as_float(((ew >> 8) & 0xffu) << 23), idy),
+                        az = ex_mul(__uint_as_float(((ew >> 16) & 0xffu) << 23), idz);
+            const float px = __uint_as_float(q0.x), py = __uint_as_float(q0.y), pz = __uint_as_float(q0.z);
+            const float rdx = __fsub_rd(px, t.o.x), rux = __fsub_ru(px, t.o.x), rdy = __fsub_rd(py, t.o.y), ruy = __fsub_ru(py, t.o.y),
+                        rdz = __fsub_rd(pz, t.o.z), ruz = __fsub_ru(pz, t.o.z);
+            const float bnx = __fmul_rd(negx ? rux : rdx, idx), bfx = __fmul_ru(negx ? rdx : rux, idx);
+            const float bny = __fmul_rd(negy ? ruy : rdy, idy), bfy = __fmul_ru(negy ? rdy : ruy, idy);
+            const float bnz = __fmul_rd(negz ? ruz : rdz, idz), bfz = __fmul_ru(negz ? rdz : ruz, idz);
+            const unsigned r4 = r * 0x01010101u;
+            unsigned hitmask = 0u;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                // slots 4h .. 4h + 3: near / far plane bytes by ray direction
+                const unsigned lox = h ? q2.y : q2.x, loy = h ? q2.w : q2.z, loz = h ? q3.y : q3.x;
+                const unsigned hix = h ? q3.w : q3.z, hiy = h ? q4.y : q4.x, hiz = h ? q4.w : q4.z;
+                const unsigned nx = negx ? hix : lox, fx = negx ? lox : hix;
+                const unsigned ny = negy ? hiy : loy, fy = negy ? loy : hiy;
+                const unsigned nz = negz ? hiz : loz, fz = negz ? loz : hiz;
+                const unsigned meta4 = h ? q1.w : q1.z;
+                const unsigned is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+                const unsigned inner_mask4 = (is_inner4 >> 4) * 0xffu;
+                const unsigned bit_index4 = (meta4 ^ (r4 & inner_mask4)) & 0x1f1f1f1fu;
+                const unsigned child_bits4 = (meta4 >> 5) & 0x07070707u;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float tn = fmaxf(fmaxf(__fmaf_rd(u8f(nx, k), ax, bnx), __fmaf_rd(u8f(ny, k), ay, bny)),
+                                           fmaxf(__fmaf_rd(u8f(nz, k), az, bnz), t.tminp));
+                    const float tf = ex_mul(fminf(fminf(__fmaf_ru(u8f(fx, k), ax, bfx), __fmaf_ru(u8f(fy, k), ay, bfy)),
+                                                  __fmaf_ru(u8f(fz, k), az, bfz)), 1.000001f);
+                    if (tn <= tf && tn <= t.best.t) hitmask |= ((child_bits4 >> (8 * k)) & 0xffu) << ((bit_index4 >> (8 * k)) & 0xffu);
+                }
+            }
+            gbase = q1.x; ghits = (hitmask & 0xff000000u) | (ew >> 24);
+            tbase = q1.y; tbits = hitmask & 0x00ffffffu;
+            --budget;
+            if (tbits) break;
+        }
+        if (tbits) {
+            do {
+                const int j = __ffs((int)tbits) - 1;
+                tbits &= tbits - 1u;
+                const float4* tp = tris8 + (size_t)(tbase + (unsigned)j) * 3;
+                const float4 a = __ldg(tp + 0), b = __ldg(tp + 1), c = __ldg(tp + 2);
+                if (COUNT) cnt->tris++;
+                float th, b1, b2;
+                if (ray_tri(t.o, t.rs, mk3(a), mk3(b), mk3(c), t.tmin, t.tmax, &th, &b1, &b2)) {
+                    const int prim = __float_as_int(a.w);
+                    if (th < t.best.t || (th == t.best.t && t.best.prim >= 0 && prim < t.best.prim)) {
+                        t.best.t = th; t.best.b1 = b1; t.best.b2 = b2; t.best.prim = prim;
+                    }
+                }
+            } while (tbits);
+            budget -= 2;
+        }
+        if (ghits <= 0x00ffffffu && t.sp == 0) { t.node = PTB_TRAV_SENTINEL; return true; }
+    }
+    t.node = (int)gbase; t.grp = ghits;
+    return false;
+}
+
+// WIDTH = 2, 4, 8: the tree the kernel was instantiated for; 0: by what the scene was built with (uniform over the launch)
+template <int WIDTH>
+PTB_DEV void trav_begin_any(Trav& t, int* stack, const ptbv::SceneView& s, float3 o, float3 d, float tmin, float tmax) {
+    if (WIDTH == 8 || (WIDTH == 0 && s.nodes8)) trav_begin8(t, o, d, tmin, tmax);
+    else trav_begin(t, stack, o, d, tmin, tmax);
+}
+
+template <bool COUNT, int WIDTH>
+PTB_DEV bool trav_run_any(Trav& t, int* stack, const ptbv::SceneView& s, int budget, TravCounters* cnt) {
+    if (WIDTH == 8 || (WIDTH == 0 && s.nodes8)) return trav_run8<COUNT>(t, stack, s.nodes8, s.tris8, budget, cnt);
+    if (WIDTH == 4 || (WIDTH == 0 && s.nodes4)) return trav_run4<COUNT>(t, stack, s.nodes4, s.tris, budget, cnt);
+    return trav_run<COUNT>(t, stack, s.nodes, s.tris, budget, cnt);
+}
+
+template <bool COUNT>
+PTB_DEV HitRec bvh_closest_hit(const ptbv::SceneView& s, float3 o, float3 d, float tmin, float tmax, TravCounters* cnt) {
+    __align__(16) int stack[PTB_BVH_STACK];
     Trav t;
-    trav_begin(t, stack, o, d, tmin, tmax);
-    while (!trav_run_any<COUNT>(t, stack, nodes, nodes4, tris, 1 << 20, cnt)) {}
+    trav_begin_any<0>(t, stack, s, o, d, tmin, tmax);
+    while (!trav_run_any<COUNT, 0>(t, stack, s, 1 << 20, cnt)) {}
     return t.best;
 }
 

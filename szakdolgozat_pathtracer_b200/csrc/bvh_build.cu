@@ -29,6 +29,7 @@
 #include <vector>
 
 #include "bvh_build.h"
+#include "bvh8.cuh"
 #include "bvh_refine.cuh"
 #include "device_math.cuh"
 
@@ -424,6 +425,28 @@ __global__ void k_collapse4(const float4* __restrict__ nodes2, const int* __rest
     atomicAdd(count4, 1u);
 }
 
+// ---- 8-wide quantised collapse (bvh8.cuh) -----------------------------------------------------------------------------
+// One level of the 8-wide tree per launch: every work item (8-wide node index, 2-wide node it starts from) opens 2-wide
+// nodes greedily by surface area until it holds eight children, quantises their boxes, copies the triangles of its leaf
+// children into one contiguous range and queues its internal children (which get consecutive node indices) for the next
+// level.  counters8: [0] nodes allocated, [1] triangles allocated, [2] error bits, [3 + (level & 1)] length of the queue
+// being written.
+struct Alloc8 {
+    unsigned int* counters; ptb8::WorkItem* next; unsigned int* next_count;
+    __device__ uint32_t nodes(uint32_t n) { return atomicAdd(&counters[0], n); }
+    __device__ uint32_t tris(uint32_t n) { return atomicAdd(&counters[1], n); }
+    __device__ void push(ptb8::WorkItem w) { next[atomicAdd(next_count, 1u)] = w; }
+    __device__ void error(int bits) { atomicOr(&counters[2], (unsigned int)bits); }
+};
+__global__ void k_collapse8_level(const float4* __restrict__ nodes2, const float4* __restrict__ tris2, const ptb8::WorkItem* __restrict__ in,
+                                  unsigned int n_in, ptb8::WorkItem* __restrict__ out, unsigned int* __restrict__ out_count,
+                                  unsigned int* __restrict__ counters8, uint4* __restrict__ nodes8, float4* __restrict__ tris8) {
+    const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_in) return;
+    Alloc8 al; al.counters = counters8; al.next = out; al.next_count = out_count;
+    ptb8::collapse8_node(nodes2, tris2, in[i], nodes8, tris8, al);
+}
+
 // One device allocation for all the builder's temporaries, carved into 256-byte aligned pieces.
 struct Scratch {
     char* base = nullptr; size_t used = 0, cap = 0;
@@ -452,7 +475,10 @@ bool build_bvh_impl(const float4* d_verts, uint32_t n, const ptb_build_cfg& cfg,
                     ptb_build_stats& stats, std::string& err) {
     memset(&stats, 0, sizeof(stats));
     stats.num_triangles = n;
-    const int max_leaf = cfg.max_leaf_size < 1 ? 1 : (cfg.max_leaf_size > 8 ? 8 : cfg.max_leaf_size);
+    // the 8-wide quantised tree holds at most 24 triangles per node: leaves of at most 3
+    const bool want8 = n >= 2 && cfg.bvh_width == 8;
+    const int max_leaf_cfg = cfg.max_leaf_size < 1 ? 1 : (cfg.max_leaf_size > 8 ? 8 : cfg.max_leaf_size);
+    const int max_leaf = want8 && max_leaf_cfg > 3 ? 3 : max_leaf_cfg;
     const bool refine = cfg.sah_refine != 0;
     if (n >= (1u << 28)) { err = "BVH build: more than 2^28 triangles"; return false; }
 
@@ -501,12 +527,12 @@ bool build_bvh_impl(const float4* d_verts, uint32_t n, const ptb_build_cfg& cfg,
     Scratch sc;
     float4 *tri_lo, *tri_hi, *leaf_lo, *leaf_hi, *node_lo, *node_hi;
     float* scene_bounds; uint64_t* keys[2]; uint32_t *vals[2], *hist; int2 *children, *ranges; int *node_parent, *leaf_parent;
-    unsigned int *flags, *counters; float* sah; unsigned char* collapse; int* treelets; uint32_t* bin_total;
+    unsigned int *flags, *counters, *counters8; float* sah; unsigned char* collapse; int* treelets; uint32_t* bin_total;
     const uint32_t n_tiles = (n + SORT_TILE - 1) / SORT_TILE;
     for (int k = 0; k < 6; ++k) sc.reserve<float4>(n);
     sc.reserve<float>(12); sc.reserve<uint64_t>(n); sc.reserve<uint64_t>(n); sc.reserve<uint32_t>(n); sc.reserve<uint32_t>(n);
     sc.reserve<uint32_t>((size_t)256 * n_tiles); sc.reserve<int2>(n); sc.reserve<int2>(n); sc.reserve<int>(n); sc.reserve<int>(n);
-    sc.reserve<unsigned int>(n); sc.reserve<unsigned int>(8); sc.reserve<float>(1); sc.reserve<unsigned char>(n); sc.reserve<int>(n);
+    sc.reserve<unsigned int>(n); sc.reserve<unsigned int>(8); sc.reserve<unsigned int>(8); sc.reserve<float>(1); sc.reserve<unsigned char>(n); sc.reserve<int>(n);
     sc.reserve<uint32_t>(512);
     if (!sc.commit(err)) return false;
     tri_lo = sc.take<float4>(n); tri_hi = sc.take<float4>(n); leaf_lo = sc.take<float4>(n); leaf_hi = sc.take<float4>(n);
@@ -514,7 +540,7 @@ bool build_bvh_impl(const float4* d_verts, uint32_t n, const ptb_build_cfg& cfg,
     scene_bounds = sc.take<float>(12); keys[0] = sc.take<uint64_t>(n); keys[1] = sc.take<uint64_t>(n);
     vals[0] = sc.take<uint32_t>(n); vals[1] = sc.take<uint32_t>(n); hist = sc.take<uint32_t>((size_t)256 * n_tiles);
     children = sc.take<int2>(n); ranges = sc.take<int2>(n); node_parent = sc.take<int>(n); leaf_parent = sc.take<int>(n);
-    flags = sc.take<unsigned int>(n); counters = sc.take<unsigned int>(8); sah = sc.take<float>(1);
+    flags = sc.take<unsigned int>(n); counters = sc.take<unsigned int>(8); counters8 = sc.take<unsigned int>(8); sah = sc.take<float>(1);
     collapse = sc.take<unsigned char>(n); treelets = sc.take<int>(n); bin_total = sc.take<uint32_t>(512);
     // the timed region starts here: kernels and memsets of the build only, no allocation
     CK(cudaEventRecord(ev0, stream));
@@ -564,6 +590,31 @@ bool build_bvh_impl(const float4* d_verts, uint32_t n, const ptb_build_cfg& cfg,
     k_emit_tris<<<G, B, 0, stream>>>(d_verts, vals[cur], n, d_tris);
     if (out.nodes4) k_collapse4<<<G, B, 0, stream>>>(d_nodes, node_parent, collapse, (int)n, out.nodes4, counters + 4);
     CK(cudaGetLastError());
+    uint32_t levels8 = 0;
+    if (want8) {
+        // level-synchronous collapse; the queues reuse builder scratch that is dead by now (keys: 8 B per triangle each)
+        uint4* d_nodes8 = nullptr; float4* d_tris8 = nullptr;
+        if (cudaMalloc((void**)&d_nodes8, (size_t)n_nodes * 80) != cudaSuccess || cudaMalloc((void**)&d_tris8, (size_t)n * 48) != cudaSuccess) {
+            cudaFree(d_nodes8); err = "cudaMalloc (8-wide BVH) failed"; return false;
+        }
+        out.nodes8 = d_nodes8; out.tris8 = d_tris8;
+        ptb8::WorkItem* q[2] = {reinterpret_cast<ptb8::WorkItem*>(keys[0]), reinterpret_cast<ptb8::WorkItem*>(keys[1])};
+        unsigned int* c8 = counters8;
+        const unsigned int init8[5] = {1u, 0u, 0u, 0u, 0u};
+        const ptb8::WorkItem root = {0, 0};
+        CK(cudaMemcpyAsync(c8, init8, sizeof(init8), cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(q[0], &root, sizeof(root), cudaMemcpyHostToDevice, stream));
+        unsigned int n_in = 1;
+        while (n_in > 0 && levels8 < 200) {
+            const int w = (int)(levels8 & 1u);
+            CK(cudaMemsetAsync(c8 + 3 + (w ^ 1), 0, sizeof(unsigned int), stream));
+            k_collapse8_level<<<(n_in + 127u) / 128u, 128, 0, stream>>>(d_nodes, d_tris, q[w], n_in, q[w ^ 1], c8 + 3 + (w ^ 1), c8, d_nodes8, d_tris8);
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(&n_in, c8 + 3 + (w ^ 1), sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
+            ++levels8;
+        }
+    }
     CK(cudaEventRecord(ev1, stream));
 
     unsigned int h_counters[4]; float h_sah = 0.0f; float4 root_lo, root_hi;
@@ -606,6 +657,28 @@ bool build_bvh_impl(const float4* d_verts, uint32_t n, const ptb_build_cfg& cfg,
     // the 4-wide traversal pushes up to three entries per level of the collapsed tree (half the 2-wide depth)
     if (out.nodes4 && (stats.max_depth / 2 + 1) * 3 + 2 >= PTB_BVH_MAX_DEPTH) { cudaFree(out.nodes4); out.nodes4 = nullptr; }
     stats.bvh_width = out.nodes4 ? 4 : 2;  // what the traversal kernels will walk
+    if (out.nodes8) {
+        unsigned int h8[3] = {0u, 0u, 0u};
+        CK(cudaMemcpyAsync(h8, counters8, sizeof(h8), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        // a stack entry per level of the 8-wide tree (uint2 entries in the PTB_BVH_STACK ints); any collapse error
+        // (a leaf of more than 3 triangles, a non-finite box) falls back to the narrower tree
+        if (h8[2] != 0u || levels8 + 2 >= PTB_BVH_MAX_DEPTH / 2 || h8[1] != n || h8[0] > n_nodes) {
+            cudaFree(out.nodes8); cudaFree(out.tris8); out.nodes8 = nullptr; out.tris8 = nullptr;
+        } else {
+            out.n_nodes8 = h8[0];
+            // give back what the worst-case allocation did not need
+            uint4* tight = nullptr;
+            if (h8[0] < n_nodes && cudaMalloc((void**)&tight, (size_t)h8[0] * 80) == cudaSuccess) {
+                CK(cudaMemcpyAsync(tight, out.nodes8, (size_t)h8[0] * 80, cudaMemcpyDeviceToDevice, stream));
+                CK(cudaStreamSynchronize(stream));
+                cudaFree(out.nodes8); out.nodes8 = tight;
+            }
+            stats.bvh_width = 8;
+            stats.bvh_bytes += (uint64_t)h8[0] * 80 + (uint64_t)n * 48;
+            stats.num_nodes8 = h8[0];
+        }
+    }
     if (stats.max_depth >= PTB_BVH_MAX_DEPTH) {
         err = "BVH build: tree depth " + std::to_string(stats.max_depth) + " exceeds the traversal stack (" + std::to_string(PTB_BVH_MAX_DEPTH) + ")";
         return false;
@@ -626,6 +699,8 @@ bool build_bvh(const float4* d_verts, uint32_t n, const ptb_build_cfg& cfg, cuda
 void free_bvh(DeviceBvh& b) {
     if (b.nodes) cudaFree(b.nodes);
     if (b.nodes4) cudaFree(b.nodes4);
+    if (b.nodes8) cudaFree(b.nodes8);
+    if (b.tris8) cudaFree(b.tris8);
     if (b.tris) cudaFree(b.tris);
     b = DeviceBvh();
 }

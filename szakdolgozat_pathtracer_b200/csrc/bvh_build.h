@@ -16,7 +16,9 @@ struct DeviceBvh {
     float4* nodes = nullptr;  // n_nodes x 4 float4 (64 B each), layout in bvh.cuh
     float4* nodes4 = nullptr; // optional 4-wide copy: n_nodes x 8 float4 (128 B each, indexed like `nodes`), layout in bvh.cuh
     float4* tris = nullptr;   // n_tris x 3 float4 (48 B each), leaf order
-    uint32_t n_nodes = 0, n_tris = 0;
+    uint4* nodes8 = nullptr;  // optional 8-wide quantised copy: n_nodes8 x 5 uint4 (80 B each), layout in bvh8.cuh
+    float4* tris8 = nullptr;  // its triangles (the leaf triangles again, contiguous per 8-wide node)
+    uint32_t n_nodes = 0, n_tris = 0, n_nodes8 = 0;
 };
 
 // d_verts: 3 float4 per triangle (the reference's vertex buffer, optixSphere.cpp:871-894).

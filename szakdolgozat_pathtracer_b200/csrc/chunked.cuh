@@ -164,16 +164,16 @@ PTB_DEV void chunk_build_two(ChunkSharedT<SPT>& sh, const unsigned char* __restr
 }
 
 // ---- stage bodies over one chunk ---------------------------------------------------------------------------
-template <bool COUNT, int QUANTUM, int SPT>
+template <bool COUNT, int QUANTUM, int SPT, int WIDTH = 0>
 PTB_DEV void chunk_stage_trace(ChunkSharedT<SPT>& sh, const SceneView& s, const FrameView& f, const PathView& p,
                                unsigned char* __restrict__ status, uint32_t base, unsigned int n, bool first_iteration,
                                TravCounters& tc, uint32_t sbase = 0, unsigned int n_front = 0xffffffffu) {
     // the list is [0, n_front) at the front of sh.list and the remaining n - n_front entries at its back (chunk_build_two)
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
-    int stack[PTB_BVH_STACK];
+    __align__(16) int stack[PTB_BVH_STACK];
     Trav t;
-    t.node = PTB_TRAV_SENTINEL; t.sp = 0; t.best.prim = -1; t.best.t = 0.0f; t.best.b1 = 0.0f; t.best.b2 = 0.0f;
+    t.node = PTB_TRAV_SENTINEL; t.sp = 0; t.grp = 0u; t.best.prim = -1; t.best.t = 0.0f; t.best.b1 = 0.0f; t.best.b2 = 0.0f;
     uint32_t slot = 0;
     bool have = false, exhausted = false;
     unsigned int hits = 0;
@@ -191,14 +191,14 @@ PTB_DEV void chunk_stage_trace(ChunkSharedT<SPT>& sh, const SceneView& s, const 
                 if (!have && idx < n) {
                     slot = base + sh.list[idx < n_front ? idx : ChunkSharedT<SPT>::CHUNK - n + idx];
                     const float4 o4 = ldp(&p.ray_o[slot]), d4 = ldp(&p.ray_d[slot]);
-                    trav_begin(t, stack, mk3(o4), mk3(d4), f.tmin, f.tmax);
+                    trav_begin_any<WIDTH>(t, stack, s, mk3(o4), mk3(d4), f.tmin, f.tmax);
                     have = true;
                 }
                 if (b0 + cnt >= n) exhausted = true;  // warp-uniform
             }
         }
         if (!__any_sync(0xffffffffu, have)) break;
-        if (have && trav_run_any<COUNT>(t, stack, s.nodes, s.nodes4, s.tris, QUANTUM, &tc)) {
+        if (have && trav_run_any<COUNT, WIDTH>(t, stack, s, QUANTUM, &tc)) {
             have = false;
             stp(&p.hit[slot], make_float4(t.best.t, t.best.b1, t.best.b2, __int_as_float(t.best.prim)));
             const bool is_hit = t.best.prim >= 0;
@@ -358,7 +358,9 @@ __global__ void __launch_bounds__(PTB_CHUNK_THREADS) k_chunk_miss(SceneView s, F
 // One block = one chunk, from the first camera ray to the last sample of its pixels.  Two list passes per wavefront
 // iteration (one code copy, alternating phases): {TRACE, BUSY} before the trace stage, {HIT, MISS} before shade + miss.
 // totals[3] is not touched here (launch count is added by k_fold_counters' sibling on the host path).
-template <bool COUNT, int QUANTUM, int MINB, int SPT>
+// WIDTH: the tree the trace stage walks (2, 4, 8: one instantiation each, so that the 2-wide kernel does not carry the wide
+// traversals' code; 0: decided at run time, the instrumented variant).
+template <bool COUNT, int QUANTUM, int MINB, int SPT, int WIDTH>
 __global__ void __launch_bounds__(PTB_CHUNK_THREADS, (MINB * 128 + PTB_CHUNK_THREADS - 1) / PTB_CHUNK_THREADS) k_chunk_fused(SceneView s, FrameView f, PathView p, unsigned char* status,
                                                                   unsigned long long* totals, unsigned long long* trav_stats,
                                                                   unsigned int* max_iters_seen) {
@@ -389,7 +391,7 @@ __global__ void __launch_bounds__(PTB_CHUNK_THREADS, (MINB * 128 + PTB_CHUNK_THR
         if (phase == 0u) {
             if (na + nb == 0u) break;  // every pixel of the chunk has finished its samples
             if (threadIdx.x == 0) sh.count[0] += na + nb;
-            chunk_stage_trace<COUNT, QUANTUM>(sh, s, f, p, stp_, base, na + nb, iter == 0, tc, sbase, na);
+            chunk_stage_trace<COUNT, QUANTUM, SPT, WIDTH>(sh, s, f, p, stp_, base, na + nb, iter == 0, tc, sbase, na);
             ++iter;
         } else {
             chunk_stage_shade_miss(sh, s, f, p, stp_, base, na, nb, sbase, PTB_TRACE_TWO_LISTS != 0);
@@ -430,12 +432,15 @@ inline void launch_chunk_fused(const ChunkLaunch& a, cudaStream_t st) {
     // 64 registers once there are enough chunks to keep that many blocks busy, the unconstrained ~80-register build for
     // launches that cannot fill the chip anyway
     const bool wide = chunks >= full;
-#define PTB_CF_LAUNCH(COUNT, MINB, SPT) k_chunk_fused<COUNT, PTB_TRACE_QUANTUM, MINB, SPT><<<chunks, PTB_CHUNK_THREADS, 0, st>>>(a.s, a.f, a.p, a.status, a.totals, a.trav_stats, a.max_iters)
-#define PTB_CF_BY_SPT(COUNT, MINB) do { if (spt == 8) PTB_CF_LAUNCH(COUNT, MINB, 8); else if (spt == 4) PTB_CF_LAUNCH(COUNT, MINB, 4); \
-                                        else if (spt == 2) PTB_CF_LAUNCH(COUNT, MINB, 2); else PTB_CF_LAUNCH(COUNT, MINB, 1); } while (0)
-    if (a.count) PTB_CF_LAUNCH(true, 5, 8);
-    else if (wide) PTB_CF_BY_SPT(false, PTB_MINB_WIDE);
-    else PTB_CF_BY_SPT(false, 5);
+    const int width = a.s.nodes8 ? 8 : (a.s.nodes4 ? 4 : 2);
+#define PTB_CF_LAUNCH(COUNT, MINB, SPT, WIDTH) k_chunk_fused<COUNT, PTB_TRACE_QUANTUM, MINB, SPT, WIDTH><<<chunks, PTB_CHUNK_THREADS, 0, st>>>(a.s, a.f, a.p, a.status, a.totals, a.trav_stats, a.max_iters)
+#define PTB_CF_BY_SPT(MINB, WIDTH) do { if (spt == 8) PTB_CF_LAUNCH(false, MINB, 8, WIDTH); else if (spt == 4) PTB_CF_LAUNCH(false, MINB, 4, WIDTH); \
+                                        else if (spt == 2) PTB_CF_LAUNCH(false, MINB, 2, WIDTH); else PTB_CF_LAUNCH(false, MINB, 1, WIDTH); } while (0)
+#define PTB_CF_BY_WIDTH(MINB) do { if (width == 8) PTB_CF_BY_SPT(MINB, 8); else if (width == 4) PTB_CF_BY_SPT(MINB, 4); else PTB_CF_BY_SPT(MINB, 2); } while (0)
+    if (a.count) PTB_CF_LAUNCH(true, 5, 8, 0);
+    else if (wide) PTB_CF_BY_WIDTH(PTB_MINB_WIDE);
+    else PTB_CF_BY_WIDTH(5);
+#undef PTB_CF_BY_WIDTH
 #undef PTB_CF_BY_SPT
 #undef PTB_CF_LAUNCH
 }

@@ -151,9 +151,9 @@ __global__ void __launch_bounds__(128) k_trace(SceneView s, FrameView f, PathVie
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
     TravCounters tc; tc.nodes = 0; tc.tris = 0;
-    int stack[PTB_BVH_STACK];
+    __align__(16) int stack[PTB_BVH_STACK];
     Trav t;
-    t.node = PTB_TRAV_SENTINEL; t.sp = 0; t.best.prim = -1; t.best.t = 0.0f; t.best.b1 = 0.0f; t.best.b2 = 0.0f;
+    t.node = PTB_TRAV_SENTINEL; t.sp = 0; t.grp = 0u; t.best.prim = -1; t.best.t = 0.0f; t.best.b1 = 0.0f; t.best.b2 = 0.0f;
     uint32_t slot = 0;
     bool have = false, pending = false, exhausted = false;
     for (;;) {
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(128) k_trace(SceneView s, FrameView f, PathVie
                 if (!have && idx < n) {
                     slot = in[idx];
                     const float4 o4 = ldp(&p.ray_o[slot]), d4 = ldp(&p.ray_d[slot]);
-                    trav_begin(t, stack, mk3(o4), mk3(d4), f.tmin, f.tmax);
+                    trav_begin_any<0>(t, stack, s, mk3(o4), mk3(d4), f.tmin, f.tmax);
                     have = true;
                 }
                 if (base + cnt >= n) exhausted = true;  // warp-uniform
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(128) k_trace(SceneView s, FrameView f, PathVie
         }
         if (!__any_sync(0xffffffffu, have)) break;
         if (have) {
-            if (trav_run_any<COUNT>(t, stack, s.nodes, s.nodes4, s.tris, QUANTUM, &tc)) { have = false; pending = true; }
+            if (trav_run_any<COUNT, 0>(t, stack, s, QUANTUM, &tc)) { have = false; pending = true; }
         }
     }
     if (COUNT) {
@@ -721,7 +721,7 @@ __global__ void k_trace_rays(SceneView s, const float* __restrict__ origins, con
     const float3 o = mk3(origins[3 * (size_t)i], origins[3 * (size_t)i + 1], origins[3 * (size_t)i + 2]);
     const float3 d = mk3(dirs[3 * (size_t)i], dirs[3 * (size_t)i + 1], dirs[3 * (size_t)i + 2]);
     TravCounters tc;
-    const HitRec h = bvh_closest_hit<false>(s.nodes, s.nodes4, s.tris, o, d, tmin, tmax, &tc);
+    const HitRec h = bvh_closest_hit<false>(s, o, d, tmin, tmax, &tc);
     if (prim) prim[i] = h.prim;
     if (t) t[i] = h.t;
     if (b1) b1[i] = h.b1;

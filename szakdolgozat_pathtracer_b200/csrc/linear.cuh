@@ -189,7 +189,7 @@ PTB_DEV void chunk_stage_shadow(ChunkShared& sh, const SceneView& s, const Frame
         const float4 d = lv.shadow_d[slot], c = lv.shadow_c[slot];
         const float3 o = mk3(lv.shadow_o[slot]);
         TravCounters tc;
-        const HitRec h = bvh_closest_hit<false>(s.nodes, s.nodes4, s.tris, o, mk3(d), f.tmin, f.tmax, &tc);
+        const HitRec h = bvh_closest_hit<false>(s, o, mk3(d), f.tmin, f.tmax, &tc);
         if (h.prim < 0) add_to_pixel(p, slot, mk3(c));
         lv.shadow_flag[slot] = 0;
     }

@@ -79,7 +79,7 @@ PTB_DEV void pool_stage_trace(PoolShared& sh, const SceneView& s, const FrameVie
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
     Trav t;
-    t.node = PTB_TRAV_SENTINEL; t.sp = 0; t.best.prim = -1; t.best.t = 0.0f; t.best.b1 = 0.0f; t.best.b2 = 0.0f;
+    t.node = PTB_TRAV_SENTINEL; t.sp = 0; t.grp = 0u; t.best.prim = -1; t.best.t = 0.0f; t.best.b1 = 0.0f; t.best.b2 = 0.0f;
     unsigned int pos = 0;
     bool have = false, exhausted = false;
     unsigned int hits = 0;
@@ -97,14 +97,14 @@ PTB_DEV void pool_stage_trace(PoolShared& sh, const SceneView& s, const FrameVie
                 if (!have && idx < n) {
                     pos = sh.list[idx];
                     const float4 o4 = p.ray_o[gbase + pos], d4 = p.ray_d[gbase + pos];
-                    trav_begin(t, stack, mk3(o4), mk3(d4), f.tmin, f.tmax);
+                    trav_begin_any<0>(t, stack, s, mk3(o4), mk3(d4), f.tmin, f.tmax);
                     have = true;
                 }
                 if (b0 + cnt >= n) exhausted = true;  // warp-uniform
             }
         }
         if (!__any_sync(0xffffffffu, have)) break;
-        if (have && trav_run_any<COUNT>(t, stack, s.nodes, s.nodes4, s.tris, QUANTUM, &tc)) {
+        if (have && trav_run_any<COUNT, 0>(t, stack, s, QUANTUM, &tc)) {
             have = false;
             p.hit[gbase + pos] = make_float4(t.best.t, t.best.b1, t.best.b2, __int_as_float(t.best.prim));
             const bool is_hit = t.best.prim >= 0;
@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(PTB_CHUNK_THREADS, (MINB * 128) / PTB_CHUNK_TH
     if (threadIdx.x == 0) { sh.batch_next = 0u; sh.batch_end = 0u; sh.pool_dry = 0u; }
     for (unsigned int i = threadIdx.x; i < PTB_CHUNK; i += PTB_CHUNK_THREADS) { sh.status[i] = ST_FREE; sh.slot[i] = 0u; }
     TravCounters tc; tc.nodes = 0; tc.tris = 0;
-    int stack[PTB_BVH_STACK];
+    __align__(16) int stack[PTB_BVH_STACK];
     __syncthreads();
     unsigned int iter = 0;
     for (;; ++iter) {

@@ -168,6 +168,7 @@ int ensure_pool(ptb_context* c, uint32_t slots, uint32_t iters) {
 SceneView scene_view(const DeviceScene* d) {
     SceneView s;
     s.nodes = d->bvh.nodes; s.nodes4 = d->bvh.nodes4; s.tris = d->bvh.tris;
+    s.nodes8 = d->bvh.nodes8; s.tris8 = d->bvh.tris8;
     s.verts = d->verts; s.normals = d->normals; s.uvs = d->uvs; s.mat_ids = d->mat_ids; s.mats = d->mats;
     s.env = d->env; s.env_w = d->env_w; s.env_h = d->env_h;
     return s;
@@ -348,6 +349,26 @@ int ptb_accel_read(ptb_context* ctx, unsigned long long handle, float* nodes, ui
     if (tris) {
         if (cap_tris < d->bvh.n_tris) return fail(PTB_ERR_INVALID, "ptb_accel_read: triangle buffer too small");
         CU(cudaMemcpy(tris, d->bvh.tris, (size_t)d->bvh.n_tris * 48, cudaMemcpyDeviceToHost));
+    }
+    return PTB_OK;
+}
+
+int ptb_accel_read8(ptb_context* ctx, unsigned long long handle, uint32_t* nodes8, uint32_t cap_nodes8, float* tris8, uint32_t cap_tris,
+                    uint32_t* n_nodes8, uint32_t* n_tris) {
+    if (!ctx) return fail(PTB_ERR_INVALID, "ptb_accel_read8: null context");
+    DeviceScene* d = find_scene(ctx, handle);
+    if (!d) return fail(PTB_ERR_INVALID, "ptb_accel_read8: unknown handle");
+    CU(cudaSetDevice(ctx->device));
+    const uint32_t nn = d->bvh.nodes8 ? d->bvh.n_nodes8 : 0u, nt = d->bvh.nodes8 ? d->bvh.n_tris : 0u;
+    if (n_nodes8) *n_nodes8 = nn;
+    if (n_tris) *n_tris = nt;
+    if (nodes8 && nn) {
+        if (cap_nodes8 < nn) return fail(PTB_ERR_INVALID, "ptb_accel_read8: node buffer too small");
+        CU(cudaMemcpy(nodes8, d->bvh.nodes8, (size_t)nn * 80, cudaMemcpyDeviceToHost));
+    }
+    if (tris8 && nt) {
+        if (cap_tris < nt) return fail(PTB_ERR_INVALID, "ptb_accel_read8: triangle buffer too small");
+        CU(cudaMemcpy(tris8, d->bvh.tris8, (size_t)nt * 48, cudaMemcpyDeviceToHost));
     }
     return PTB_OK;
 }

@@ -19,6 +19,7 @@ struct DevMaterial {
 
 struct SceneView {
     const float4* nodes; const float4* nodes4; const float4* tris;  // nodes4: 4-wide copy of the tree or nullptr
+    const uint4* nodes8; const float4* tris8;                       // 8-wide quantised copy + its triangle order (bvh8.cuh) or nullptr
     const float4* verts; const float4* normals; const float2* uvs; const uint32_t* mat_ids;
     const DevMaterial* mats;
     const float4* env; int env_w, env_h;

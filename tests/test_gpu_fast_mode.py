@@ -130,6 +130,22 @@ def test_fast_mode_stage_kernels_equal_fused(ptb, ctx, assets):
     assert np.array_equal(a2.view(np.uint32), a3.view(np.uint32))
 
 
+def test_fast_mode_wide_trees_equal_two_wide(ptb, ctx, assets):
+    """The traversal is exact arithmetic in both builds and the hit rule does not depend on the tree: the fast build gives
+    the same image over the 2-wide, the 4-wide and the 8-wide quantised tree, bit for bit (fused and stage kernels)."""
+    sc = load_config(ptb, assets, "c2")
+    ref = None
+    for width in (2, 4, 8):
+        handle, st = ctx.accel_build(sc, ptb.default_build_cfg(bvh_width=width))
+        assert st.bvh_width == width
+        for pipeline in (3, 2):
+            a, f, h, s = _render(ptb, ctx, handle, 160, 90, "monkey_close", True, ptb.PTB_ARITH_FAST, 4, 2, 6, want_hits=True, pipeline=pipeline)
+            if ref is None:
+                ref = (a, f, h, s.segments)
+            assert s.segments == ref[3] and np.array_equal(h, ref[2]) and np.array_equal(f, ref[1]), (width, pipeline)
+            assert np.array_equal(a.view(np.uint32), ref[0].view(np.uint32)), (width, pipeline)
+
+
 def test_fast_mode_refused_where_it_does_not_exist(ptb, ctx, assets):
     sc = load_config(ptb, assets, "c1", small=True)
     handle, _ = ctx.accel_build(sc)

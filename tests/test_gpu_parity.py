@@ -151,6 +151,92 @@ def _check_bvh(nodes, tris, n_tris, max_leaf):
     return visited
 
 
+def _check_bvh8(nodes8, tris8, n_tris):
+    """Structural validation of the 8-wide quantised tree (csrc/bvh8.cuh) read back from the device: every triangle in
+    exactly one leaf slot, internal children contiguous, and every child's quantised box contains what lies below it."""
+    seen = np.zeros(n_tris, np.int32)
+    prim_ids = tris8[:, 3].view(np.int32)
+    tv = tris8.reshape(-1, 3, 4)[:, :, :3]
+    visited, children = 0, 0
+    def bounds(ni):
+        """(lo, hi) of the triangles under node ni, checking the node on the way (a child's own quantised boxes may stick out
+        of the box its parent holds for it: only the geometry has to be inside)"""
+        nonlocal visited, children
+        visited += 1
+        q = nodes8[ni]
+        p = q[0:3].view(np.float32).astype(np.float64)
+        ew = int(q[3])
+        step = np.array([2.0 ** (((ew >> (8 * d)) & 0xff) - 127) for d in range(3)])
+        imask = ew >> 24
+        child_base, tri_base = int(q[4]), int(q[5])
+        by = q[6:20].view(np.uint8).reshape(7, 8)   # meta, lox, loy, loz, hix, hiy, hiz (little endian: byte k of a word pair = slot k)
+        lo_all, hi_all = np.full(3, np.inf), np.full(3, -np.inf)
+        rank = 0
+        for s in range(8):
+            meta = int(by[0, s])
+            qlo, qhi = by[1:4, s].astype(np.float64), by[4:7, s].astype(np.float64)
+            if meta == 0:
+                assert not (imask >> s) & 1 and np.all(qlo == 255) and np.all(qhi == 0)
+                continue
+            children += 1
+            blo, bhi = p + qlo * step, p + qhi * step
+            if (meta & 0x1f) >= 24:
+                assert (meta >> 5) == 1 and (meta & 0x1f) == 24 + s and (imask >> s) & 1
+                clo, chi = bounds(child_base + rank)
+                rank += 1
+            else:
+                assert not (imask >> s) & 1
+                cnt = {1: 1, 3: 2, 7: 3}[meta >> 5]
+                first = tri_base + (meta & 0x1f)
+                seen[prim_ids[first:first + cnt]] += 1
+                v = tv[first:first + cnt].reshape(-1, 3).astype(np.float64)
+                clo, chi = v.min(0), v.max(0)
+            assert np.all(blo <= clo) and np.all(bhi >= chi), (ni, s)
+            lo_all, hi_all = np.minimum(lo_all, clo), np.maximum(hi_all, chi)
+        assert rank == bin(imask).count("1")
+        return lo_all, hi_all
+    import sys
+    sys.setrecursionlimit(10000)
+    bounds(0)
+    assert np.all(seen == 1), "every triangle must be referenced by exactly one leaf slot"
+    return visited, children
+
+
+@pytest.mark.parametrize("name,small", [("c1", True), ("c2", False)])
+def test_bvh8_structure_and_ray_queries(ptb, ctx, oh, assets, name, small):
+    """ptb_build_cfg.bvh_width = 8: the quantised 8-wide tree is structurally valid and gives the brute-force hits bit for bit."""
+    if PIPELINE != 3:
+        pytest.skip("the BVH does not depend on the render pipeline")
+    sc = load_config(ptb, assets, name, small=small)
+    handle, st = ctx.accel_build(sc, ptb.default_build_cfg(bvh_width=8))
+    assert st.bvh_width == 8 and st.num_nodes8 > 0
+    nodes8, tris8 = ctx.accel_read8(handle)
+    visited, children = _check_bvh8(nodes8, tris8, sc.num_triangles)
+    assert visited == st.num_nodes8 == len(nodes8)
+    assert children / visited > 3.0, "the greedy collapse should fill most nodes"
+    osc = oh.OracleScene.from_ptb(sc, guard=False)
+    v = osc.vertices[:, :3]
+    lo, hi = v[:-6].min(0), v[:-6].max(0)
+    rng = np.random.default_rng(321)
+    o, d = random_rays(rng, 20000, lo, hi)
+    d[::7, 0] = 0.0          # axis-parallel rays: 1 / d = inf
+    d[3::11, 1] = -0.0
+    prim, t, b1, b2 = ctx.trace_rays(handle, o, d)
+    handle2, _ = ctx.accel_build(sc, ptb.default_build_cfg(bvh_width=2, max_leaf_size=3))
+    for a, b in zip((prim, t, b1, b2), ctx.trace_rays(handle2, o, d)):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    mism = 0
+    for i in range(0, len(o), 2 if name == "c1" else 20):
+        rp, rt, rb1, rb2 = oh.closest_hit("oracle", osc, o[i], d[i], use_bvh=0)
+        if rp != prim[i]:
+            mism += 1
+            continue
+        if rp >= 0:
+            assert np.float32(rt) == t[i] and np.float32(rb1) == b1[i] and np.float32(rb2) == b2[i]
+    assert mism == 0
+    assert (prim >= 0).mean() > 0.2
+
+
 @pytest.mark.parametrize("refine", [0, 1], ids=["lbvh", "lbvh+sah"])
 @pytest.mark.parametrize("name,small", [("c1", True), ("c2", False)])
 def test_bvh_structure_and_ray_queries(ptb, ctx, oh, assets, name, small, refine):
@@ -198,10 +284,13 @@ def test_bvh_builder_options(ptb, ctx, oh, assets):
     o, d = random_rays(rng, 4000, v[:-6].min(0), v[:-6].max(0))
     ref = None
     for kw in (dict(), dict(morton_bits=63), dict(treelet_size=32), dict(max_leaf_size=1), dict(max_leaf_size=8), dict(sah_refine=0, morton_bits=63),
-               dict(bvh_width=4), dict(bvh_width=4, sah_refine=0), dict(bvh_width=4, max_leaf_size=1), dict(bvh_width=2)):
+               dict(bvh_width=4), dict(bvh_width=4, sah_refine=0), dict(bvh_width=4, max_leaf_size=1), dict(bvh_width=2),
+               dict(bvh_width=8), dict(bvh_width=8, sah_refine=0), dict(bvh_width=8, max_leaf_size=1), dict(bvh_width=8, morton_bits=63, treelet_size=64)):
         handle, st = ctx.accel_build(sc, ptb.default_build_cfg(**kw))
         nodes, tris = ctx.accel_read(handle)
-        assert _check_bvh(nodes, tris, n, kw.get("max_leaf_size", 4)) == st.num_nodes, kw
+        leaf_cap = min(kw.get("max_leaf_size", 4), 3) if kw.get("bvh_width") == 8 else kw.get("max_leaf_size", 4)   # the 8-wide tree holds leaves of <= 3
+        assert _check_bvh(nodes, tris, n, leaf_cap) == st.num_nodes, kw
+        assert st.bvh_width == kw.get("bvh_width", 2), kw
         if kw.get("max_leaf_size", 4) != 1:  # with leaf size 1 the two floor triangles are two leaves under one node next to the root
             codes = nodes[0, 12:14].view(np.int32)
             leaf = [c for c in codes if c < 0]
@@ -342,18 +431,21 @@ def test_chunk_sizes_bit_identical(ptb, ctx, assets):
 
 
 def test_wide_bvh_render_bit_identical(ptb, ctx, oh, assets):
-    """4-wide traversal (the default for large scenes) against the 2-wide one and the oracle: same image, bit for bit."""
+    """4-wide traversal (the default for large scenes) and the 8-wide quantised one against the 2-wide one and the oracle: same
+    image, bit for bit."""
     if PIPELINE not in (1, 3, 4):
         pytest.skip("pipeline 2 shares the traversal code of pipeline 3")
     sc = load_config(ptb, assets, "c2")
     W, H = 160, 90
     kw = dict(spp_per_launch=3, max_depth=6)
     res = []
-    for width in (2, 4):
+    for width in (2, 4, 8):
         handle, st = ctx.accel_build(sc, ptb.default_build_cfg(bvh_width=width))
+        assert st.bvh_width == width
         a, f, h, stl = _render_gpu(ptb, ctx, handle, W, H, kw, camera="monkey_close")
         res.append((a.view(np.uint32), f, h, stl[0].segments))
-    assert all(np.array_equal(x, y) for x, y in zip(res[0][:3], res[1][:3])) and res[0][3] == res[1][3]
+    for other in res[1:]:
+        assert all(np.array_equal(x, y) for x, y in zip(res[0][:3], other[:3])) and res[0][3] == other[3]
     osc = oh.OracleScene.from_ptb(sc, guard=False)
     ca, cf, ch, cseg = _render_cpu(oh, ptb, osc, W, H, kw, camera="monkey_close")
     assert np.array_equal(res[1][0], ca.view(np.uint32)) and np.array_equal(res[1][2], ch) and res[1][3] == cseg

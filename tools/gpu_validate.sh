@@ -1,0 +1,10 @@
+#!/bin/bash
+# what the driver runs at round end, in small: GPU test suite, smoke(), the bench line
+mkdir -p gpurun_out
+( time python -m pytest tests -x -q -m gpu ) > gpurun_out/r2_validate_tests.log 2>&1; tail -4 gpurun_out/r2_validate_tests.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+python bench.py --steps 10 > gpurun_out/r2_validate_bench.json 2> gpurun_out/r2_validate_bench.err; echo "bench rc=$?"; python - <<'PY'
+import json
+d=json.load(open('gpurun_out/r2_validate_bench.json'))
+print({k:d[k] for k in ('value','ms_per_step','gpu_launches')}, d['e2e']['value'], d['other_arith']['value'], d['roofline']['frac'], d['roofline']['dram_frac'], d['clocks'])
+PY
