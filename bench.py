@@ -184,12 +184,14 @@ def main():
     ap.add_argument("--split", default="samples", choices=["samples", "tiles"],
                     help="N > 1: split the frame's subframes across ranks (weak scaling, default) or its rows (tile partitioning, strong scaling)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="N > 1: fused peer-memory exchange (default) or NCCL reduce")
+    ap.add_argument("--other-configs", default="default",
+                    help="comma list of the other BASELINE workloads timed briefly after the headline one and reported under \"configs\" "
+                         "(default: c2_close,c3,c4,c5 when --config is c2; \"none\" to skip)")
+    ap.add_argument("--other-steps", type=int, default=2, help="timed steps of each --other-configs workload (after 1 warm-up step)")
     args = ap.parse_args()
     select_config(args.config)
     if args.impl == "reference":
         return run_reference_arm(args)
-    if args.cpu_rows > H:
-        args.cpu_rows = H
 
     import torch
     import torch.distributed as dist
@@ -214,6 +216,34 @@ def main():
     if args.pipeline not in (2, 3):   # the fast build exists for the chunked pipelines only
         arith, other = "exact", None
 
+    others = []
+    if args.other_configs == "default":
+        others = ["c2_close", "c3", "c4", "c5"] if args.config == "c2" else []
+    elif args.other_configs != "none":
+        others = [c for c in args.other_configs.split(",") if c]
+    for c in others:
+        if c not in CONFIGS:
+            raise SystemExit(f"bench.py: unknown config {c!r} in --other-configs")
+
+    line = run_config(args, args.config, False, torch, dist, ptb, parallel, make_assets, CAMERAS, load_config, world, rank, local_rank, dev, ARITH, arith, other)
+    # the other BASELINE workloads (north_star: every named scene at 1 / 2 / 4 / 8 GPUs), same launch path, briefly
+    per_config = {}
+    for c in others:
+        select_config(c)
+        per_config[c] = run_config(args, c, True, torch, dist, ptb, parallel, make_assets, CAMERAS, load_config, world, rank, local_rank, dev, ARITH, arith, None)
+    if rank == 0:
+        if others:
+            line["configs"] = per_config
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def run_config(args, config_name, brief, torch, dist, ptb, parallel, make_assets, CAMERAS, load_config, world, rank, local_rank, dev, ARITH, arith, other):
+    """One workload on all ranks.  brief: only the headline timing (1 warm-up + --other-steps steps), returned as a small dict."""
+    cpu_rows = min(args.cpu_rows, H)
     ctx = ptb.Context(local_rank)
     if rank == 0:
         make_assets.ensure(SCENE)
@@ -314,6 +344,24 @@ def main():
     # ---- headline: weak scaling (64 spp per GPU), arithmetic mode `arith` ----
     total_subframes = LAUNCHES_PER_STEP * (1 if (tiles or not multi) else world)   # subframes in the frame all ranks produce together
     cfg = make_cfg(arith, tiled=tiles)
+    if brief:
+        k_b = max(1, args.other_steps)
+        bms, bseg, _ = timed(cfg, total_subframes, k_b, 1, tiled=tiles)
+        timed_out = bool(exchange.timed_out(stream)) if exchange is not None else False
+        if exchange is not None:
+            sync_all()
+            exchange.close()
+        del accum, frame
+        sc.close()
+        ctx.close()
+        out = {"workload": WORKLOAD, "value": bseg / (bms * 1e-3) / 1e6, "unit": "Msegments/s", "ms_per_step": bms / k_b, "steps": k_b, "warmup": 1,
+               "arith_mode": arith, "segments_per_step": bseg / k_b, "spp_per_step_per_gpu": SPP_PER_LAUNCH * LAUNCHES_PER_STEP,
+               "spp_per_s_1080p": SPP_PER_LAUNCH * total_subframes * k_b / (bms * 1e-3) * (W * H / (1920.0 * 1080.0)),
+               "scaling": "strong" if tiles else "weak",
+               "bvh": {"triangles": bst.num_triangles, "width": bst.bvh_width, "build_ms": bst.build_ms}}
+        if timed_out:
+            out["exchange_error"] = "a peer signal timed out: numbers of this workload are invalid"
+        return out
     ms_max, seg_total, clocks = timed(cfg, total_subframes, args.steps, args.warmup, tiled=tiles, sample_clocks=True)
     value = seg_total / (ms_max * 1e-3) / 1e6
     gpu_launches = int(ctx.launch_stats().kernel_launches) * args.steps + (3 * args.steps if multi else 0)
@@ -454,8 +502,9 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         import orchelp as oh
         osc = oh.OracleScene.from_ptb(sc, guard=True)
-        cpu_baseline, _ = cpu_reference_sample(oh, ptb, osc, args.cpu_rows)
+        cpu_baseline, _ = cpu_reference_sample(oh, ptb, osc, cpu_rows)
 
+    line = None
     if rank == 0:
         pool_gb = min(LAUNCHES_PER_STEP * W * H * 97, 2 << 30) / 1e9
         line = {
@@ -480,16 +529,15 @@ def main():
         }
         if timed_out:
             line["exchange_error"] = "a peer signal timed out (flag wait gave up after 4 s): numbers of this run are invalid"
-        print(json.dumps(line))
     if exchange is not None:
         torch.cuda.synchronize()
         if multi:
             dist.barrier()
         exchange.close()
-    if multi:
-        dist.barrier()
-        dist.destroy_process_group()
-    return 0
+    del accum, frame
+    sc.close()
+    ctx.close()
+    return line if rank == 0 else None
 
 
 if __name__ == "__main__":
