@@ -375,7 +375,9 @@ int ptb_device_alloc(ptb_context* ctx, size_t bytes, void** out);
 int ptb_device_free(ptb_context* ctx, void* p);
 int ptb_device_memset(ptb_context* ctx, void* p, int value, size_t bytes, void* stream);
 int ptb_copy_to_device(ptb_context* ctx, void* dst, const void* src, size_t bytes, void* stream);
-int ptb_copy_to_host(ptb_context* ctx, void* dst, const void* src, size_t bytes, void* stream);
+int ptb_copy_to_host(ptb_context* ctx, void* dst, const void* src, size_t bytes, void* stream);   /* returns when the copy has finished */
+/* the same without waiting: dst must be page-locked host memory; the caller orders it (stream / event / ptb_context_synchronize) */
+int ptb_copy_to_host_async(ptb_context* ctx, void* dst, const void* src, size_t bytes, void* stream);
 
 /* ---- image files: sutil::loadImage / sutil::saveImage (optixSphere.cpp:359, 836,
  *      1483-1489).  PNG (8/16-bit gray, gray+alpha, RGB, RGBA, palette) -> RGBA8 with

@@ -123,7 +123,7 @@ EXPORTS = [
     "ptb_camera_uvw", "ptb_params_default_camera", "ptb_default_render_cfg", "ptb_launch", "ptb_launch_get_stats", "ptb_launch_get_stage_ms", "ptb_context_get_totals",
     "ptb_resolve", "ptb_resolve_peers", "ptb_resolve_peers_accumulate", "ptb_resolve_peers_sync", "ptb_peer_flags_create", "ptb_peer_signal", "ptb_peer_wait", "ptb_peer_flags_error", "ptb_multi_create", "ptb_multi_destroy", "ptb_multi_device_count", "ptb_multi_context", "ptb_multi_stream", "ptb_multi_accel_build", "ptb_multi_launch", "ptb_multi_synchronize", "ptb_multi_get_totals", "ptb_ipc_export", "ptb_ipc_open", "ptb_ipc_close", "ptb_trace_rays", "ptb_output_create", "ptb_output_resize", "ptb_output_map", "ptb_output_unmap",
     "ptb_output_host_ptr", "ptb_output_width", "ptb_output_height", "ptb_output_destroy", "ptb_device_alloc",
-    "ptb_device_free", "ptb_device_memset", "ptb_copy_to_device", "ptb_copy_to_host", "ptb_image_load_rgba8",
+    "ptb_device_free", "ptb_device_memset", "ptb_copy_to_device", "ptb_copy_to_host", "ptb_copy_to_host_async", "ptb_image_load_rgba8",
     "ptb_image_load_float4", "ptb_save_image", "ptb_save_accum_raw", "ptb_load_accum_raw", "ptb_free", "ptb_obj_read", "ptb_microbench_read", "ptb_test_env_sample", "ptb_test_device_math",
 ]
 

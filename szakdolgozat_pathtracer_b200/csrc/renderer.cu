@@ -872,6 +872,12 @@ int ptb_copy_to_device(ptb_context* ctx, void* dst, const void* src, size_t byte
     CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
     return PTB_OK;
 }
+int ptb_copy_to_host_async(ptb_context* ctx, void* dst, const void* src, size_t bytes, void* stream) {
+    if (!ctx || !dst || !src) return fail(PTB_ERR_INVALID, "ptb_copy_to_host_async: bad arguments");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return PTB_OK;
+}
 int ptb_copy_to_host(ptb_context* ctx, void* dst, const void* src, size_t bytes, void* stream) {
     if (!ctx || !dst || !src) return fail(PTB_ERR_INVALID, "ptb_copy_to_host: bad arguments");
     CU(cudaSetDevice(ctx->device));
