@@ -47,9 +47,13 @@ namespace PTB_NS {
 #ifndef PTB_STATUS_SMEM          // 1: the fused kernel keeps its chunk's status bytes in shared memory: +1 % at 256 threads per block,
 #define PTB_STATUS_SMEM (!PTB_FAST)  // -1.7 % at 128 (eight blocks' worth of shared memory takes the next L1 carve-out step)
 #endif
-#ifndef PTB_MINB_WIDE
-#define PTB_MINB_WIDE 8          // fused kernel, launches that fill the chip: resident 128-thread units per SM the register
-#endif                           // budget is sized for (8 -> 64 registers, 10 -> 51, 12 -> 42)
+#ifndef PTB_MINB_WIDE            // fused kernel, launches that fill the chip: resident 128-thread units per SM the register budget
+#if PTB_FAST                     // is sized for (8 -> 64 registers, 9 -> 56, 10 -> 48; the exact build's 256-thread blocks: 8 -> 64).
+#define PTB_MINB_WIDE 9          // Measured with the early-store / late-load shade stage: fast 9 > 8 > 10 (18.39 / 18.66 / 19.03 ms),
+#else                            // exact 8 > 10 > 9 (23.37 / 23.94 / 24.11 ms)
+#define PTB_MINB_WIDE 8
+#endif
+#endif
 // The chunk helpers are templates on SPT = slots per thread (chunk = PTB_CHUNK_THREADS * SPT slots): the fused kernel uses
 // smaller chunks for small launches (a 600 x 400 frame has 117 chunks of 2048 slots -- less than one block per SM -- but
 // 938 chunks of 256), everything else uses the default through the aliases below.
@@ -271,14 +275,26 @@ PTB_DEV void chunk_stage_shade_miss(ChunkSharedT<SPT>& sh, const SceneView& s, c
 #endif
         const bool is_hit = i < n_hit;
         const uint32_t slot = base + sh.list[is_hit ? i : ChunkSharedT<SPT>::CHUNK - total + i];
-        const float4 d4 = ldp(&p.ray_d[slot]), as = ldp(&p.atten_seed[slot]);
-        const uint4 mi = ldp(&p.misc[slot]);
+        // Hits: only the words the hit shader needs are read up front (payload seed, depth); the attenuation and the raygen-side
+        // words are read AFTER it and applied to what it returns for an attenuation of 1 (x * 1 and 0 + x are exact, so the
+        // values are the same).  With the bounce ray stored early (closest_hit<true>) this takes ~12 live values out of the BSDF
+        // code: spills of the 64-register build 200 -> 76 B stores, 116 -> 52 B loads; +1 % fast, +4 % exact, and the fast build
+        // then runs best at 56 registers / 9 blocks per SM (PTB_MINB_WIDE): +2.3 to +3.6 % in total (profiles/r2_experiments.md).
+        const float4 d4 = ldp(&p.ray_d[slot]);
+        float4 as; uint4 mi;
         Bounce b;
-        b.atten = mk3(as); b.seed = __float_as_uint(as.w);
         if (is_hit) {
+            b.seed = __ldcs(reinterpret_cast<const unsigned int*>(&p.atten_seed[slot]) + 3);
+            const int depth_h = (int)__ldcs(reinterpret_cast<const unsigned int*>(&p.misc[slot]) + 1);
+            b.atten = mk3(1.0f);
             const float4 o4 = ldp(&p.ray_o[slot]), h4 = ldp(&p.hit[slot]);
-            closest_hit(s, f, __float_as_int(h4.w), h4.y, h4.z, h4.x, mk3(o4), mk3(d4), (int)mi.y, b);
+            closest_hit<true>(s, f, __float_as_int(h4.w), h4.y, h4.z, h4.x, mk3(o4), mk3(d4), depth_h, b, &p.ray_o[slot], &p.ray_d[slot]);
+            as = ldp(&p.atten_seed[slot]); mi = ldp(&p.misc[slot]);
+            b.atten = mk3(as) * b.atten;
+            b.radiance = mk3(as) * b.radiance;
         } else {
+            as = ldp(&p.atten_seed[slot]); mi = ldp(&p.misc[slot]);
+            b.atten = mk3(as); b.seed = __float_as_uint(as.w);
             const float3 ray_dir = normalize(mk3(d4));
             const float u = 0.5f + AR_DIVC(det_atan2f(ray_dir.z, ray_dir.x), 2.0f * PTB_PI_F);
             const float v = 0.5f - AR_DIVC(det_asinf(ray_dir.y), PTB_PI_F);
@@ -287,7 +303,7 @@ PTB_DEV void chunk_stage_shade_miss(ChunkSharedT<SPT>& sh, const SceneView& s, c
             b.origin = mk3(0.0f); b.direction = mk3(0.0f);
             b.done = 1;
         }
-        const int next = after_segment(f, p, slot, b, mi.x, (int)mi.y, mi.z);
+        const int next = after_segment<true>(f, p, slot, b, mi.x, (int)mi.y, mi.z);
         status[slot - sbase] = next == 0 ? ST_DONE : (next == 2 && mark_new ? ST_TRACE_NEW : ST_TRACE);
     }
 }

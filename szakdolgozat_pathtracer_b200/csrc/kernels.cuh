@@ -350,8 +350,12 @@ struct Bounce {
 };
 
 // __closesthit__radiance (cu:616-871); the glass branch cu:803-856 lives in glass_bounce.
+// EARLY (the fused kernel): the hit position and the bounce direction are stored as the slot's next ray the moment they are known
+// (early_origin / early_dir = &ray_o[slot], &ray_d[slot]) instead of being carried to after_segment: six values less that are
+// live through the BSDF code.  A path that ends here overwrites them with its next camera ray or abandons them.
+template <bool EARLY = false>
 PTB_DEV void closest_hit(const SceneView& s, const FrameView& f, int prim_idx, float b1, float b2, float t_hit,
-                         float3 ray_orig, float3 ray_dir, int depth, Bounce& io) {
+                         float3 ray_orig, float3 ray_dir, int depth, Bounce& io, float4* early_origin = nullptr, float4* early_dir = nullptr) {
     const DevMaterial& m = s.mats[__ldg(s.mat_ids + prim_idx)];
     const size_t vo = (size_t)prim_idx * 3;
 
@@ -373,6 +377,7 @@ PTB_DEV void closest_hit(const SceneView& s, const FrameView& f, int prim_idx, f
     }
 
     const float3 hit_pos = ray_orig + t_hit * ray_dir;
+    if (EARLY) stp(early_origin, make_float4(hit_pos.x, hit_pos.y, hit_pos.z, 0.0f));
     uint32_t seed = io.seed;
 
     // setMaterialProperty x 4 (cu:682-714).  ONE copy of the bilinear fetch in the instruction stream, run up to four
@@ -459,6 +464,7 @@ PTB_DEV void closest_hit(const SceneView& s, const FrameView& f, int prim_idx, f
     const float dpdf = 1.0f / PTB_PI_F;
     if (myrnd(seed) < specular_probability) io.direction = light_dir_n;
     else io.direction = normalize(onb.inverse_transform(cosine_sample_hemisphere(r1, r2)));
+    if (EARLY && !m.transparent) stp(early_dir, make_float4(io.direction.x, io.direction.y, io.direction.z, 0.0f));
 #if PTB_FAST
     const float3 brdf = specular_probability * (brdf_specular / spdf) + (1.0f - specular_probability) * (diffuse_albedo * PTB_PI_F);
     (void)dpdf;
@@ -469,25 +475,28 @@ PTB_DEV void closest_hit(const SceneView& s, const FrameView& f, int prim_idx, f
     if (m.transparent) {  // cu:803-856; kept out of line: no scene of the reference reaches it (see glass_bounce)
         const GlassOut g = glass_bounce(normal, ray_dir, ior, alpha, r1, r2, seed);
         io.direction = g.direction;
-        io.origin = hit_pos;
+        if (EARLY) stp(early_dir, make_float4(io.direction.x, io.direction.y, io.direction.z, 0.0f));
+        if (!EARLY) io.origin = hit_pos;
         io.seed = g.seed;
         return;
     }
     if (length(brdf) >= 1e-10f) io.atten = io.atten * (brdf * IdotN);
-    io.origin = hit_pos;
+    if (!EARLY) io.origin = hit_pos;
     io.seed = seed;
 }
 
 // Raygen side after a segment (cu:376-395) plus path regeneration.  Returns 0 when the slot has finished its samples,
 // 1 when it continues with a bounce ray, 2 when it starts the camera ray of its next sample.
+// EARLY: the bounce ray is in the pool already (closest_hit<true>).
+template <bool EARLY = false>
 PTB_DEV int after_segment(const FrameView& f, const PathView& p, uint32_t slot, const Bounce& b, uint32_t seed_rg,
                            int depth, uint32_t sample) {
     const float pr = fmaxf(b.atten.x, fmaxf(b.atten.y, b.atten.z));
     bool done = b.done != 0;
     if (!done) done = myrnd(seed_rg) > pr;  // short-circuit: no draw when payload.done
     if (!done) {
-        stp(&p.ray_o[slot], make_float4(b.origin.x, b.origin.y, b.origin.z, 0.0f));
-        stp(&p.ray_d[slot], make_float4(b.direction.x, b.direction.y, b.direction.z, 0.0f));
+        if (!EARLY) stp(&p.ray_o[slot], make_float4(b.origin.x, b.origin.y, b.origin.z, 0.0f));
+        if (!EARLY) stp(&p.ray_d[slot], make_float4(b.direction.x, b.direction.y, b.direction.z, 0.0f));
         stp(&p.atten_seed[slot], make_float4(b.atten.x, b.atten.y, b.atten.z, __uint_as_float(b.seed)));
         stp(&p.misc[slot], make_uint4(seed_rg, (uint32_t)(depth - 1), sample, 0u));
         return 1;
