@@ -166,6 +166,17 @@ typedef struct ptb_render_cfg {
     int64_t max_pool_bytes;   /* bound of the path-state pool (97 B per resident path slot); 0 = 2 GiB.  A launch of
                                  subframes_per_launch * W * H slots that would exceed it is rendered as consecutive batches
                                  of subframes inside ptb_launch(): same result bit for bit, bounded memory. */
+    int32_t overlap_lanes;    /* consecutive SMALL launches (the reference's render loop issues one subframe of 600x400 .. 1600x1200
+                                 pixels per optixLaunch, optixSphere.cpp:1390-1437) end in a long thin tail: every pixel's samples
+                                 are one sequential chain.  0 (default) = automatic: in the reference's accumulate mode (accumulate_mode
+                                 0) a single-subframe launch of the default pipeline with fewer than 9 M path slots renders on one
+                                 of 4 internal streams with its own path pool, so that the tail of launch k overlaps the start of
+                                 launch k + 1 (600x400: 2.15 -> 0.73 ms per launch); the accumulate / tonemap stage stays on the
+                                 caller's stream, in call order -- buffers and results are exactly those of serial launches.
+                                 1 = off; 2..4 = that many lanes (any accumulate mode).  The render of such a launch does not wait for
+                                 work the caller enqueued on `stream` before the call (only the accumulate stage does); launches
+                                 with aux_primary_hit, counters, stage profiling or stream capture never overlap. */
+    int32_t reserved0;
 } ptb_render_cfg;
 
 typedef struct ptb_launch_stats {

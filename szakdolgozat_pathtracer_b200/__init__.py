@@ -79,6 +79,7 @@ class RenderCfg(C.Structure):
         ("accumulate_mode", C.c_int32), ("write_frame", C.c_int32), ("env_importance_sampling", C.c_int32),
         ("count_traversal", C.c_int32), ("profile_stages", C.c_int32), ("subframes_per_launch", C.c_int32), ("pipeline", C.c_int32), ("row_begin", C.c_int32), ("row_end", C.c_int32), ("row_interleave_count", C.c_int32), ("row_interleave_index", C.c_int32),
         ("row_interleave_height", C.c_int32), ("aux_primary_hit", C.c_void_p), ("chunk_slots_per_thread", C.c_int32), ("arith_mode", C.c_int32), ("max_pool_bytes", C.c_int64),
+        ("overlap_lanes", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 

@@ -93,7 +93,41 @@ struct ptb_context {
     uint32_t prof_iters = 0;  // iterations of the last profiled launch, 0 = none
     std::map<unsigned long long, DeviceScene*> scenes;
     unsigned long long next_handle = 1;
+    // launch overlap (ptb_render_cfg.overlap_lanes): lane 0's path pool is the members above, lanes 1.. keep theirs here and
+    // are swapped in for the duration of a ptb_launch call (LaneGuard); every lane has its render stream and two events
+    struct LanePool {
+        uint32_t pool_slots = 0;
+        float4 *ray_o = nullptr, *ray_d = nullptr, *hit = nullptr, *atten_seed = nullptr, *pixsum = nullptr;
+        uint4* misc = nullptr;
+        uint32_t *q_trace[2] = {nullptr, nullptr}, *q_hit = nullptr, *q_miss = nullptr;
+        uint32_t* counters = nullptr; uint32_t counters_cap = 0;
+        unsigned long long *trav_stats = nullptr, *launch_totals = nullptr;
+        unsigned char* status = nullptr;
+    };
+    struct LaneSync { cudaStream_t stream = nullptr; cudaEvent_t render_done = nullptr, resolve_done = nullptr; bool used = false; };
+    LanePool extra_lanes[3];
+    LaneSync lane_sync[4];
+    int next_lane = 0, last_lane = 0;
 };
+
+namespace {
+// exchanges the path pool of lane `lane` (> 0) with the context's own members; a second call swaps back
+void swap_lane(ptb_context* c, int lane) {
+    if (lane <= 0) return;
+    ptb_context::LanePool& l = c->extra_lanes[lane - 1];
+    std::swap(c->pool_slots, l.pool_slots);
+    std::swap(c->ray_o, l.ray_o); std::swap(c->ray_d, l.ray_d); std::swap(c->hit, l.hit); std::swap(c->atten_seed, l.atten_seed);
+    std::swap(c->pixsum, l.pixsum); std::swap(c->misc, l.misc);
+    std::swap(c->q_trace[0], l.q_trace[0]); std::swap(c->q_trace[1], l.q_trace[1]); std::swap(c->q_hit, l.q_hit); std::swap(c->q_miss, l.q_miss);
+    std::swap(c->counters, l.counters); std::swap(c->counters_cap, l.counters_cap);
+    std::swap(c->trav_stats, l.trav_stats); std::swap(c->launch_totals, l.launch_totals); std::swap(c->status, l.status);
+}
+struct LaneGuard {
+    ptb_context* c; int lane;
+    LaneGuard(ptb_context* c_, int lane_) : c(c_), lane(lane_) { swap_lane(c, lane); }
+    ~LaneGuard() { swap_lane(c, lane); }
+};
+}  // namespace
 
 struct ptb_output {
     ptb_context* ctx = nullptr;
@@ -207,6 +241,18 @@ void ptb_context_destroy(ptb_context* ctx) {
     cudaDeviceSynchronize();
     // scenes stay owned by their ptb_scene; just detach them
     for (auto& kv : ctx->scenes) kv.second->owner = nullptr;
+    for (int lane = 1; lane < 4; ++lane) {   // the extra lanes' pools
+        swap_lane(ctx, lane);
+        free_pool(ctx);
+        cudaFree(ctx->counters); cudaFree(ctx->trav_stats); cudaFree(ctx->launch_totals);
+        ctx->counters = nullptr; ctx->counters_cap = 0; ctx->trav_stats = nullptr; ctx->launch_totals = nullptr;
+        swap_lane(ctx, lane);
+    }
+    for (auto& l : ctx->lane_sync) {
+        if (l.stream) cudaStreamDestroy(l.stream);
+        if (l.render_done) cudaEventDestroy(l.render_done);
+        if (l.resolve_done) cudaEventDestroy(l.resolve_done);
+    }
     free_pool(ctx);
     cudaFree(ctx->counters); cudaFree(ctx->trav_stats); cudaFree(ctx->totals); cudaFree(ctx->launch_totals);
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
@@ -464,6 +510,34 @@ int ptb_launch(ptb_context* ctx, const ptb_Params* P, const ptb_render_cfg* cfg_
     const uint32_t pool_cap = (uint32_t)ctx->num_sms * (pool_wide ? 1024u / PTB_CHUNK_THREADS : 640u / PTB_CHUNK_THREADS);
     const uint32_t pool_grid = pool_blocks_needed < pool_cap ? pool_blocks_needed : pool_cap;
     const bool use_pool = pipeline == PTB_PIPELINE_POOL_FUSED;
+
+    // Launch overlap (ptb_render_cfg.overlap_lanes): a small single-subframe launch renders on one of the context's internal
+    // streams with that lane's own path pool, so that its thin tail (every pixel's samples are one sequential chain) runs beside
+    // the start of the next launch; accumulate / tonemap (k_resolve) and the counter fold stay on the caller's stream in call
+    // order.  Same kernels, same buffers, same results.
+    // automatic: four lanes for the reference's own accumulate mode (the viewer loop); the sum mode of the multi-GPU exchanges
+    // keeps serial launches unless the caller asks for lanes
+    const int n_lanes = cfg.overlap_lanes == 0 ? (cfg.accumulate_mode == 0 ? 4 : 1) : cfg.overlap_lanes;
+    if (n_lanes < 1 || n_lanes > 4) return fail(PTB_ERR_INVALID, "ptb_launch: overlap_lanes must be 0 (automatic), 1 (off), 2, 3 or 4");
+    bool overlap = n_lanes > 1 && pipeline == PTB_PIPELINE_CHUNK_FUSED && n_sub == 1 && slots < 9000000u && !cfg.profile_stages &&
+                   !cfg.count_traversal && !cfg.aux_primary_hit && !cfg.env_importance_sampling && !ctx->keep_launch_totals && !ctx->defer_fold;
+    if (overlap) {
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) { cudaGetLastError(); overlap = false; }
+    }
+    int lane = 0;
+    if (overlap) { lane = ctx->next_lane % n_lanes; ctx->next_lane = (lane + 1) % n_lanes; }
+    ptb_context::LaneSync& ls = ctx->lane_sync[lane];
+    if (!ls.resolve_done) {
+        CU(cudaEventCreateWithFlags(&ls.render_done, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ls.resolve_done, cudaEventDisableTiming));
+    }
+    if (overlap && !ls.stream) CU(cudaStreamCreateWithFlags(&ls.stream, cudaStreamNonBlocking));
+    const cudaStream_t rst = overlap ? ls.stream : st;   // where the path tracing of this launch runs
+    LaneGuard lane_guard(ctx, lane);                      // lanes 1.. bring their own pool for the duration of this call
+    // the lane's previous accumulate stage (on whatever stream it ran) has to be done with the pool before it is overwritten
+    if (ls.used) CU(cudaStreamWaitEvent(rst, ls.resolve_done, 0));
+
     int rc = ensure_pool(ctx, use_pool ? pool_grid * PTB_CHUNK : slots, iters);
     if (rc != PTB_OK) return rc;
     if (use_pool && slots > ctx->out_pixsum_slots) {
@@ -498,17 +572,17 @@ int ptb_launch(ptb_context* ctx, const ptb_Params* P, const ptb_render_cfg* cfg_
     q.counters = ctx->counters; q.trav_stats = ctx->trav_stats;
     const SceneView s = scene_view(d);
 
-    CU(cudaMemsetAsync(ctx->counters, 0, (size_t)(iters + 2) * 4 * sizeof(uint32_t), st));
+    CU(cudaMemsetAsync(ctx->counters, 0, (size_t)(iters + 2) * 4 * sizeof(uint32_t), rst));
     if (!ctx->keep_launch_totals) {  // later batches of one launch add to the counters of the first
-        CU(cudaMemsetAsync(ctx->trav_stats, 0, 2 * sizeof(unsigned long long), st));
-        CU(cudaMemsetAsync(ctx->launch_totals, 0, 4 * sizeof(unsigned long long), st));
+        CU(cudaMemsetAsync(ctx->trav_stats, 0, 2 * sizeof(unsigned long long), rst));
+        CU(cudaMemsetAsync(ctx->launch_totals, 0, 4 * sizeof(unsigned long long), rst));
     }
     const uint32_t pix_blocks = (slots + 255u) / 256u;
     const bool prof = cfg.profile_stages != 0;
     if (prof) {
         const size_t need_ev = (size_t)iters * 3 + 4;
         while (ctx->events.size() < need_ev) { cudaEvent_t e; CU(cudaEventCreate(&e)); ctx->events.push_back(e); }
-        CU(cudaEventRecord(ctx->events[0], st));
+        CU(cudaEventRecord(ctx->events[0], rst));
     }
     ctx->prof_iters = 0;
     ctx->stage_sum_valid = false;
@@ -523,30 +597,30 @@ int ptb_launch(ptb_context* ctx, const ptb_Params* P, const ptb_render_cfg* cfg_
             CU(cudaMalloc((void**)&ctx->shadow_c, (size_t)slots * 16)); CU(cudaMalloc((void**)&ctx->shadow_flag, (size_t)slots + 64));
             ctx->shadow_slots = slots;
         }
-        CU(cudaMemsetAsync(ctx->shadow_flag, 0, (size_t)slots + 64, st));
+        CU(cudaMemsetAsync(ctx->shadow_flag, 0, (size_t)slots + 64, rst));
         LinearView lv;
         lv.cdf.marginal = d->cdf_marginal; lv.cdf.conditional = d->cdf_conditional; lv.cdf.row_weight = d->cdf_row_weight;
         lv.cdf.total = d->cdf_total; lv.cdf.w = d->env_w; lv.cdf.h = d->env_h;
         lv.shadow_o = ctx->shadow_o; lv.shadow_d = ctx->shadow_d; lv.shadow_c = ctx->shadow_c; lv.shadow_flag = ctx->shadow_flag;
         lv.nee = cfg.env_importance_sampling == 1 ? 1 : 0;
         const uint32_t chunks = (slots + PTB_CHUNK - 1u) / PTB_CHUNK;
-        k_chunk_raygen<<<pix_blocks, 256, 0, st>>>(f, p, ctx->status);
-        if (prof) CU(cudaEventRecord(ctx->events[1], st));
+        k_chunk_raygen<<<pix_blocks, 256, 0, rst>>>(f, p, ctx->status);
+        if (prof) CU(cudaEventRecord(ctx->events[1], rst));
         launches = 1;
         for (uint32_t it = 0; it < iters; ++it) {
-            k_chunk_trace<false, PTB_TRACE_QUANTUM><<<chunks, PTB_CHUNK_THREADS, 0, st>>>(s, f, p, ctx->status, ctx->launch_totals, ctx->trav_stats, (int)it);
-            if (prof) CU(cudaEventRecord(ctx->events[2 + (size_t)it * 3 + 0], st));
-            k_chunk_shade_linear<<<chunks, PTB_CHUNK_THREADS, 0, st>>>(s, f, p, lv, ctx->status);
-            if (lv.nee) { k_chunk_shadow<<<chunks, PTB_CHUNK_THREADS, 0, st>>>(s, f, p, lv); launches += 1; }
-            if (prof) CU(cudaEventRecord(ctx->events[2 + (size_t)it * 3 + 1], st));
-            k_chunk_miss_linear<<<chunks, PTB_CHUNK_THREADS, 0, st>>>(s, f, p, lv, ctx->status);
-            if (prof) CU(cudaEventRecord(ctx->events[2 + (size_t)it * 3 + 2], st));
+            k_chunk_trace<false, PTB_TRACE_QUANTUM><<<chunks, PTB_CHUNK_THREADS, 0, rst>>>(s, f, p, ctx->status, ctx->launch_totals, ctx->trav_stats, (int)it);
+            if (prof) CU(cudaEventRecord(ctx->events[2 + (size_t)it * 3 + 0], rst));
+            k_chunk_shade_linear<<<chunks, PTB_CHUNK_THREADS, 0, rst>>>(s, f, p, lv, ctx->status);
+            if (lv.nee) { k_chunk_shadow<<<chunks, PTB_CHUNK_THREADS, 0, rst>>>(s, f, p, lv); launches += 1; }
+            if (prof) CU(cudaEventRecord(ctx->events[2 + (size_t)it * 3 + 1], rst));
+            k_chunk_miss_linear<<<chunks, PTB_CHUNK_THREADS, 0, rst>>>(s, f, p, lv, ctx->status);
+            if (prof) CU(cudaEventRecord(ctx->events[2 + (size_t)it * 3 + 2], rst));
             launches += 3;
         }
     } else if (pipeline == PTB_PIPELINE_QUEUES) {
         // global queues, one kernel per stage and iteration (kernels.cuh)
-        k_raygen_init<<<pix_blocks, 256, 0, st>>>(f, p, q);
-        if (prof) CU(cudaEventRecord(ctx->events[1], st));
+        k_raygen_init<<<pix_blocks, 256, 0, rst>>>(f, p, q);
+        if (prof) CU(cudaEventRecord(ctx->events[1], rst));
         const uint32_t need = (slots + 127u) / 128u;
         const uint32_t cap = (uint32_t)ctx->num_sms * 32u;
         const uint32_t grid = need < cap ? need : cap;
@@ -554,16 +628,16 @@ int ptb_launch(ptb_context* ctx, const ptb_Params* P, const ptb_render_cfg* cfg_
         const uint32_t tgrid = need < tcap ? need : tcap;
         launches = 1;
         for (uint32_t it = 0; it < iters; ++it) {
-            if (cfg.count_traversal) k_trace<true, PTB_TRACE_QUANTUM><<<tgrid, 128, 0, st>>>(s, f, p, q, (int)it);
-            else k_trace<false, PTB_TRACE_QUANTUM><<<tgrid, 128, 0, st>>>(s, f, p, q, (int)it);
-            if (prof) CU(cudaEventRecord(ctx->events[2 + (size_t)it * 3 + 0], st));
-            k_shade<<<grid, 128, 0, st>>>(s, f, p, q, (int)it);
-            if (prof) CU(cudaEventRecord(ctx->events[2 + (size_t)it * 3 + 1], st));
-            k_miss<<<grid, 128, 0, st>>>(s, f, p, q, (int)it);
-            if (prof) CU(cudaEventRecord(ctx->events[2 + (size_t)it * 3 + 2], st));
+            if (cfg.count_traversal) k_trace<true, PTB_TRACE_QUANTUM><<<tgrid, 128, 0, rst>>>(s, f, p, q, (int)it);
+            else k_trace<false, PTB_TRACE_QUANTUM><<<tgrid, 128, 0, rst>>>(s, f, p, q, (int)it);
+            if (prof) CU(cudaEventRecord(ctx->events[2 + (size_t)it * 3 + 0], rst));
+            k_shade<<<grid, 128, 0, rst>>>(s, f, p, q, (int)it);
+            if (prof) CU(cudaEventRecord(ctx->events[2 + (size_t)it * 3 + 1], rst));
+            k_miss<<<grid, 128, 0, rst>>>(s, f, p, q, (int)it);
+            if (prof) CU(cudaEventRecord(ctx->events[2 + (size_t)it * 3 + 2], rst));
             launches += 3;
         }
-        k_fold_counters<<<1, 256, 0, st>>>(ctx->counters, iters, ctx->launch_totals);
+        k_fold_counters<<<1, 256, 0, rst>>>(ctx->counters, iters, ctx->launch_totals);
         launches += 1;
     } else if (use_pool) {
         // persistent block-local wavefront (pool.cuh): one kernel, camera rays included
@@ -572,14 +646,14 @@ int ptb_launch(ptb_context* ctx, const ptb_Params* P, const ptb_render_cfg* cfg_
         pv.out_pixsum = ctx->out_pixsum; pv.next_slot = max_iters + 1;  // both words zeroed by the memset above
         pv.n_slots = slots; pv.grid = pool_grid;
         PathView ps = p; ps.n_slots = pool_grid * PTB_CHUNK;
-        if (prof) CU(cudaEventRecord(ctx->events[1], st));  // no separate raygen kernel
-        if (cfg.count_traversal) k_pool_fused<true, PTB_TRACE_QUANTUM, 5><<<pool_grid, PTB_CHUNK_THREADS, 0, st>>>(s, f, ps, pv, ctx->launch_totals, ctx->trav_stats, max_iters);
-        else if (pool_wide) k_pool_fused<false, PTB_TRACE_QUANTUM, 8><<<pool_grid, PTB_CHUNK_THREADS, 0, st>>>(s, f, ps, pv, ctx->launch_totals, ctx->trav_stats, max_iters);
-        else k_pool_fused<false, PTB_TRACE_QUANTUM, 5><<<pool_grid, PTB_CHUNK_THREADS, 0, st>>>(s, f, ps, pv, ctx->launch_totals, ctx->trav_stats, max_iters);
+        if (prof) CU(cudaEventRecord(ctx->events[1], rst));  // no separate raygen kernel
+        if (cfg.count_traversal) k_pool_fused<true, PTB_TRACE_QUANTUM, 5><<<pool_grid, PTB_CHUNK_THREADS, 0, rst>>>(s, f, ps, pv, ctx->launch_totals, ctx->trav_stats, max_iters);
+        else if (pool_wide) k_pool_fused<false, PTB_TRACE_QUANTUM, 8><<<pool_grid, PTB_CHUNK_THREADS, 0, rst>>>(s, f, ps, pv, ctx->launch_totals, ctx->trav_stats, max_iters);
+        else k_pool_fused<false, PTB_TRACE_QUANTUM, 5><<<pool_grid, PTB_CHUNK_THREADS, 0, rst>>>(s, f, ps, pv, ctx->launch_totals, ctx->trav_stats, max_iters);
         launches = 1;
         prof_iters = 0;
         if (prof) {
-            CU(cudaEventRecord(ctx->events[2], st)); CU(cudaEventRecord(ctx->events[3], st)); CU(cudaEventRecord(ctx->events[4], st));
+            CU(cudaEventRecord(ctx->events[2], rst)); CU(cudaEventRecord(ctx->events[3], rst)); CU(cudaEventRecord(ctx->events[4], rst));
             prof_iters = 1;
         }
         p.pixsum = ctx->out_pixsum;  // what k_resolve folds
@@ -598,30 +672,34 @@ int ptb_launch(ptb_context* ctx, const ptb_Params* P, const ptb_render_cfg* cfg_
         if (fast) {
             fa.s = s; fa.f = f; fa.p = p; fa.status = cl.status; fa.totals = cl.totals; fa.trav_stats = cl.trav_stats; fa.max_iters = cl.max_iters;
             fa.num_sms = cl.num_sms; fa.spt_request = cl.spt_request; fa.count = cl.count;
-            ptb_fast_api::raygen(fa, st);
-        } else launch_chunk_raygen(cl, st);
-        if (prof) CU(cudaEventRecord(ctx->events[1], st));
+            ptb_fast_api::raygen(fa, rst);
+        } else launch_chunk_raygen(cl, rst);
+        if (prof) CU(cudaEventRecord(ctx->events[1], rst));
         launches = 1;
         if (pipeline == PTB_PIPELINE_CHUNK_STAGES) {
             for (uint32_t it = 0; it < iters; ++it) {
                 for (int stage = 0; stage < 3; ++stage) {
-                    if (fast) ptb_fast_api::stage(fa, stage, (int)it, st); else launch_chunk_stage(cl, stage, (int)it, st);
-                    if (prof) CU(cudaEventRecord(ctx->events[2 + (size_t)it * 3 + stage], st));
+                    if (fast) ptb_fast_api::stage(fa, stage, (int)it, rst); else launch_chunk_stage(cl, stage, (int)it, rst);
+                    if (prof) CU(cudaEventRecord(ctx->events[2 + (size_t)it * 3 + stage], rst));
                 }
                 launches += 3;
             }
         } else {
-            if (fast) ptb_fast_api::fused(fa, st); else launch_chunk_fused(cl, st);
+            if (fast) ptb_fast_api::fused(fa, rst); else launch_chunk_fused(cl, rst);
             launches += 1;
             prof_iters = 0;
             if (prof) {  // a single kernel: everything between raygen and resolve is reported as "trace"
-                CU(cudaEventRecord(ctx->events[2], st)); CU(cudaEventRecord(ctx->events[3], st)); CU(cudaEventRecord(ctx->events[4], st));
+                CU(cudaEventRecord(ctx->events[2], rst)); CU(cudaEventRecord(ctx->events[3], rst)); CU(cudaEventRecord(ctx->events[4], rst));
                 prof_iters = 1;
             }
         }
     }
+    if (overlap) { CU(cudaEventRecord(ls.render_done, rst)); CU(cudaStreamWaitEvent(st, ls.render_done, 0)); }
     k_resolve<<<(n_pixels + 255u) / 256u, 256, 0, st>>>(f, p);
     if (!ctx->defer_fold) k_fold_totals<<<1, 32, 0, st>>>(ctx->launch_totals, ctx->totals);
+    CU(cudaEventRecord(ls.resolve_done, st));
+    ls.used = true;
+    ctx->last_lane = lane;
     launches += 2;
     if (prof) { CU(cudaEventRecord(ctx->events[2 + (size_t)prof_iters * 3], st)); ctx->prof_iters = prof_iters; }
     CU(cudaGetLastError());
@@ -636,6 +714,7 @@ int ptb_launch_get_stats(ptb_context* ctx, ptb_launch_stats* out) {
     memset(out, 0, sizeof(*out));
     if (!ctx->last_iters) return fail(PTB_ERR_INVALID, "ptb_launch_get_stats: no launch yet");
     CU(cudaSetDevice(ctx->device));
+    LaneGuard lane_guard(ctx, ctx->last_lane);   // the counters of the lane the last launch ran on
     std::vector<uint32_t> h((size_t)(ctx->last_iters + 1) * 4);
     CU(cudaMemcpyAsync(h.data(), ctx->counters, h.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->last_stream));
     unsigned long long tv[2] = {0, 0}, lt[4] = {0, 0, 0, 0};

@@ -176,6 +176,55 @@ def test_bounded_pool_batches_bit_identical(ptb, ctx, assets):
     assert res[0][3][3] == n * 3 * 7 and res[0][3][0] > res[0][3][3]
 
 
+@pytest.mark.parametrize("arith", [0, 1], ids=["exact", "fast"])
+def test_overlapped_launches_equal_serial_launches(ptb, ctx, assets, arith):
+    """ptb_render_cfg.overlap_lanes: the reference's render loop (one subframe per launch, running average, tonemapped frame,
+    optixSphere.cpp:1390-1437) with launches overlapping on the context's internal lanes (0 = automatic, 2, 4) against strictly
+    serial launches (1): accumulation buffer, frame, per-launch statistics and context totals identical; also when the caller
+    clears or reads the buffers between launches on its stream."""
+    from scenes import CAMERAS
+    sc = load_config(ptb, assets, "c2")
+    handle, _ = ctx.accel_build(sc)
+    W, H, N = 320, 200, 9
+    n = W * H
+    results = []
+    for lanes in (1, 0, 2, 4):
+        d_accum, d_frame = ctx.alloc(n * 16), ctx.alloc(n * 4)
+        try:
+            ctx.memset(d_accum, 0, n * 16)
+            ctx.totals(reset=True)
+            cfg = ptb.default_render_cfg(spp_per_launch=3, max_depth=6, arith_mode=arith, overlap_lanes=lanes)
+            seg, mids = [], []
+            for k in range(N):
+                p = ptb.make_params(W, H, subframe_index=k, dof=True, **CAMERAS["monkey_close"])
+                p.accum_buffer, p.frame_buffer, p.handle = d_accum, d_frame, handle
+                ctx.launch(p, cfg)
+                if k in (2, 5):
+                    st = ctx.launch_stats()      # synchronises: statistics of THIS launch, whatever lane it ran on
+                    seg.append((st.segments, st.hits, st.misses, st.iterations))
+                if k == 4:
+                    mids.append(ctx.to_host(d_frame, (H, W, 4), np.uint8).copy())   # a read in the middle of the loop
+            st = ctx.launch_stats()
+            seg.append((st.segments, st.hits, st.misses, st.iterations))
+            results.append((ctx.to_host(d_accum, (H, W, 4), np.float32).view(np.uint32), ctx.to_host(d_frame, (H, W, 4), np.uint8), seg, mids[0],
+                            ctx.totals(reset=True)))
+        finally:
+            ctx.free(d_accum); ctx.free(d_frame)
+    ref = results[0]
+    assert ref[4]["segments"] > N * n and ref[4]["launches"] == N
+    for got in results[1:]:
+        assert np.array_equal(ref[0], got[0]) and np.array_equal(ref[1], got[1]) and np.array_equal(ref[3], got[3])
+        assert ref[2] == got[2] and ref[4] == got[4]
+    with pytest.raises(ptb.PtbError):
+        p = ptb.make_params(W, H)
+        d = ctx.alloc(n * 16)
+        try:
+            p.accum_buffer, p.handle = d, handle
+            ctx.launch(p, ptb.default_render_cfg(write_frame=0, overlap_lanes=5))
+        finally:
+            ctx.free(d)
+
+
 def test_glass_branch_parity(ptb, ctx, oh, assets):
     """HitGroupData.transparent (optixSphere.cu:803-856): exact build bit-identical to the oracle (which is pinned to the
     reference's own code by tests/golden/ref_glass_demo.npz); the fast build renders the same picture within noise."""
