@@ -50,6 +50,38 @@ PTB8_HD void load2(const float4* nodes2, int b, float lo0[3], float hi0[3], int*
     *c0 = f2i(n3.x); *c1 = f2i(n3.y);
 }
 
+// 4-wide collapse of 2-wide node `b`, greedy by surface area (bvh_build.cu: k_collapse4_level; layout of the 128-byte node in bvh.cuh).
+// Writes nodes4[b]; calls push(child) for every internal child (a 2-wide node index: where that child's 4-wide node will be stored).
+template <class Push>
+PTB8_HD void collapse4_node(const float4* nodes2, int b, float4* nodes4, Push& push) {
+    float lo[4][3], hi[4][3]; int code[4];
+    int m = 2;
+    load2(nodes2, b, lo[0], hi[0], &code[0], lo[1], hi[1], &code[1]);
+    while (m < 4) {
+        int best = -1; float best_a = -1.0f;
+        for (int k = 0; k < m; ++k) {
+            if (code[k] < 0) continue;
+            const float dx = hi[k][0] - lo[k][0], dy = hi[k][1] - lo[k][1], dz = hi[k][2] - lo[k][2];
+            const float a = dx * dy + dy * dz + dz * dx;
+            if (a > best_a) { best_a = a; best = k; }
+        }
+        if (best < 0) break;
+        const int c = code[best];
+        load2(nodes2, c, lo[best], hi[best], &code[best], lo[m], hi[m], &code[m]);
+        ++m;
+    }
+    union { uint32_t u; float f; } qn; qn.u = 0x7fc00000u;
+    for (int k = m; k < 4; ++k) { for (int d = 0; d < 3; ++d) { lo[k][d] = qn.f; hi[k][d] = qn.f; } code[k] = -1; }
+    for (int k = 0; k < m; ++k) if (code[k] >= 0) push(code[k]);
+    union { int i; float f; } c0, c1, c2, c3; c0.i = code[0]; c1.i = code[1]; c2.i = code[2]; c3.i = code[3];
+    float4* o = nodes4 + (size_t)b * 8;
+    o[0] = make_float4(lo[0][0], lo[1][0], lo[2][0], lo[3][0]); o[1] = make_float4(hi[0][0], hi[1][0], hi[2][0], hi[3][0]);
+    o[2] = make_float4(lo[0][1], lo[1][1], lo[2][1], lo[3][1]); o[3] = make_float4(hi[0][1], hi[1][1], hi[2][1], hi[3][1]);
+    o[4] = make_float4(lo[0][2], lo[1][2], lo[2][2], lo[3][2]); o[5] = make_float4(hi[0][2], hi[1][2], hi[2][2], hi[3][2]);
+    o[6] = make_float4(c0.f, c1.f, c2.f, c3.f);
+    o[7] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+}
+
 // Alloc: uint32_t nodes(uint32_t n), uint32_t tris(uint32_t n) hand out consecutive indices; void push(WorkItem) appends
 // to the next level's queue; void error(int bits).
 // Returns the number of internal children.

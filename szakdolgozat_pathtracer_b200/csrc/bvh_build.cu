@@ -392,41 +392,20 @@ __global__ void k_emit_tris(const float4* __restrict__ verts, const uint32_t* __
 // tree (>= 0: node index, < 0: leaf code).  Layout (bvh.cuh): 8 x float4 = 128 B:
 //   lo.x[4], hi.x[4], lo.y[4], hi.y[4], lo.z[4], hi.z[4], codes[4], pad; unused slots have NaN boxes (never entered).
 // Fewer DEPENDENT node fetches per ray is what pays once the tree is larger than L2.
+struct Push4 {   // internal children of one 4-wide node: up to four entries, appended to the next level's queue in one piece
+    int c[4]; int n = 0;
+    __device__ void operator()(int child) { c[n++] = child; }
+};
 __global__ void k_collapse4_level(const float4* __restrict__ nodes2, const int* __restrict__ in, unsigned int n_in, int* __restrict__ out,
                                   unsigned int* __restrict__ out_count, float4* __restrict__ nodes4) {
     const unsigned int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= n_in) return;
-    const int i = in[w];
-    const float qnan = __int_as_float(0x7fc00000);
-    float lo[4][3], hi[4][3]; int code[4];
-    int m = 2;
-    ptb8::load2(nodes2, i, lo[0], hi[0], &code[0], lo[1], hi[1], &code[1]);
-    while (m < 4) {
-        int best = -1; float best_a = -1.0f;
-        for (int k = 0; k < m; ++k) {
-            if (code[k] < 0) continue;
-            const float dx = hi[k][0] - lo[k][0], dy = hi[k][1] - lo[k][1], dz = hi[k][2] - lo[k][2];
-            const float a = dx * dy + dy * dz + dz * dx;
-            if (a > best_a) { best_a = a; best = k; }
-        }
-        if (best < 0) break;
-        const int c = code[best];
-        ptb8::load2(nodes2, c, lo[best], hi[best], &code[best], lo[m], hi[m], &code[m]);
-        ++m;
+    Push4 push;
+    ptb8::collapse4_node(nodes2, in[w], nodes4, push);
+    if (push.n) {
+        unsigned int at = atomicAdd(out_count, (unsigned int)push.n);
+        for (int k = 0; k < push.n; ++k) out[at++] = push.c[k];
     }
-    for (int k = m; k < 4; ++k) { for (int d = 0; d < 3; ++d) { lo[k][d] = qnan; hi[k][d] = qnan; } code[k] = -1; }
-    unsigned int n_int = 0;
-    for (int k = 0; k < m; ++k) n_int += code[k] >= 0 ? 1u : 0u;
-    if (n_int) {
-        unsigned int at = atomicAdd(out_count, n_int);
-        for (int k = 0; k < m; ++k) if (code[k] >= 0) out[at++] = code[k];
-    }
-    float4* o = nodes4 + (size_t)i * 8;
-    o[0] = make_float4(lo[0][0], lo[1][0], lo[2][0], lo[3][0]); o[1] = make_float4(hi[0][0], hi[1][0], hi[2][0], hi[3][0]);
-    o[2] = make_float4(lo[0][1], lo[1][1], lo[2][1], lo[3][1]); o[3] = make_float4(hi[0][1], hi[1][1], hi[2][1], hi[3][1]);
-    o[4] = make_float4(lo[0][2], lo[1][2], lo[2][2], lo[3][2]); o[5] = make_float4(hi[0][2], hi[1][2], hi[2][2], hi[3][2]);
-    o[6] = make_float4(__int_as_float(code[0]), __int_as_float(code[1]), __int_as_float(code[2]), __int_as_float(code[3]));
-    o[7] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 }
 
 // ---- 8-wide quantised collapse (bvh8.cuh) -----------------------------------------------------------------------------

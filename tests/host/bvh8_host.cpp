@@ -1,5 +1,5 @@
-// bvh8_host.cpp -- CPU harness for the 8-wide quantised BVH: the collapse (csrc/bvh8.cuh) and the traversals
-// (csrc/bvh.cuh: trav_run, trav_run4 is not built here, trav_run8) compiled for the host through cuda_host_shim.h and
+// bvh8_host.cpp -- CPU harness for the wide BVHs: the 4-wide and the 8-wide quantised collapse (csrc/bvh8.cuh) and the traversals
+// (csrc/bvh.cuh: trav_run, trav_run4, trav_run8) compiled for the host through cuda_host_shim.h and
 // checked against a brute-force loop over all triangles with the same watertight test and tie rule.
 // Test infrastructure (run by tests/test_bvh8_host.py); the 2-wide input tree is a median-split tree built here in the
 // library's node format.
@@ -149,11 +149,26 @@ int main(int argc, char** argv) {
     { std::vector<int> seen(tris2.size() / 3, 0);
       for (size_t i = 0; i < tris8.size() / 3; ++i) { const int id = __float_as_int(tris8[i * 3].w); if (id < 0 || id >= (int)seen.size() || seen[id]++) { printf("FAIL: triangle order\n"); return 1; } } }
 
+    // ---- and into the 4-wide tree (greedy by surface area), level by level
+    std::vector<float4> nodes4(n_nodes2 * 8);
+    size_t n_nodes4 = 0; int levels4 = 0;
+    {
+        struct HostPush { std::vector<int>* q; void operator()(int c) { q->push_back(c); } };
+        std::vector<int> cur4(1, 0), next4;
+        while (!cur4.empty()) {
+            next4.clear();
+            HostPush hp{&next4};
+            for (int b : cur4) ptb8::collapse4_node(B.nodes.data(), b, nodes4.data(), hp);
+            n_nodes4 += cur4.size(); cur4 = next4; ++levels4;
+        }
+    }
+
     ptbv::SceneView sv; memset(&sv, 0, sizeof(sv));
     sv.nodes = B.nodes.data(); sv.tris = tris2.data(); sv.nodes8 = nodes8.data(); sv.tris8 = tris8.data();
     ptbv::SceneView sv2 = sv; sv2.nodes8 = nullptr;
+    ptbv::SceneView sv4 = sv2; sv4.nodes4 = nodes4.data();
 
-    unsigned long long n2 = 0, t2 = 0, n8 = 0, t8 = 0; int bad = 0, hits = 0;
+    unsigned long long n2 = 0, t2 = 0, n8 = 0, t8 = 0, n4 = 0, t4 = 0; int bad = 0, hits = 0;
     unsigned long long kn2[16] = {0}, kn8[16] = {0}, kt2[16] = {0}, kt8[16] = {0}; int kc[16] = {0};
     for (int r = 0; r < n_rays; ++r) {
         float3 o = mk3(60.0f * U(rng), 8.0f * U(rng) + 6.0f, 60.0f * U(rng));
@@ -176,6 +191,9 @@ int main(int argc, char** argv) {
         TravCounters c2 = {0, 0}, c8 = {0, 0}, c8q = {0, 0};
         const HitRec h2 = bvh_closest_hit<true>(sv2, o, d, tmin, tmax, &c2);
         const HitRec h8 = bvh_closest_hit<true>(sv, o, d, tmin, tmax, &c8);
+        TravCounters c4 = {0, 0};
+        const HitRec h4 = bvh_closest_hit<true>(sv4, o, d, tmin, tmax, &c4);
+        n4 += c4.nodes; t4 += c4.tris;
         // the same ray in quanta of 8 steps, as the wavefront kernels run it
         __attribute__((aligned(16))) int stack[PTB_BVH_STACK];
         Trav t;
@@ -185,15 +203,15 @@ int main(int argc, char** argv) {
         n2 += c2.nodes; t2 += c2.tris; n8 += c8.nodes; t8 += c8.tris;
         kn2[kind] += c2.nodes; kn8[kind] += c8.nodes; kt2[kind] += c2.tris; kt8[kind] += c8.tris; kc[kind]++;
         hits += hb.prim >= 0;
-        if (!same(hb, h2) || !same(hb, h8) || !same(hb, t.best) || c8q.nodes != c8.nodes || c8q.tris != c8.tris) {
+        if (!same(hb, h2) || !same(hb, h8) || !same(hb, h4) || !same(hb, t.best) || c8q.nodes != c8.nodes || c8q.tris != c8.tris) {
             if (bad < 10) printf("MISMATCH ray %d kind %d: brute prim %d t %.9g | 2-wide %d %.9g | 8-wide %d %.9g | quanta %d %.9g (nodes %u/%u)\n", r, kind, hb.prim, hb.t,
                                  h2.prim, h2.t, h8.prim, h8.t, t.best.prim, t.best.t, c8q.nodes, c8.nodes);
             ++bad;
         }
     }
     printf("triangles %zu  nodes2 %zu  nodes8 %u  levels %d  slots used per node %.2f\n", tris2.size() / 3, n_nodes2, al.n_nodes, levels, (double)slots_used / al.n_nodes);
-    printf("rays %d  hits %d  per ray: 2-wide %.2f nodes %.2f tris | 8-wide %.2f nodes %.2f tris\n", n_rays, hits, (double)n2 / n_rays, (double)t2 / n_rays,
-           (double)n8 / n_rays, (double)t8 / n_rays);
+    printf("rays %d  hits %d  per ray: 2-wide %.2f nodes %.2f tris | 4-wide (%zu nodes, %d levels) %.2f nodes %.2f tris | 8-wide %.2f nodes %.2f tris\n", n_rays, hits,
+           (double)n2 / n_rays, (double)t2 / n_rays, n_nodes4, levels4, (double)n4 / n_rays, (double)t4 / n_rays, (double)n8 / n_rays, (double)t8 / n_rays);
     for (int k = 0; k < 8; ++k) if (kc[k]) printf("  ray kind %d: 2-wide %.1f nodes %.1f tris | 8-wide %.1f nodes %.1f tris\n", k, (double)kn2[k] / kc[k], (double)kt2[k] / kc[k], (double)kn8[k] / kc[k], (double)kt8[k] / kc[k]);
     if (bad) { printf("FAIL: %d mismatches\n", bad); return 1; }
     printf("OK\n");
