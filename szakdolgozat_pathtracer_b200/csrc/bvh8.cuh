@@ -19,8 +19,9 @@
 //   Slots are assigned by octant affinity (slot bit set on an axis <=> the child lies towards + on that axis), so that the
 //   traversal can order the children a ray hits by (slot ^ ray octant) instead of sorting distances.
 //
-// collapse8_node is plain C++ (host + device): the build kernel (bvh_build.cu: k_collapse8_level) and the CPU test
-// harness (tests/host/bvh8_host.cpp) run the same code.
+// collapse8_node and collapse4_node (the greedy 4-wide collapse, uncompressed 128-byte nodes of bvh.cuh) are plain C++
+// (host + device): the build kernels (bvh_build.cu: k_collapse8_level, k_collapse4_level) and the CPU test harness
+// (tests/host/bvh8_host.cpp) run the same code.
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>

@@ -1,7 +1,7 @@
-"""The 8-wide quantised BVH on the CPU: the collapse (csrc/bvh8.cuh) and the traversal code (csrc/bvh.cuh) are compiled for the
-host (tests/host/cuda_host_shim.h stands in for the device intrinsics) and checked against a brute-force loop over all
-triangles: hit, t and barycentrics bit-identical for random, axis-parallel, grazing, far-away and surface-start rays; the
-2-wide traversal of the same tree and the 8-wide traversal run in quanta of 8 steps agree as well."""
+"""The wide BVHs on the CPU: the greedy 4-wide collapse, the 8-wide quantised collapse (csrc/bvh8.cuh) and the traversal code
+(csrc/bvh.cuh: trav_run, trav_run4, trav_run8) are compiled for the host (tests/host/cuda_host_shim.h stands in for the device
+intrinsics) and checked against a brute-force loop over all triangles: hit, t and barycentrics bit-identical for random,
+axis-parallel, grazing, far-away and surface-start rays; the 8-wide traversal run in quanta of 8 steps agrees as well."""
 import subprocess
 from pathlib import Path
 
