@@ -446,7 +446,7 @@ def run_config(args, config_name, brief, torch, dist, ptb, parallel, make_assets
         "kernel": kernel, "arith": arith,
         "bound": "latency/issue",
         "bound_note": "no memory level is near its peak (see dram_frac, l2_frac): the kernel is bound by instruction issue and dependent-load latency "
-                      "at 8 warps per scheduler; `frac` below is ALGORITHMIC bytes over the HBM copy peak (SURVEY.md section 8d) -- most of those bytes "
+                      "at 8-9 warps per scheduler; `frac` below is ALGORITHMIC bytes over the HBM copy peak (SURVEY.md section 8d) -- most of those bytes "
                       "are served by L1/L2, so it is not an HBM utilisation",
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
         "traffic": traffic,
