@@ -169,7 +169,7 @@ typedef struct ptb_render_cfg {
     int32_t overlap_lanes;    /* consecutive SMALL launches (the reference's render loop issues one subframe of 600x400 .. 1600x1200
                                  pixels per optixLaunch, optixSphere.cpp:1390-1437) end in a long thin tail: every pixel's samples
                                  are one sequential chain.  0 (default) = automatic: in the reference's accumulate mode (accumulate_mode
-                                 0) a single-subframe launch of the default pipeline with fewer than 9 M path slots renders on one
+                                 0) a launch of the default pipeline with fewer than 9 M path slots (subframes x pixels) renders on one
                                  of 4 internal streams with its own path pool, so that the tail of launch k overlaps the start of
                                  launch k + 1 (600x400: 2.15 -> 0.73 ms per launch); the accumulate / tonemap stage stays on the
                                  caller's stream, in call order -- buffers and results are exactly those of serial launches.

@@ -511,7 +511,7 @@ int ptb_launch(ptb_context* ctx, const ptb_Params* P, const ptb_render_cfg* cfg_
     const uint32_t pool_grid = pool_blocks_needed < pool_cap ? pool_blocks_needed : pool_cap;
     const bool use_pool = pipeline == PTB_PIPELINE_POOL_FUSED;
 
-    // Launch overlap (ptb_render_cfg.overlap_lanes): a small single-subframe launch renders on one of the context's internal
+    // Launch overlap (ptb_render_cfg.overlap_lanes): a small launch (fewer than 9 M path slots) renders on one of the context's internal
     // streams with that lane's own path pool, so that its thin tail (every pixel's samples are one sequential chain) runs beside
     // the start of the next launch; accumulate / tonemap (k_resolve) and the counter fold stay on the caller's stream in call
     // order.  Same kernels, same buffers, same results.
@@ -519,7 +519,7 @@ int ptb_launch(ptb_context* ctx, const ptb_Params* P, const ptb_render_cfg* cfg_
     // keeps serial launches unless the caller asks for lanes
     const int n_lanes = cfg.overlap_lanes == 0 ? (cfg.accumulate_mode == 0 ? 4 : 1) : cfg.overlap_lanes;
     if (n_lanes < 1 || n_lanes > 4) return fail(PTB_ERR_INVALID, "ptb_launch: overlap_lanes must be 0 (automatic), 1 (off), 2, 3 or 4");
-    bool overlap = n_lanes > 1 && pipeline == PTB_PIPELINE_CHUNK_FUSED && n_sub == 1 && slots < 9000000u && !cfg.profile_stages &&
+    bool overlap = n_lanes > 1 && pipeline == PTB_PIPELINE_CHUNK_FUSED && slots < 9000000u && !cfg.profile_stages &&
                    !cfg.count_traversal && !cfg.aux_primary_hit && !cfg.env_importance_sampling && !ctx->keep_launch_totals && !ctx->defer_fold;
     if (overlap) {
         cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;

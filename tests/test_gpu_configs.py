@@ -176,8 +176,8 @@ def test_bounded_pool_batches_bit_identical(ptb, ctx, assets):
     assert res[0][3][3] == n * 3 * 7 and res[0][3][0] > res[0][3][3]
 
 
-@pytest.mark.parametrize("arith", [0, 1], ids=["exact", "fast"])
-def test_overlapped_launches_equal_serial_launches(ptb, ctx, assets, arith):
+@pytest.mark.parametrize("arith,batch", [(0, 1), (1, 1), (0, 3)], ids=["exact", "fast", "exact-batched"])
+def test_overlapped_launches_equal_serial_launches(ptb, ctx, assets, arith, batch):
     """ptb_render_cfg.overlap_lanes: the reference's render loop (one subframe per launch, running average, tonemapped frame,
     optixSphere.cpp:1390-1437) with launches overlapping on the context's internal lanes (0 = automatic, 2, 4) against strictly
     serial launches (1): accumulation buffer, frame, per-launch statistics and context totals identical; also when the caller
@@ -193,10 +193,10 @@ def test_overlapped_launches_equal_serial_launches(ptb, ctx, assets, arith):
         try:
             ctx.memset(d_accum, 0, n * 16)
             ctx.totals(reset=True)
-            cfg = ptb.default_render_cfg(spp_per_launch=3, max_depth=6, arith_mode=arith, overlap_lanes=lanes)
+            cfg = ptb.default_render_cfg(spp_per_launch=3, max_depth=6, arith_mode=arith, overlap_lanes=lanes, subframes_per_launch=batch)
             seg, mids = [], []
             for k in range(N):
-                p = ptb.make_params(W, H, subframe_index=k, dof=True, **CAMERAS["monkey_close"])
+                p = ptb.make_params(W, H, subframe_index=k * batch, dof=True, **CAMERAS["monkey_close"])
                 p.accum_buffer, p.frame_buffer, p.handle = d_accum, d_frame, handle
                 ctx.launch(p, cfg)
                 if k in (2, 5):
