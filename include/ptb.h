@@ -173,7 +173,8 @@ typedef struct ptb_render_cfg {
                                  of 4 internal streams with its own path pool, so that the tail of launch k overlaps the start of
                                  launch k + 1 (600x400: 2.15 -> 0.73 ms per launch); the accumulate / tonemap stage stays on the
                                  caller's stream, in call order -- buffers and results are exactly those of serial launches.
-                                 1 = off; 2..4 = that many lanes (any accumulate mode).  The render of such a launch does not wait for
+                                 1 = off; 2..4 = that many lanes (any accumulate mode).  Every lane in use owns a path pool of
+                                 the launch's size (97 B per slot: 4 x 23 MB at 600x400, 4 x 186 MB at 1600x1200).  The render of such a launch does not wait for
                                  work the caller enqueued on `stream` before the call (only the accumulate stage does); launches
                                  with aux_primary_hit, counters, stage profiling or stream capture never overlap. */
     int32_t reserved0;
