@@ -78,7 +78,7 @@ class ClockSampler:
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, gpu_index):
-        self.gpu, self.lines, self.proc = gpu_index, [], None
+        self.gpu, self.lines, self.proc, self.first = gpu_index, [], None, 0
 
     def start(self):
         try:
@@ -92,12 +92,25 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def wait_running(self, timeout=3.0):
+        """Blocks until nvidia-smi has printed its first sample (its start-up can take longer than a short timed region)."""
+        t0 = time.time()
+        while self.proc and not self.lines and time.time() - t0 < timeout:
+            time.sleep(0.01)
+
+    def mark(self):
+        """Samples from here on belong to the timed region."""
+        self.first = len(self.lines)
+
     def stop(self):
         if self.proc:
-            time.sleep(0.25)
+            time.sleep(0.12)
             self.proc.terminate()
+        # the samples taken inside the timed region; a region shorter than the sampling period falls back to the samples taken
+        # under the same load during the warm-up steps
+        lines = self.lines[self.first:] if len(self.lines) > self.first else self.lines[-4:]
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        for ln in lines:
             parts = [x.strip() for x in ln.split(",")]
             if len(parts) < 8:
                 continue
@@ -317,15 +330,18 @@ def run_config(args, config_name, brief, torch, dist, ptb, parallel, make_assets
 
     def timed(cfg_used, frame_subframes, steps, warmup, tiled=False, sample_clocks=False):
         """W warm-up steps, then K steps between CUDA events on the launch stream; max over ranks; device-counted segments."""
+        sampler = ClockSampler(local_rank) if (sample_clocks and rank == 0) else None
+        if sampler:
+            sampler.start()          # before the warm-up: nvidia-smi is up and sampling by the time the timed region starts
+            sampler.wait_running()
         for _ in range(warmup):
             one_step(cfg_used, frame_subframes, tiled)
         sync_all()
         ctx.totals(reset=True)
-        sampler = ClockSampler(local_rank) if (sample_clocks and rank == 0) else None
-        if sampler:
-            sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         sync_all()
+        if sampler:
+            sampler.mark()
         e0.record()
         for _ in range(steps):
             one_step(cfg_used, frame_subframes, tiled)

@@ -362,20 +362,8 @@ PTB_DEV void closest_hit(const SceneView& s, const FrameView& f, int prim_idx, f
     // getPayloadCH (cu:160-172): radiance/origin/direction/done restart from zero
     io.radiance = mk3(0.0f); io.origin = mk3(0.0f); io.direction = mk3(0.0f); io.done = 0;
 
-    const float3 n0 = mk3(__ldg(s.normals + vo)), n1 = mk3(__ldg(s.normals + vo + 1)), n2 = mk3(__ldg(s.normals + vo + 2));
     const float bary_beta = b1, bary_gamma = b2;
     const float bary_alpha = 1.0f - bary_beta - bary_gamma;
-    float3 normal = bary_alpha * n0 + bary_beta * n1 + bary_gamma * n2;
-    if (length(normal) > 0.01f) normal = normalize(normal);
-    else { io.done = 1; return; }
-    if (dot(normal, ray_dir) > 0.0f) {
-        // the flat normal (cu:631-638) is only ever used here, so the three vertex fetches and its normalisation are done
-        // for the few hits whose shading normal faces away from the ray, not for all of them (same value either way)
-        const float3 v0 = mk3(__ldg(s.verts + vo)), v1 = mk3(__ldg(s.verts + vo + 1)), v2 = mk3(__ldg(s.verts + vo + 2));
-        const float3 flat_normal = normalize(cross(v1 - v0, v2 - v0));
-        normal = faceforward(flat_normal, -ray_dir, flat_normal);
-    }
-
     const float3 hit_pos = ray_orig + t_hit * ray_dir;
     if (EARLY) stp(early_origin, make_float4(hit_pos.x, hit_pos.y, hit_pos.z, 0.0f));
     uint32_t seed = io.seed;
@@ -405,6 +393,18 @@ PTB_DEV void closest_hit(const SceneView& s, const FrameView& f, int prim_idx, f
         else if (k == 2) normal_map = mk3(c);
         else metallicity = c.x;
     }
+    const float3 n0 = mk3(__ldg(s.normals + vo)), n1 = mk3(__ldg(s.normals + vo + 1)), n2 = mk3(__ldg(s.normals + vo + 2));
+    float3 normal = bary_alpha * n0 + bary_beta * n1 + bary_gamma * n2;
+    if (length(normal) > 0.01f) normal = normalize(normal);
+    else { io.done = 1; return; }
+    if (dot(normal, ray_dir) > 0.0f) {
+        // the flat normal (cu:631-638) is only ever used here, so the three vertex fetches and its normalisation are done
+        // for the few hits whose shading normal faces away from the ray, not for all of them (same value either way)
+        const float3 v0 = mk3(__ldg(s.verts + vo)), v1 = mk3(__ldg(s.verts + vo + 1)), v2 = mk3(__ldg(s.verts + vo + 2));
+        const float3 flat_normal = normalize(cross(v1 - v0, v2 - v0));
+        normal = faceforward(flat_normal, -ray_dir, flat_normal);
+    }
+
     if (m.tex[2].fmt != 0) {
         normal_map = normalize(2.0f * normal_map - mk3(1.0f));
         normal_map = mk3(normal_map.x, normal_map.z, normal_map.y);
